@@ -1,0 +1,138 @@
+/*
+ * s3d_b200.h — C-ABI of the B200-native scan-matching path behind slam3d::PointCloudSensor.
+ *
+ * This is the drop-in boundary: the two call sites in the reference that do all the
+ * arithmetic — PointCloudSensor::downsample (slam3d/sensor/pcl/PointCloudSensor.cpp:190-201) and the
+ * free function align() (PointCloudSensor.cpp:119-174, which calls doICP<> :52-82) — are replaced by
+ * s3d_voxel_downsample() and s3d_gicp_align().  Everything above (createConstraint :269-299,
+ * ScanSensor::addMeasurement / link, the graph, the g2o solver) stays host code and is untouched.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all pointers are caller-owned and only read/written during the call;
+ *   - point clouds are arrays of 16-byte points {x,y,z,w} == pcl::PointXYZ memory
+ *     (PointCloudSensor.hpp:43-44); `w` is ignored on input and written as 1.0f on output;
+ *   - cloud pointers may be HOST or DEVICE pointers (the library asks cudaPointerGetAttributes);
+ *     result structs and 4x4 poses are always host memory;
+ *   - 4x4 poses are column-major doubles == Eigen::Isometry3d::matrix().data() (core/Types.hpp:53);
+ *   - every entry point is re-entrant (ScanSensor.cpp:209-210 enters createConstraint from two threads);
+ *   - functions return an s3d_status; they never throw across the boundary.  s3d_last_error() returns a
+ *     thread-local message for the last non-OK return on the calling thread.
+ */
+#ifndef S3D_B200_H
+#define S3D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes.  1..4 map 1:1 on the exceptions thrown by the reference's align()/doICP()
+ * (SURVEY.md §8b "Error convention"); the C++ host mirror re-throws the reference's exception types. */
+typedef enum s3d_status {
+  S3D_OK = 0,
+  S3D_TOO_FEW_POINTS = 1,      /* NoMatch  "Too few points after filtering..."   PointCloudSensor.cpp:134-135 */
+  S3D_NOT_CONVERGED = 2,       /* NoMatch  "ICP failed with Fitness-Score..."    PointCloudSensor.cpp:74-77   */
+  S3D_TOO_FAR_FROM_GUESS = 3,  /* NoMatch  "ICP result is to far away from guess" PointCloudSensor.cpp:167-172 */
+  S3D_UNKNOWN_ALGORITHM = 4,   /* std::runtime_error                              PointCloudSensor.cpp:158-164 */
+  S3D_INTERNAL_ERROR = 5,      /* CUDA failure, bad argument, workspace problem   (std::runtime_error in the mirror) */
+  S3D_INVALID_ARGUMENT = 6
+} s3d_status;
+
+/* enum RegistrationAlgorithm {ICP, GICP, GICP_OMP, NDT, NDT_OMP}  — RegistrationParameters.hpp:30 */
+enum { S3D_ALG_ICP = 0, S3D_ALG_GICP = 1, S3D_ALG_GICP_OMP = 2, S3D_ALG_NDT = 3, S3D_ALG_NDT_OMP = 4 };
+
+/* Field-for-field mirror of slam3d::RegistrationParameters (RegistrationParameters.hpp:36-97),
+ * same order, same defaults (see s3d_default_parameters). */
+typedef struct s3d_registration_parameters {
+  int32_t registration_algorithm;      /* GICP */
+  double  point_cloud_density;         /* 0.2   voxel leaf applied to both clouds before matching; <=0: none */
+  double  max_fitness_score;           /* 2.0   */
+  double  max_translation;             /* 1.0   */
+  double  max_rotation;                /* 1.0   */
+  double  euclidean_fitness_epsilon;   /* 1.0   stored, never read by GICP (SURVEY A.4 note) */
+  double  transformation_epsilon;      /* 1e-5  */
+  double  max_correspondence_distance; /* 2.5   */
+  int32_t maximum_iterations;          /* 50    */
+  double  rotation_epsilon;            /* 2e-3  */
+  int32_t correspondence_randomness;   /* 20    k of the covariance kNN */
+  int32_t maximum_optimizer_iterations;/* 20    */
+  float   resolution;                  /* 1.0   NDT only */
+  double  step_size;                   /* 0.05  NDT only */
+  double  outlier_ratio;               /* 0.35  NDT only */
+} s3d_registration_parameters;
+
+typedef struct s3d_cloud {
+  const float* xyzw; /* n * 4 floats, 16-byte aligned; host or device pointer */
+  uint64_t     n;
+} s3d_cloud;
+
+/* Output of one align().  T is the pose of the *target* scan in the *source* scan's frame, i.e. what the
+ * reference's align() returns (the PCL source/target swap of PointCloudSensor.cpp:68-69 is done inside). */
+typedef struct s3d_result {
+  double   T[16];            /* column-major 4x4; valid whenever the GICP loop ran (status 0,2,3) */
+  double   fitness;          /* pcl getFitnessScore(max_correspondence_distance)  :73 */
+  int32_t  status;           /* s3d_status */
+  int32_t  converged;        /* pcl hasConverged() */
+  int32_t  outer_iterations; /* pcl nr_iterations_ */
+  int32_t  inner_iterations; /* total optimiser iterations over all outer iterations */
+  uint32_t n_source;         /* points of the (filtered) slam3d source cloud = PCL target */
+  uint32_t n_target;         /* points of the (filtered) slam3d target cloud = PCL source (the queries) */
+  uint32_t n_correspondences;/* pairs within max_correspondence_distance in the last outer iteration */
+  uint32_t reserved;
+} s3d_result;
+
+typedef struct s3d_context s3d_context;
+
+/* Library / device bring-up.  `devices` = CUDA ordinals to shard batches over (NULL/0: current device). */
+int s3d_create_context(const int* devices, int n_devices, s3d_context** out);
+int s3d_destroy_context(s3d_context* ctx);
+
+void        s3d_default_parameters(s3d_registration_parameters* p); /* RegistrationParameters.hpp defaults */
+const char* s3d_last_error(void);
+const char* s3d_version(void);
+
+/* PointCloudSensor::downsample(cloud, leaf)  — PointCloudSensor.cpp:190-201 (pcl::VoxelGrid semantics,
+ * SURVEY Appendix A.1).  out_xyzw must hold in.n points (host or device).  *n_out receives the number of
+ * output points.  If leaf_index (host or device, in.n x uint32, may be NULL) is given it receives the
+ * voxel index of every input point (the "leaf assignment"; 0xFFFFFFFF for skipped non-finite points).
+ * overflow (may be NULL) is set to 1 when PCL's int32 index guard fires and the input is returned as is. */
+int s3d_voxel_downsample(s3d_context* ctx, s3d_cloud in, float leaf, float* out_xyzw, uint64_t* n_out,
+                         uint32_t* leaf_index, int32_t* overflow);
+
+/* align(source, target, guess, config) — PointCloudSensor.cpp:119-174.  Always fills *out (status inside
+ * is the same value as the return code). */
+int s3d_gicp_align(s3d_context* ctx, s3d_cloud source, s3d_cloud target, const double guess[16],
+                   const s3d_registration_parameters* params, s3d_result* out);
+
+/* n_pairs independent align() calls (loop-closure candidates, odometry pairs), sharded over the context's
+ * devices.  guesses = n_pairs x 16 doubles.  Returns S3D_OK if the batch ran; per-pair status is in out[i]. */
+int s3d_gicp_align_batch(s3d_context* ctx, const s3d_cloud* sources, const s3d_cloud* targets,
+                         const double* guesses, const s3d_registration_parameters* params, int n_pairs,
+                         s3d_result* out);
+
+/* ---- stage-level entry points (used by the parity tests and the bench; same kernels as align) ---------- */
+
+/* GICP computeCovariances: exact kNN (k neighbours, self included, ascending (d2, index)),
+ * moments, regularised covariance.  Outputs are optional (NULL to skip), host or device:
+ *   knn_index  n*k uint32 (original indices), knn_dist2 n*k float, covariances n*9 doubles (column-major 3x3). */
+int s3d_knn_covariances(s3d_context* ctx, s3d_cloud cloud, int k, uint32_t* knn_index, float* knn_dist2,
+                        double* covariances);
+
+/* Exact 1-NN of T_f32*query[i] in `reference`: nn_index n uint32, nn_dist2 n float.
+ * transform = column-major 4x4 (cast to float and applied as in the GICP loop); NULL = identity. */
+int s3d_nearest_neighbors(s3d_context* ctx, s3d_cloud reference, s3d_cloud queries, const double* transform,
+                          uint32_t* nn_index, float* nn_dist2);
+
+/* The CUDA stream (cudaStream_t) the context launches on for device slot `device_slot`; lets a caller
+ * bracket calls with events on the right stream.  Returns NULL on a bad slot. */
+void* s3d_context_stream(s3d_context* ctx, int device_slot);
+
+/* Counters since context creation: kernel launches issued by this library, bytes copied H2D / D2H. */
+typedef struct s3d_counters { uint64_t kernel_launches, h2d_bytes, d2h_bytes; } s3d_counters;
+int s3d_get_counters(s3d_context* ctx, s3d_counters* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S3D_B200_H */

@@ -1,0 +1,141 @@
+"""Python loader of the CPU oracle (oracle/s3d_oracle.cpp).
+
+TEST INFRASTRUCTURE: may be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs only.  The product package slam3d_b200 never imports this module.
+PARITY UNPINNED: see the header of s3d_oracle.cpp.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from slam3d_b200._abi import Cloud, RegistrationParameters, Result
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libs3d_oracle.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "s3d_oracle.cpp")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.s3d_oracle_last_error.restype = C.c_char_p
+    return _lib
+
+
+def _cloud(a):
+    a = as_xyzw(a)
+    return a, Cloud(a.ctypes.data, a.shape[0])
+
+
+def as_xyzw(a):
+    """(n,3) or (n,4) array -> C-contiguous float32 (n,4) with w = 1 (pcl::PointXYZ memory)."""
+    a = np.asarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] not in (3, 4):
+        raise ValueError("cloud must be (n,3) or (n,4)")
+    if a.shape[1] == 3:
+        out = np.ones((a.shape[0], 4), np.float32)
+        out[:, :3] = a
+        return out
+    return np.ascontiguousarray(a)
+
+
+def voxel_downsample(cloud, leaf):
+    a, c = _cloud(cloud)
+    out = np.empty((max(a.shape[0], 1), 4), np.float32)
+    leaf_index = np.empty(max(a.shape[0], 1), np.uint32)
+    n_out = C.c_uint64(0)
+    overflow = C.c_int32(0)
+    lib().s3d_oracle_voxel_downsample(c, C.c_float(leaf), out.ctypes.data_as(C.c_void_p), C.byref(n_out),
+                                      leaf_index.ctypes.data_as(C.c_void_p), C.byref(overflow))
+    return out[: n_out.value].copy(), leaf_index[: a.shape[0]].copy(), bool(overflow.value)
+
+
+def knn_covariances(cloud, k):
+    a, c = _cloud(cloud)
+    n = a.shape[0]
+    idx = np.empty((n, k), np.uint32)
+    d2 = np.empty((n, k), np.float32)
+    cov = np.empty((n, 9), np.float64)
+    st = lib().s3d_oracle_knn_covariances(c, k, idx.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p),
+                                          cov.ctypes.data_as(C.c_void_p))
+    if st != 0:
+        raise RuntimeError(lib().s3d_oracle_last_error().decode())
+    return idx, d2, cov.reshape(n, 3, 3).transpose(0, 2, 1).copy()  # column-major -> [row, col]
+
+
+def knn_bruteforce(reference, queries, k):
+    r, rc = _cloud(reference)
+    q, qc = _cloud(queries)
+    idx = np.empty((q.shape[0], k), np.uint32)
+    d2 = np.empty((q.shape[0], k), np.float32)
+    st = lib().s3d_oracle_knn_bruteforce(rc, qc, k, idx.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p))
+    if st != 0:
+        raise RuntimeError("knn_bruteforce failed")
+    return idx, d2
+
+
+def nearest_neighbors(reference, queries, transform=None):
+    r, rc = _cloud(reference)
+    q, qc = _cloud(queries)
+    idx = np.empty(q.shape[0], np.uint32)
+    d2 = np.empty(q.shape[0], np.float32)
+    tp = None
+    if transform is not None:
+        t = np.ascontiguousarray(np.asarray(transform, np.float64).T)  # -> column-major
+        tp = t.ctypes.data_as(C.c_void_p)
+    st = lib().s3d_oracle_nearest_neighbors(rc, qc, tp, idx.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p))
+    if st != 0:
+        raise RuntimeError("nearest_neighbors failed")
+    return idx, d2
+
+
+def _guess_ptr(guess):
+    g = np.eye(4) if guess is None else np.asarray(guess, np.float64)
+    return np.ascontiguousarray(g.T)  # column-major
+
+
+def gicp_align(source, target, guess=None, params=None):
+    """slam3d align(source, target, guess, config) on the CPU oracle. Returns slam3d_b200._abi.Result."""
+    s, sc = _cloud(source)
+    t, tc = _cloud(target)
+    g = _guess_ptr(guess)
+    p = params if params is not None else RegistrationParameters.defaults()
+    res = Result()
+    lib().s3d_oracle_gicp_align(sc, tc, g.ctypes.data_as(C.c_void_p), C.byref(p), C.byref(res))
+    return res
+
+
+def gicp_align_batch(sources, targets, guesses=None, params=None, n_threads=0):
+    n = len(sources)
+    keep = []
+    sc = (Cloud * n)()
+    tc = (Cloud * n)()
+    for i in range(n):
+        a, c = _cloud(sources[i]); keep.append(a); sc[i] = c
+        a, c = _cloud(targets[i]); keep.append(a); tc[i] = c
+    g = np.stack([_guess_ptr(None if guesses is None else guesses[i]) for i in range(n)])
+    g = np.ascontiguousarray(g)
+    p = params if params is not None else RegistrationParameters.defaults()
+    res = (Result * n)()
+    lib().s3d_oracle_gicp_align_batch(sc, tc, g.ctypes.data_as(C.c_void_p), C.byref(p), n, n_threads, res)
+    return list(res)
+
+
+def max_threads():
+    return lib().s3d_oracle_max_threads()
+
+
+def last_error():
+    return lib().s3d_oracle_last_error().decode()
