@@ -888,6 +888,27 @@ int s3d_oracle_test_objective(const float* pts_moved, const float* pts_fixed, co
   return S3D_OK;
 }
 
+// Test hook: estimateRigidTransformationNewton on explicit correspondences. T: column-major float 4x4 in/out.
+int s3d_oracle_test_newton(const float* pts_moved, const float* pts_fixed, const double* mahal, int m, float T[16],
+                           int max_inner, int* inner_done) {
+  std::vector<P4> a(reinterpret_cast<const P4*>(pts_moved), reinterpret_cast<const P4*>(pts_moved) + m);
+  std::vector<P4> b(reinterpret_cast<const P4*>(pts_fixed), reinterpret_cast<const P4*>(pts_fixed) + m);
+  GicpProblem P;
+  P.moved = &a; P.fixed = &b;
+  P.mahalanobis.resize(m);
+  for (int i = 0; i < m; ++i) {
+    P.src_idx.push_back(i); P.tgt_idx.push_back(i);
+    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) P.mahalanobis[i].a[r][c] = mahal[i * 9 + c * 3 + r];
+  }
+  M4f Tm;
+  std::memcpy(Tm.m, T, sizeof Tm.m);
+  int done = 0;
+  const bool ok = gicp_newton(P, Tm, max_inner, &done);
+  std::memcpy(T, Tm.m, sizeof Tm.m);
+  if (inner_done) *inner_done = done;
+  return ok ? S3D_OK : S3D_NOT_CONVERGED;
+}
+
 int s3d_oracle_test_eigen3(const double A[9], double V[9], double w[3]) {
   double a[3][3], v[3][3];
   for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) a[r][c] = A[c * 3 + r];

@@ -1,0 +1,175 @@
+"""slam3d_b200 — B200-native (sm_100a) scan matching behind slam3d::PointCloudSensor.
+
+This package is a thin ctypes layer over libs3d_b200.so (hand-written CUDA, C-ABI in include/s3d_b200.h).
+There is NO CPU fallback and the package never imports the test oracle: if the CUDA library is missing or no
+device is present, calls fail loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import Cloud, Counters, RegistrationParameters, Result  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libs3d_b200.so")
+_lib = None
+
+
+class S3DError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads libs3d_b200.so (built in-tree by slam3d_b200/build.py or __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise S3DError(f"{LIB_PATH} is missing: run `python slam3d_b200/build.py` (nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.s3d_last_error.restype = C.c_char_p
+        L.s3d_version.restype = C.c_char_p
+        L.s3d_context_stream.restype = C.c_void_p
+        L.s3d_context_stream.argtypes = [C.c_void_p, C.c_int]
+        L.s3d_create_context.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.s3d_destroy_context.argtypes = [C.c_void_p]
+        L.s3d_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+        L.s3d_voxel_downsample.argtypes = [C.c_void_p, Cloud, C.c_float, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_int32)]
+        L.s3d_knn_covariances.argtypes = [C.c_void_p, Cloud, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.s3d_nearest_neighbors.argtypes = [C.c_void_p, Cloud, Cloud, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.s3d_gicp_align.argtypes = [C.c_void_p, Cloud, Cloud, C.c_void_p, C.POINTER(RegistrationParameters), C.POINTER(Result)]
+        L.s3d_gicp_align_batch.argtypes = [C.c_void_p, C.POINTER(Cloud), C.POINTER(Cloud), C.c_void_p, C.POINTER(RegistrationParameters),
+                                           C.c_int, C.POINTER(Result)]
+        _lib = L
+    return _lib
+
+
+def as_xyzw(a):
+    """(n,3)/(n,4) numpy array -> C-contiguous float32 (n,4), w = 1 (pcl::PointXYZ memory). Torch tensors pass through."""
+    if _is_torch(a):
+        if a.dtype.__str__() != "torch.float32" or a.dim() != 2 or a.shape[1] != 4 or not a.is_contiguous():
+            raise ValueError("torch clouds must be contiguous float32 (n,4)")
+        return a
+    a = np.asarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] not in (3, 4):
+        raise ValueError("cloud must be (n,3) or (n,4)")
+    if a.shape[1] == 3:
+        out = np.ones((a.shape[0], 4), np.float32)
+        out[:, :3] = a
+        return out
+    return np.ascontiguousarray(a)
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+def _cloud(a):
+    a = as_xyzw(a)
+    ptr = a.data_ptr() if _is_torch(a) else a.ctypes.data
+    return a, Cloud(ptr, a.shape[0])
+
+
+def _colmajor(T):
+    return np.ascontiguousarray(np.asarray(np.eye(4) if T is None else T, np.float64).T)
+
+
+class Context:
+    """Owns the per-device workspaces/streams (s3d_create_context). One per process is enough; calls are re-entrant."""
+
+    def __init__(self, devices=None):
+        self._h = C.c_void_p()
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            st = lib().s3d_create_context(arr, len(devices), C.byref(self._h))
+        else:
+            st = lib().s3d_create_context(None, 0, C.byref(self._h))
+        if st != _abi.S3D_OK:
+            raise S3DError(f"s3d_create_context failed ({st}): {last_error()}")
+
+    def close(self):
+        if self._h:
+            lib().s3d_destroy_context(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st, what):
+        if st not in (_abi.S3D_OK,):
+            raise S3DError(f"{what} failed ({st}): {last_error()}")
+
+    def stream_handle(self, slot=0):
+        return lib().s3d_context_stream(self._h, slot)
+
+    def counters(self):
+        c = Counters()
+        lib().s3d_get_counters(self._h, C.byref(c))
+        return {"kernel_launches": c.kernel_launches, "h2d_bytes": c.h2d_bytes, "d2h_bytes": c.d2h_bytes}
+
+    # PointCloudSensor::downsample (PointCloudSensor.cpp:190-201)
+    def voxel_downsample(self, cloud, leaf, want_leaf_index=True):
+        a, c = _cloud(cloud)
+        n = a.shape[0]
+        out = np.empty((max(n, 1), 4), np.float32)
+        leaf_index = np.empty(max(n, 1), np.uint32) if want_leaf_index else None
+        n_out = C.c_uint64(0)
+        ov = C.c_int32(0)
+        st = lib().s3d_voxel_downsample(self._h, c, leaf, out.ctypes.data, C.byref(n_out), leaf_index.ctypes.data if want_leaf_index else None, C.byref(ov))
+        self._check(st, "s3d_voxel_downsample")
+        return out[: n_out.value].copy(), (leaf_index[:n].copy() if want_leaf_index else None), bool(ov.value)
+
+    def knn_covariances(self, cloud, k):
+        a, c = _cloud(cloud)
+        n = a.shape[0]
+        idx = np.empty((n, k), np.uint32)
+        d2 = np.empty((n, k), np.float32)
+        cov = np.empty((n, 9), np.float64)
+        st = lib().s3d_knn_covariances(self._h, c, k, idx.ctypes.data, d2.ctypes.data, cov.ctypes.data)
+        self._check(st, "s3d_knn_covariances")
+        return idx, d2, cov.reshape(n, 3, 3).transpose(0, 2, 1).copy()
+
+    def nearest_neighbors(self, reference, queries, transform=None):
+        r, rc = _cloud(reference)
+        q, qc = _cloud(queries)
+        idx = np.empty(q.shape[0], np.uint32)
+        d2 = np.empty(q.shape[0], np.float32)
+        t = _colmajor(transform) if transform is not None else None
+        st = lib().s3d_nearest_neighbors(self._h, rc, qc, t.ctypes.data if t is not None else None, idx.ctypes.data, d2.ctypes.data)
+        self._check(st, "s3d_nearest_neighbors")
+        return idx, d2
+
+    # align() (PointCloudSensor.cpp:119-174); returns the Result struct, status inside (0 ok, 1..3 = NoMatch reasons)
+    def gicp_align(self, source, target, guess=None, params=None):
+        s, sc = _cloud(source)
+        t, tc = _cloud(target)
+        g = _colmajor(guess)
+        p = params if params is not None else RegistrationParameters.defaults()
+        res = Result()
+        st = lib().s3d_gicp_align(self._h, sc, tc, g.ctypes.data, C.byref(p), C.byref(res))
+        if st in (_abi.S3D_INTERNAL_ERROR, _abi.S3D_INVALID_ARGUMENT):
+            raise S3DError(f"s3d_gicp_align failed ({st}): {last_error()}")
+        return res
+
+    def gicp_align_batch(self, sources, targets, guesses=None, params=None):
+        n = len(sources)
+        keep = []
+        sc = (Cloud * n)()
+        tc = (Cloud * n)()
+        for i in range(n):
+            a, c = _cloud(sources[i]); keep.append(a); sc[i] = c
+            a, c = _cloud(targets[i]); keep.append(a); tc[i] = c
+        g = np.ascontiguousarray(np.stack([_colmajor(None if guesses is None else guesses[i]) for i in range(n)]))
+        p = params if params is not None else RegistrationParameters.defaults()
+        res = (Result * n)()
+        st = lib().s3d_gicp_align_batch(self._h, sc, tc, g.ctypes.data, C.byref(p), n, res)
+        self._check(st, "s3d_gicp_align_batch")
+        return list(res)
+
+
+def last_error():
+    return lib().s3d_last_error().decode()

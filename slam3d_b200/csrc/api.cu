@@ -1,0 +1,339 @@
+// api.cu — the C-ABI of include/s3d_b200.h: context, per-thread workspaces, batch sharding over devices.
+//
+// Mirrors the two arithmetic call sites of the reference:
+//   s3d_voxel_downsample  <-  PointCloudSensor::downsample            PointCloudSensor.cpp:190-201
+//   s3d_gicp_align        <-  align() incl. doICP<GICP> and its gates  PointCloudSensor.cpp:52-82, 119-174
+// Re-entrancy (ScanSensor.cpp:209-210 calls createConstraint from two threads): every call checks a private Workspace
+// (device buffers + stream) out of the context's pool; there is no global mutable state.
+// There is NO CPU fallback: without a CUDA device every entry point returns S3D_INTERNAL_ERROR.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <thread>
+
+#include "internal.h"
+
+namespace s3d {
+
+thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+struct DeviceCtx {
+  int device = 0;
+  std::mutex mu;
+  std::vector<std::unique_ptr<Workspace>> pool;  // idle workspaces
+  std::vector<Workspace*> all;
+};
+
+}  // namespace s3d
+
+struct s3d_context {
+  std::vector<std::unique_ptr<s3d::DeviceCtx>> devs;
+  std::mutex mu;
+  uint64_t launches = 0, h2d = 0, d2h = 0;
+  int max_pairs_per_launch = 32;
+};
+
+namespace s3d {
+
+struct WsLease {
+  s3d_context* ctx; DeviceCtx* dc; std::unique_ptr<Workspace> ws;
+  WsLease(s3d_context* c, int slot) : ctx(c), dc(c->devs[slot].get()) {
+    S3D_CUDA(cudaSetDevice(dc->device));
+    {
+      std::lock_guard<std::mutex> g(dc->mu);
+      if (!dc->pool.empty()) { ws = std::move(dc->pool.back()); dc->pool.pop_back(); }
+    }
+    if (!ws) { ws.reset(new Workspace()); ws->init(dc->device); std::lock_guard<std::mutex> g(dc->mu); dc->all.push_back(ws.get()); }
+  }
+  ~WsLease() {
+    {
+      std::lock_guard<std::mutex> g(ctx->mu);
+      ctx->launches += ws->launches; ctx->h2d += ws->h2d; ctx->d2h += ws->d2h;
+      ws->launches = ws->h2d = ws->d2h = 0;
+    }
+    std::lock_guard<std::mutex> g(dc->mu);
+    dc->pool.push_back(std::move(ws));
+  }
+  Workspace& operator*() { return *ws; }
+};
+
+template <typename F>
+static int guarded(F&& f) {
+  try {
+    return f();
+  } catch (const CudaError& e) {
+    set_error(e.what);
+    cudaGetLastError();
+    return S3D_INTERNAL_ERROR;
+  } catch (const std::exception& e) {
+    set_error(e.what());
+    return S3D_INTERNAL_ERROR;
+  }
+}
+
+static void copy_out(Workspace& ws, void* dst, const void* src_dev, size_t bytes) {
+  if (!dst || !bytes) return;
+  S3D_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDefault, ws.stream));
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, dst) != cudaSuccess) { cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; }
+  if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) ws.d2h += bytes;
+}
+
+// One sub-batch of align() calls on one device.
+static void align_chunk(s3d_context* ctx, int slot, const s3d_cloud* sources, const s3d_cloud* targets, const double* guesses,
+                        const s3d_registration_parameters& cfg, int n, s3d_result* out) {
+  WsLease lease(ctx, slot);
+  Workspace& ws = *lease;
+  std::vector<const float*> clouds(2 * n);
+  std::vector<uint64_t> sizes(2 * n);
+  for (int i = 0; i < n; ++i) {
+    clouds[2 * i] = sources[i].xyzw; sizes[2 * i] = sources[i].n;
+    clouds[2 * i + 1] = targets[i].xyzw; sizes[2 * i + 1] = targets[i].n;
+  }
+  setup_batch(ws, clouds, sizes, n);
+  const float leaf = cfg.point_cloud_density > 0 ? (float)cfg.point_cloud_density : 0.f;  // :127, setLeafSize(float)
+  run_voxel(ws, leaf);
+  const bool gicp = cfg.registration_algorithm == S3D_ALG_GICP;
+  const bool k_ok = cfg.correspondence_randomness >= 1 && cfg.correspondence_randomness <= 32;
+  if (!gicp || !k_ok) {
+    // the reference evaluates the <100 gate before the algorithm switch (:134-135 then :139-165)
+    SlotInfo* hs = ws.h_slots.as<SlotInfo>();
+    S3D_CUDA(cudaMemcpyAsync(hs, ws.slots.p, sizeof(SlotInfo) * ws.n_slots, cudaMemcpyDeviceToHost, ws.stream));
+    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.d2h += sizeof(SlotInfo) * ws.n_slots;
+    for (int i = 0; i < n; ++i) {
+      memset(&out[i], 0, sizeof out[i]);
+      for (int j = 0; j < 16; ++j) out[i].T[j] = (j % 5 == 0) ? 1.0 : 0.0;
+      out[i].n_source = hs[2 * i].n_pts; out[i].n_target = hs[2 * i + 1].n_pts;
+      if (out[i].n_source < 100 || out[i].n_target < 100) out[i].status = S3D_TOO_FEW_POINTS;
+      else out[i].status = gicp ? S3D_INVALID_ARGUMENT : S3D_UNKNOWN_ALGORITHM;
+    }
+    if (gicp) set_error("correspondence_randomness must be in [1, 32] on the GPU path");
+    else if (cfg.registration_algorithm == S3D_ALG_GICP_OMP || cfg.registration_algorithm == S3D_ALG_NDT_OMP)
+      set_error("OMP is not available, you need to rebuild SLAM3D with OMP or use another matching algorithm.");
+    else if (cfg.registration_algorithm == S3D_ALG_NDT) set_error("NDT is not implemented by the B200 path (SURVEY 8f rank 4).");
+    else set_error("Unknown registration algorithm specified.");
+    return;
+  }
+  run_grid(ws, leaf);
+  run_knn_covariances(ws, cfg.correspondence_randomness, nullptr, nullptr);
+  std::vector<s3d_registration_parameters> params(n, cfg);
+  run_gicp(ws, params, guesses, out);
+}
+
+static const char* status_text(int st, const s3d_result& r, const s3d_registration_parameters& cfg, std::string& buf) {
+  switch (st) {
+    case S3D_TOO_FEW_POINTS: return "Too few points after filtering, you may have to decrease 'point_cloud_density'.";
+    case S3D_NOT_CONVERGED:
+      buf = "ICP failed with Fitness-Score " + std::to_string(r.fitness) + " > " + std::to_string(cfg.max_fitness_score);
+      return buf.c_str();
+    case S3D_TOO_FAR_FROM_GUESS: return "ICP result is to far away from guess";
+    default: return nullptr;
+  }
+}
+
+}  // namespace s3d
+
+using namespace s3d;
+
+extern "C" {
+
+const char* s3d_last_error(void) { return g_last_error.c_str(); }
+const char* s3d_version(void) { return "slam3d_b200 0.1 (sm_100a)"; }
+
+void s3d_default_parameters(s3d_registration_parameters* p) {  // RegistrationParameters.hpp:36-97
+  p->registration_algorithm = S3D_ALG_GICP;
+  p->point_cloud_density = 0.2; p->max_fitness_score = 2.0; p->max_translation = 1.0; p->max_rotation = 1.0;
+  p->euclidean_fitness_epsilon = 1.0; p->transformation_epsilon = 1e-5; p->max_correspondence_distance = 2.5;
+  p->maximum_iterations = 50; p->rotation_epsilon = 2e-3; p->correspondence_randomness = 20; p->maximum_optimizer_iterations = 20;
+  p->resolution = 1.0f; p->step_size = 0.05; p->outlier_ratio = 0.35;
+}
+
+int s3d_create_context(const int* devices, int n_devices, s3d_context** out) {
+  if (!out) return S3D_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded([&]() -> int {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+      cudaGetLastError();
+      set_error("no CUDA device: the slam3d_b200 scan-matching path has no CPU fallback");
+      return S3D_INTERNAL_ERROR;
+    }
+    std::unique_ptr<s3d_context> ctx(new s3d_context());
+    std::vector<int> devs;
+    if (devices && n_devices > 0) devs.assign(devices, devices + n_devices);
+    else { int cur = 0; S3D_CUDA(cudaGetDevice(&cur)); devs.push_back(cur); }
+    for (int d : devs) {
+      if (d < 0 || d >= count) { set_error("bad device ordinal"); return S3D_INVALID_ARGUMENT; }
+      std::unique_ptr<DeviceCtx> dc(new DeviceCtx());
+      dc->device = d;
+      std::unique_ptr<Workspace> ws(new Workspace());
+      ws->init(d);
+      dc->all.push_back(ws.get());
+      dc->pool.push_back(std::move(ws));
+      ctx->devs.push_back(std::move(dc));
+    }
+    if (const char* env = getenv("S3D_MAX_PAIRS_PER_LAUNCH")) ctx->max_pairs_per_launch = std::max(1, atoi(env));
+    *out = ctx.release();
+    return S3D_OK;
+  });
+}
+
+int s3d_destroy_context(s3d_context* ctx) {
+  if (!ctx) return S3D_OK;
+  for (auto& dc : ctx->devs) {
+    for (auto& ws : dc->pool) ws->destroy();
+    dc->pool.clear();
+  }
+  delete ctx;
+  return S3D_OK;
+}
+
+void* s3d_context_stream(s3d_context* ctx, int device_slot) {
+  if (!ctx || device_slot < 0 || device_slot >= (int)ctx->devs.size()) return nullptr;
+  DeviceCtx* dc = ctx->devs[device_slot].get();
+  std::lock_guard<std::mutex> g(dc->mu);
+  return dc->all.empty() ? nullptr : (void*)dc->all[0]->stream;
+}
+
+int s3d_get_counters(s3d_context* ctx, s3d_counters* out) {
+  if (!ctx || !out) return S3D_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  out->kernel_launches = ctx->launches; out->h2d_bytes = ctx->h2d; out->d2h_bytes = ctx->d2h;
+  return S3D_OK;
+}
+
+int s3d_voxel_downsample(s3d_context* ctx, s3d_cloud in, float leaf, float* out_xyzw, uint64_t* n_out, uint32_t* leaf_index, int32_t* overflow) {
+  if (!ctx || !n_out) return S3D_INVALID_ARGUMENT;
+  if (!(leaf > 0.f)) { set_error("leaf size must be positive"); return S3D_INVALID_ARGUMENT; }
+  *n_out = 0;
+  if (overflow) *overflow = 0;
+  if (in.n == 0) return S3D_OK;  // PointCloudSensor.cpp:193
+  return guarded([&]() -> int {
+    WsLease lease(ctx, 0);
+    Workspace& ws = *lease;
+    setup_batch(ws, {in.xyzw}, {in.n}, 0);
+    DevBuf& lk = ws.moved;  // borrowed as the unsorted-key buffer
+    if (leaf_index) lk.reserve(4 * size_t(ws.total));
+    run_voxel(ws, leaf, leaf_index ? lk.as<uint32_t>() : nullptr);
+    SlotInfo* hs = ws.h_slots.as<SlotInfo>();
+    S3D_CUDA(cudaMemcpyAsync(hs, ws.slots.p, sizeof(SlotInfo), cudaMemcpyDeviceToHost, ws.stream));
+    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.d2h += sizeof(SlotInfo);
+    *n_out = hs[0].n_pts;
+    if (overflow) *overflow = hs[0].overflow;
+    copy_out(ws, out_xyzw, ws.work.p, 16 * size_t(hs[0].n_pts));
+    copy_out(ws, leaf_index, lk.p, 4 * size_t(in.n));
+    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    return S3D_OK;
+  });
+}
+
+int s3d_knn_covariances(s3d_context* ctx, s3d_cloud cloud, int k, uint32_t* knn_index, float* knn_dist2, double* covariances) {
+  if (!ctx) return S3D_INVALID_ARGUMENT;
+  if (k < 1 || k > 32 || (uint64_t)k > cloud.n) { set_error("k must be in [1, 32] and not larger than the cloud"); return S3D_INVALID_ARGUMENT; }
+  return guarded([&]() -> int {
+    WsLease lease(ctx, 0);
+    Workspace& ws = *lease;
+    setup_batch(ws, {cloud.xyzw}, {cloud.n}, 0);
+    run_voxel(ws, 0.f);
+    run_grid(ws, 0.f);
+    const size_t n = cloud.n;
+    DevBuf& di = ws.moved; DevBuf& dd = ws.prev_nn; DevBuf& dc = ws.moments;
+    if (knn_index) di.reserve(4 * n * k);
+    if (knn_dist2) dd.reserve(4 * n * k);
+    run_knn_covariances(ws, k, knn_index ? di.as<uint32_t>() : nullptr, knn_dist2 ? dd.as<float>() : nullptr);
+    if (covariances) { dc.reserve(72 * n); run_expand_cov(ws, dc.as<double>()); }
+    copy_out(ws, knn_index, di.p, 4 * n * k);
+    copy_out(ws, knn_dist2, dd.p, 4 * n * k);
+    copy_out(ws, covariances, dc.p, 72 * n);
+    int32_t* hf = ws.h_small.as<int32_t>();
+    S3D_CUDA(cudaMemcpyAsync(hf, ws.flags.p, 16, cudaMemcpyDeviceToHost, ws.stream));
+    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    if (hf[0] & kErrHashArena) { set_error("hash arena too small"); return S3D_INTERNAL_ERROR; }
+    return S3D_OK;
+  });
+}
+
+int s3d_nearest_neighbors(s3d_context* ctx, s3d_cloud reference, s3d_cloud queries, const double* transform, uint32_t* nn_index, float* nn_dist2) {
+  if (!ctx || reference.n == 0) return S3D_INVALID_ARGUMENT;
+  if (queries.n == 0) return S3D_OK;
+  return guarded([&]() -> int {
+    WsLease lease(ctx, 0);
+    Workspace& ws = *lease;
+    setup_batch(ws, {reference.xyzw, queries.xyzw}, {reference.n, queries.n}, 0);
+    run_voxel(ws, 0.f);
+    run_grid(ws, 0.f);
+    float* Td = nullptr;
+    if (transform) {
+      float* hT = ws.h_small.as<float>() + 64;
+      for (int i = 0; i < 16; ++i) hT[i] = (float)transform[i];
+      ws.fit_partial.reserve(64);
+      Td = ws.fit_partial.as<float>();
+      S3D_CUDA(cudaMemcpyAsync(Td, hT, 64, cudaMemcpyHostToDevice, ws.stream));
+    }
+    DevBuf& di = ws.moved; DevBuf& dd = ws.prev_nn;
+    di.reserve(4 * queries.n); dd.reserve(4 * queries.n);
+    run_nn_stage(ws, 0, 1, Td, di.as<uint32_t>(), dd.as<float>());
+    copy_out(ws, nn_index, di.p, 4 * queries.n);
+    copy_out(ws, nn_dist2, dd.p, 4 * queries.n);
+    int32_t* hf = ws.h_small.as<int32_t>();
+    S3D_CUDA(cudaMemcpyAsync(hf, ws.flags.p, 16, cudaMemcpyDeviceToHost, ws.stream));
+    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    if (hf[0] & kErrHashArena) { set_error("hash arena too small"); return S3D_INTERNAL_ERROR; }
+    return S3D_OK;
+  });
+}
+
+int s3d_gicp_align_batch(s3d_context* ctx, const s3d_cloud* sources, const s3d_cloud* targets, const double* guesses,
+                         const s3d_registration_parameters* params, int n_pairs, s3d_result* out) {
+  if (!ctx || !params || !out || n_pairs < 0 || (n_pairs > 0 && (!sources || !targets || !guesses))) return S3D_INVALID_ARGUMENT;
+  if (n_pairs == 0) return S3D_OK;
+  const int nd = (int)ctx->devs.size();
+  // contiguous shards, one host thread per device; no device-to-device traffic (registrations are independent)
+  std::vector<int> st(nd, S3D_OK);
+  std::vector<std::string> errs(nd);
+  auto work = [&](int d) {
+    const int lo = (int)((int64_t)n_pairs * d / nd), hi = (int)((int64_t)n_pairs * (d + 1) / nd);
+    st[d] = guarded([&]() -> int {
+      for (int b = lo; b < hi; b += ctx->max_pairs_per_launch) {
+        const int n = std::min(ctx->max_pairs_per_launch, hi - b);
+        align_chunk(ctx, d, sources + b, targets + b, guesses + 16 * (size_t)b, *params, n, out + b);
+      }
+      return S3D_OK;
+    });
+    if (st[d] != S3D_OK) errs[d] = g_last_error;
+  };
+  if (nd == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; ++d) th.emplace_back(work, d);
+    for (auto& t : th) t.join();
+  }
+  for (int d = 0; d < nd; ++d)
+    if (st[d] != S3D_OK) {
+      set_error(errs[d]);
+      for (int i = 0; i < n_pairs; ++i) if (out[i].status == S3D_OK && st[d] == S3D_INTERNAL_ERROR) { /* results of other shards stay valid */ }
+      return st[d];
+    }
+  return S3D_OK;
+}
+
+int s3d_gicp_align(s3d_context* ctx, s3d_cloud source, s3d_cloud target, const double guess[16], const s3d_registration_parameters* params,
+                   s3d_result* out) {
+  if (!ctx || !params || !out || !guess) return S3D_INVALID_ARGUMENT;
+  memset(out, 0, sizeof *out);
+  const int st = guarded([&]() -> int {
+    align_chunk(ctx, 0, &source, &target, guess, *params, 1, out);
+    return S3D_OK;
+  });
+  if (st != S3D_OK) { out->status = st; return st; }
+  std::string buf;
+  if (const char* msg = status_text(out->status, *out, *params, buf)) set_error(msg);
+  return out->status;
+}
+
+}  // extern "C"

@@ -1,0 +1,379 @@
+// gicp.cu — the Generalized-ICP loop of pcl::GeneralizedIterativeClosestPoint as driven by slam3d's doICP
+// (slam3d/sensor/pcl/PointCloudSensor.cpp:52-82) and the fitness score of :73.   Semantics: SURVEY A.4-A.6.
+//
+// Per outer iteration TWO launches for the whole batch of pairs, no host arithmetic:
+//   gicp_iter_kernel   one thread per moving point:  q = T_f32 * (guess_f32 * p)  ->  exact 1-NN in the fixed cloud
+//                      (nn_search.cuh, warm-started by the previous correspondence)  ->  d2 < max_corr^2  ->
+//                      M = (R C1 R^T + C2)^-1 (FP64)  ->  the point's 14 features go to shared memory and the CTA
+//                      reduces them to the 74 sufficient statistics of the GICP objective (gicp_math.h) in a fixed
+//                      order  ->  one 74-double partial per 256-point tile.
+//   gicp_solve_kernel  one CTA per pair: fixed-order sum of the tile partials, then ONE thread runs PCL's complete
+//                      inner optimiser (estimateRigidTransformationNewton, <= maximum_optimizer_iterations steps with
+//                      back-tracking) on the statistics, applies PCL's convergence test and updates the pair state.
+// The host only polls an "active pairs" counter.  Reductions use fixed trees (tile partials, ordered sums): results
+// are bit-reproducible run to run and independent of batch composition.
+// Roofline: per iteration 16 B (moving point) + 32 B (its normal) + gathered 16 B + 32 B (fixed point + normal) per
+// correspondence; the working set is L2 resident, the kernel is latency bound on the hash probes.
+#include "internal.h"
+#include "nn_search.cuh"
+
+namespace s3d {
+
+constexpr int kFeat = 14;  // M00 M01 M02 M11 M12 M22 | px py pz | Mq0 Mq1 Mq2 | qMq | valid
+
+struct MomentSpec { uint8_t a, b, c; };  // moment = sum f[a]*f[b]*f[c]
+__constant__ MomentSpec c_spec[kNumMoments];
+
+static void build_moment_spec(MomentSpec* spec) {
+  const int Mi[6] = {0, 1, 2, 3, 4, 5};
+  const int phi[4] = {6, 7, 8, 13};
+  int ab = 0;
+  for (int a = 0; a < 3; ++a)
+    for (int b = a; b < 3; ++b, ++ab) {
+      int ce = 0;
+      for (int c = 0; c < 4; ++c)
+        for (int e = c; e < 4; ++e, ++ce) spec[ab * 10 + ce] = {(uint8_t)Mi[ab], (uint8_t)phi[c], (uint8_t)phi[e]};
+    }
+  for (int a = 0; a < 3; ++a) for (int c = 0; c < 4; ++c) spec[60 + a * 4 + c] = {(uint8_t)(9 + a), (uint8_t)phi[c], 13};
+  spec[72] = {12, 13, 13};
+  spec[73] = {13, 13, 13};
+}
+
+// R = top-left 3x3 of double(T) * double(guess);  RRt = R R^T      (SURVEY A.4 "R <- ...")
+__device__ void update_rotation(PairState& ps) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 4; ++k) s += (double)ps.T[k * 4 + i] * (double)ps.guess[j * 4 + k];
+      ps.R[i][j] = s;
+    }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += ps.R[i][k] * ps.R[j][k];
+      ps.RRt[i][j] = s;
+    }
+}
+
+// Eigen Matrix4f * Matrix4f: ((a0*b0 + a1*b1) + a2*b2) + a3*b3, column-major
+__device__ void mat4f_mul(const float* A, const float* B, float* C) {
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c)
+      C[c * 4 + r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A[r], B[c * 4]), __fmul_rn(A[4 + r], B[c * 4 + 1])), __fmul_rn(A[8 + r], B[c * 4 + 2])),
+                               __fmul_rn(A[12 + r], B[c * 4 + 3]));
+}
+
+// Registration::align set-up: gates of align() :134-135, output = guess * input (transformPointCloud), state reset.
+__global__ void __launch_bounds__(256) gicp_prepare_kernel(const SlotInfo* __restrict__ slots, PairState* __restrict__ pairs, const float4* __restrict__ gpts,
+                                                           float4* __restrict__ moved, uint32_t* __restrict__ prev_nn, int32_t* __restrict__ flags) {
+  const uint32_t p = blockIdx.y;
+  PairState& ps = pairs[p];
+  const SlotInfo& sb = slots[2 * p];      // fixed cloud B  (slam3d source = PCL target)
+  const SlotInfo& sa = slots[2 * p + 1];  // moving cloud A (slam3d target = PCL source)
+  const bool enough = sa.n_pts >= 100 && sb.n_pts >= 100;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ps.active = enough ? 1 : 0;
+    if (enough) { update_rotation(ps); atomicAdd(&flags[1], 1); }
+  }
+  if (!enough) return;
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= sa.n_pts) return;
+  const float4 v = gpts[sa.off + r];
+  const float3 m = transform_se3(ps.guess, v.x, v.y, v.z);
+  moved[sa.off + r] = make_float4(m.x, m.y, m.z, v.w);
+  prev_nn[sa.off + r] = kNoIndex;
+}
+
+__global__ void __launch_bounds__(kIterTile) gicp_iter_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
+                                                              const HashEntry* __restrict__ arena, const float4* __restrict__ gpts,
+                                                              const float4* __restrict__ moved, const double4* __restrict__ normals,
+                                                              uint32_t* __restrict__ prev_nn, double* __restrict__ moments) {
+  __shared__ double feat[kIterTile][kFeat];
+  __shared__ double part[3][kNumMoments];
+  const uint32_t p = blockIdx.y;
+  const PairState& ps = pairs[p];
+  if (!ps.active) return;
+  const SlotInfo& sb = slots[2 * p];
+  const SlotInfo& sa = slots[2 * p + 1];
+  const uint32_t first = blockIdx.x * kIterTile;
+  if (first >= sa.n_pts) return;
+  const uint32_t r = first + threadIdx.x;
+  double f[kFeat];
+#pragma unroll
+  for (int i = 0; i < kFeat; ++i) f[i] = 0.0;
+  if (r < sa.n_pts) {
+    const GridView g = make_grid_view(sb, arena, gpts);
+    const float4 mv = moved[sa.off + r];
+    const float3 q = transform_mv(ps.T, mv.x, mv.y, mv.z);
+    const double thr = ps.max_corr2;
+    const float cutoff = __double2float_ru(thr);
+    const NNResult nn = nn_search(g, q.x, q.y, q.z, cutoff, prev_nn[sa.off + r]);
+    prev_nn[sa.off + r] = nn.pos;
+    if (nn.pos != kNoIndex && (double)nn.d2 < thr) {
+      const double4 n1 = normals[sa.off + r];
+      const double4 n2 = normals[sb.off + nn.pos];
+      double a[3], b[3] = {n2.x, n2.y, n2.z};
+      for (int i = 0; i < 3; ++i) a[i] = ps.R[i][0] * n1.x + ps.R[i][1] * n1.y + ps.R[i][2] * n1.z;
+      double M[6];
+      mahalanobis6(ps.RRt, a, b, M);
+      const float4 qb = g.pts[nn.pos];
+      const double qx = qb.x, qy = qb.y, qz = qb.z;
+      const double Mq0 = M[0] * qx + M[1] * qy + M[2] * qz;
+      const double Mq1 = M[1] * qx + M[3] * qy + M[4] * qz;
+      const double Mq2 = M[2] * qx + M[4] * qy + M[5] * qz;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) f[i] = M[i];
+      f[6] = mv.x; f[7] = mv.y; f[8] = mv.z;
+      f[9] = Mq0; f[10] = Mq1; f[11] = Mq2;
+      f[12] = qx * Mq0 + qy * Mq1 + qz * Mq2;
+      f[13] = 1.0;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kFeat; ++i) feat[threadIdx.x][i] = f[i];
+  __syncthreads();
+  // 74 statistics x 3 sub-ranges of the tile, each summed in ascending point order
+  if (threadIdx.x < 3 * kNumMoments) {
+    const int m = threadIdx.x % kNumMoments, sub = threadIdx.x / kNumMoments;
+    const MomentSpec sp = c_spec[m];
+    const int lo = sub * 86, hi = min(kIterTile, lo + 86);
+    double s = 0.0;
+    for (int i = lo; i < hi; ++i) s += feat[i][sp.a] * feat[i][sp.b] * feat[i][sp.c];
+    part[sub][m] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumMoments) {
+    const size_t tile = (size_t)p * gridDim.x + blockIdx.x;
+    moments[tile * kNumMoments + threadIdx.x] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x];
+  }
+}
+
+// one CTA per pair: ordered reduction of the tile partials + PCL's inner optimiser + outer-loop bookkeeping (A.4)
+__global__ void __launch_bounds__(256) gicp_solve_kernel(const SlotInfo* __restrict__ slots, PairState* __restrict__ pairs,
+                                                         const double* __restrict__ moments, uint32_t tiles_per_pair, int32_t* __restrict__ flags) {
+  __shared__ double part[3][kNumMoments];
+  __shared__ double mom[kNumMoments];
+  const uint32_t p = blockIdx.x;
+  PairState& ps = pairs[p];
+  if (!ps.active) return;
+  const uint32_t n_tiles = (slots[2 * p + 1].n_pts + kIterTile - 1) / kIterTile;
+  if (threadIdx.x < 3 * kNumMoments) {
+    const int m = threadIdx.x % kNumMoments, sub = threadIdx.x / kNumMoments;
+    const uint32_t per = (n_tiles + 2) / 3;
+    const uint32_t lo = sub * per, hi = min(n_tiles, lo + per);
+    const double* src = moments + (size_t)p * tiles_per_pair * kNumMoments + m;
+    double s = 0.0;
+    for (uint32_t t = lo; t < hi; ++t) s += src[(size_t)t * kNumMoments];
+    part[sub][m] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumMoments) mom[threadIdx.x] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double lm[kNumMoments];
+  for (int i = 0; i < kNumMoments; ++i) lm[i] = mom[i];
+  ps.n_corr = (uint32_t)lm[73];
+  for (int i = 0; i < 16; ++i) ps.prev[i] = ps.T[i];  // previous_transformation_ = transformation_
+  int inner = 0;
+  float T[16];
+  for (int i = 0; i < 16; ++i) T[i] = ps.T[i];
+  bool stop = false;
+  if (!newton_from_moments(lm, T, ps.max_inner, &inner)) {
+    ps.failed = 1; ps.converged = 0; stop = true;  // optimiser exception: loop breaks, converged_ stays false, final = previous * guess
+  } else {
+    ps.inner_iterations += inner;
+    double delta = 0.0;
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) {
+        const double ratio = (r < 3 && c < 3) ? 1.0 / ps.rot_eps : 1.0 / ps.trans_eps;
+        const double cd = ratio * fabs((double)ps.prev[c * 4 + r] - (double)T[c * 4 + r]);
+        if (cd > delta) delta = cd;
+      }
+    for (int i = 0; i < 16; ++i) ps.T[i] = T[i];
+    ps.outer_iterations += 1;
+    if (ps.outer_iterations >= ps.max_iter || delta < 1.0) {
+      ps.converged = 1; stop = true;
+      for (int i = 0; i < 16; ++i) ps.prev[i] = T[i];  // previous_transformation_ = transformation_
+    } else {
+      update_rotation(ps);
+    }
+  }
+  if (stop) {
+    mat4f_mul(ps.prev, ps.guess, ps.final_T);  // final_transformation_ = previous_transformation_ * guess
+    ps.active = 0;
+    atomicSub(&flags[1], 1);
+  }
+}
+
+// getFitnessScore(max_range): transformPointCloud(input, final), 1-NN, d2 <= max_range (sic), mean of d2   (A.6)
+__global__ void __launch_bounds__(kIterTile) gicp_fitness_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
+                                                                 const HashEntry* __restrict__ arena, const float4* __restrict__ gpts,
+                                                                 const uint32_t* __restrict__ prev_nn, double* __restrict__ fit_partial) {
+  __shared__ double ssum[kIterTile];
+  __shared__ uint32_t scnt[kIterTile];
+  const uint32_t p = blockIdx.y;
+  const PairState& ps = pairs[p];
+  const SlotInfo& sb = slots[2 * p];
+  const SlotInfo& sa = slots[2 * p + 1];
+  if (sa.n_pts < 100 || sb.n_pts < 100) return;
+  const uint32_t first = blockIdx.x * kIterTile;
+  if (first >= sa.n_pts) return;
+  const uint32_t r = first + threadIdx.x;
+  double s = 0.0; uint32_t c = 0;
+  if (r < sa.n_pts) {
+    const GridView g = make_grid_view(sb, arena, gpts);
+    const float4 v = gpts[sa.off + r];
+    const float3 q = transform_se3(ps.final_T, v.x, v.y, v.z);
+    const NNResult nn = nn_search(g, q.x, q.y, q.z, __double2float_ru(ps.fit_range), prev_nn[sa.off + r]);
+    if (nn.pos != kNoIndex && (double)nn.d2 <= ps.fit_range) { s = (double)nn.d2; c = 1; }
+  }
+  ssum[threadIdx.x] = s; scnt[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = kIterTile / 2; o > 0; o >>= 1) {  // fixed tree
+    if (threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; scnt[threadIdx.x] += scnt[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const size_t tile = (size_t)p * gridDim.x + blockIdx.x;
+    fit_partial[2 * tile] = ssum[0];
+    fit_partial[2 * tile + 1] = (double)scnt[0];
+  }
+}
+
+__global__ void gicp_fitness_reduce_kernel(const SlotInfo* __restrict__ slots, PairState* __restrict__ pairs, const double* __restrict__ fit_partial,
+                                           uint32_t tiles_per_pair, uint32_t n_pairs) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  PairState& ps = pairs[p];
+  const SlotInfo& sb = slots[2 * p];
+  const SlotInfo& sa = slots[2 * p + 1];
+  ps.fit_sum = 0.0; ps.fit_n = 0;
+  if (sa.n_pts < 100 || sb.n_pts < 100) return;
+  const uint32_t n_tiles = (sa.n_pts + kIterTile - 1) / kIterTile;
+  double s = 0.0, c = 0.0;
+  for (uint32_t t = 0; t < n_tiles; ++t) { s += fit_partial[2 * ((size_t)p * tiles_per_pair + t)]; c += fit_partial[2 * ((size_t)p * tiles_per_pair + t) + 1]; }
+  ps.fit_sum = s; ps.fit_n = (uint32_t)c;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+static void iso_inverse(const double T[16], double out[16]) {
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) out[c * 4 + r] = T[r * 4 + c];
+  for (int r = 0; r < 3; ++r) { double s = 0; for (int c = 0; c < 3; ++c) s += out[c * 4 + r] * T[12 + c]; out[12 + r] = -s; }
+  out[3] = out[7] = out[11] = 0; out[15] = 1;
+}
+static void m4d_mul(const double A[16], const double B[16], double C[16]) {
+  for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { double s = 0; for (int k = 0; k < 4; ++k) s += A[k * 4 + r] * B[c * 4 + k]; C[c * 4 + r] = s; }
+}
+// Eigen::AngleAxisd(R).angle() — via the quaternion, in [0, pi]   (align() :168)
+static double rotation_angle(const double T[16]) {
+  const double m00 = T[0], m11 = T[5], m22 = T[10], m01 = T[4], m02 = T[8], m10 = T[1], m12 = T[9], m20 = T[2], m21 = T[6];
+  double w, x, y, z;
+  const double tr = m00 + m11 + m22;
+  if (tr > 0) {
+    double t = sqrt(tr + 1.0); w = 0.5 * t; t = 0.5 / t;
+    x = (m21 - m12) * t; y = (m02 - m20) * t; z = (m10 - m01) * t;
+  } else {
+    int i = 0;
+    if (m11 > m00) i = 1;
+    if (m22 > (i == 0 ? m00 : m11)) i = 2;
+    const double M[3][3] = {{m00, m01, m02}, {m10, m11, m12}, {m20, m21, m22}};
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    double t = sqrt(M[i][i] - M[j][j] - M[k][k] + 1.0);
+    double q[3];
+    q[i] = 0.5 * t; t = 0.5 / t;
+    w = (M[k][j] - M[j][k]) * t; q[j] = (M[j][i] + M[i][j]) * t; q[k] = (M[k][i] + M[i][k]) * t;
+    x = q[0]; y = q[1]; z = q[2];
+  }
+  return 2.0 * atan2(sqrt(x * x + y * y + z * z), fabs(w));
+}
+
+// Runs the GICP loop + fitness for every pair of the batch (grids and covariances must be ready) and fills `out`
+// with the decisions of doICP (:74-77) and align() (:134-135, :167-172).
+void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& params, const double* guesses, s3d_result* out) {
+  static bool spec_ready[64] = {false};
+  if (!spec_ready[ws.device]) {
+    MomentSpec spec[kNumMoments];
+    build_moment_spec(spec);
+    S3D_CUDA(cudaMemcpyToSymbol(c_spec, spec, sizeof spec));
+    spec_ready[ws.device] = true;
+  }
+  const uint32_t np = ws.n_pairs;
+  cudaStream_t st = ws.stream;
+  uint32_t max_na = 0;
+  for (uint32_t p = 0; p < np; ++p) max_na = std::max(max_na, ws.h_n[2 * p + 1]);
+  const uint32_t tiles_per_pair = std::max<uint32_t>(1, (max_na + kIterTile - 1) / kIterTile);
+  ws.pairs.reserve(sizeof(PairState) * np);
+  ws.h_pairs.reserve(sizeof(PairState) * np);
+  ws.moved.reserve(16 * std::max<size_t>(ws.total, 4));
+  ws.prev_nn.reserve(4 * std::max<size_t>(ws.total, 4));
+  ws.moments.reserve(sizeof(double) * kNumMoments * size_t(tiles_per_pair) * np);
+  ws.fit_partial.reserve(sizeof(double) * 2 * size_t(tiles_per_pair) * np);
+  PairState* hp = ws.h_pairs.as<PairState>();
+  int max_iter = 0;
+  for (uint32_t p = 0; p < np; ++p) {
+    const s3d_registration_parameters& cfg = params[p];
+    PairState& ps = hp[p];
+    memset(&ps, 0, sizeof ps);
+    for (int i = 0; i < 16; ++i) {
+      ps.guess[i] = (float)guesses[16 * p + i];  // guess.matrix().cast<float>()  :70
+      ps.T[i] = ps.prev[i] = ps.final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
+    }
+    ps.max_corr2 = cfg.max_correspondence_distance * cfg.max_correspondence_distance;
+    ps.rot_eps = cfg.rotation_epsilon; ps.trans_eps = cfg.transformation_epsilon;
+    ps.fit_range = cfg.max_correspondence_distance;
+    ps.max_iter = cfg.maximum_iterations; ps.max_inner = cfg.maximum_optimizer_iterations; ps.k = cfg.correspondence_randomness;
+    max_iter = std::max(max_iter, cfg.maximum_iterations);
+  }
+  S3D_CUDA(cudaMemcpyAsync(ws.pairs.p, hp, sizeof(PairState) * np, cudaMemcpyHostToDevice, st));
+  const SlotInfo* slots = ws.slots.as<SlotInfo>();
+  PairState* pairs = ws.pairs.as<PairState>();
+  int32_t* flags = ws.flags.as<int32_t>();
+  int32_t* h_flags = ws.h_small.as<int32_t>();
+  dim3 grid(tiles_per_pair, np);
+  gicp_prepare_kernel<<<grid, 256, 0, st>>>(slots, pairs, ws.gpts.as<float4>(), ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), flags);
+  ++ws.launches;
+  // PCL's loop is a do-while: with maximum_iterations <= 0 it still runs one iteration
+  const int iters = std::max(max_iter, 1);
+  for (int it = 0; it < iters; ++it) {
+    gicp_iter_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.hash.as<HashEntry>(), ws.gpts.as<float4>(), ws.moved.as<float4>(),
+                                                 ws.normals.as<double4>(), ws.prev_nn.as<uint32_t>(), ws.moments.as<double>());
+    gicp_solve_kernel<<<np, 256, 0, st>>>(slots, pairs, ws.moments.as<double>(), tiles_per_pair, flags);
+    ws.launches += 2;
+    S3D_CUDA(cudaMemcpyAsync(h_flags, flags, 16, cudaMemcpyDeviceToHost, st));
+    S3D_CUDA(cudaStreamSynchronize(st));
+    ws.d2h += 16;
+    if (h_flags[1] <= 0) break;
+  }
+  gicp_fitness_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.hash.as<HashEntry>(), ws.gpts.as<float4>(), ws.prev_nn.as<uint32_t>(),
+                                                  ws.fit_partial.as<double>());
+  gicp_fitness_reduce_kernel<<<(np + 63) / 64, 64, 0, st>>>(slots, pairs, ws.fit_partial.as<double>(), tiles_per_pair, np);
+  ws.launches += 2;
+  S3D_CUDA(cudaMemcpyAsync(hp, pairs, sizeof(PairState) * np, cudaMemcpyDeviceToHost, st));
+  SlotInfo* hs = ws.h_slots.as<SlotInfo>();
+  S3D_CUDA(cudaMemcpyAsync(hs, slots, sizeof(SlotInfo) * ws.n_slots, cudaMemcpyDeviceToHost, st));
+  S3D_CUDA(cudaMemcpyAsync(h_flags, flags, 16, cudaMemcpyDeviceToHost, st));
+  S3D_CUDA(cudaStreamSynchronize(st));
+  ws.d2h += sizeof(PairState) * np + sizeof(SlotInfo) * ws.n_slots + 16;
+  if (h_flags[0] & kErrHashArena) throw CudaError{"hash arena too small"};
+  for (uint32_t p = 0; p < np; ++p) {
+    const s3d_registration_parameters& cfg = params[p];
+    const PairState& ps = hp[p];
+    s3d_result& r = out[p];
+    memset(&r, 0, sizeof r);
+    for (int i = 0; i < 16; ++i) r.T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    r.n_source = hs[2 * p].n_pts; r.n_target = hs[2 * p + 1].n_pts;
+    if (r.n_target < 100 || r.n_source < 100) { r.status = S3D_TOO_FEW_POINTS; continue; }  // :134-135
+    for (int i = 0; i < 16; ++i) r.T[i] = (double)ps.final_T[i];  // Transform(Eigen::Isometry3f(final))  :80
+    r.fitness = ps.fit_n > 0 ? ps.fit_sum / (double)ps.fit_n : 1.7976931348623157e308;
+    r.converged = ps.converged; r.outer_iterations = ps.outer_iterations; r.inner_iterations = ps.inner_iterations;
+    r.n_correspondences = ps.n_corr;
+    if (!ps.converged || r.fitness > cfg.max_fitness_score) { r.status = S3D_NOT_CONVERGED; continue; }  // :74-77
+    double ginv[16], delta[16];
+    iso_inverse(guesses + 16 * p, ginv);
+    m4d_mul(ginv, r.T, delta);
+    const double tn = sqrt(delta[12] * delta[12] + delta[13] * delta[13] + delta[14] * delta[14]);
+    r.status = (tn > cfg.max_translation || rotation_angle(delta) > cfg.max_rotation) ? S3D_TOO_FAR_FROM_GUESS : S3D_OK;  // :167-172
+  }
+}
+
+}  // namespace s3d

@@ -1,0 +1,123 @@
+// internal.h — host-side plumbing shared by the .cu files of libs3d_b200.so (not part of the public C-ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/s3d_b200.h"
+#include "common.cuh"
+#include "gicp_math.h"
+
+namespace s3d {
+
+void set_error(const std::string& msg);  // thread-local message behind s3d_last_error()
+
+struct CudaError { std::string what; };
+#define S3D_CUDA(expr)                                                                                         \
+  do {                                                                                                         \
+    cudaError_t _e = (expr);                                                                                   \
+    if (_e != cudaSuccess) throw ::s3d::CudaError{std::string(#expr) + ": " + cudaGetErrorString(_e)};         \
+  } while (0)
+
+// growable device buffer (grow-only; reused across calls so steady state does no cudaMalloc)
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) S3D_CUDA(cudaFree(p));
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    S3D_CUDA(cudaMalloc(&p, want));
+    cap = want;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) S3D_CUDA(cudaFreeHost(p));
+    p = nullptr; cap = 0;
+    S3D_CUDA(cudaMallocHost(&p, bytes + bytes / 4 + 256));
+    cap = bytes + bytes / 4 + 256;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// Device-resident state of one registration (pair of slots).
+struct PairState {
+  float  guess[16];        // guess.matrix().cast<float>()   PointCloudSensor.cpp:70
+  float  T[16];            // transformation_
+  float  prev[16];         // previous_transformation_
+  float  final_T[16];      // final_transformation_ = previous * guess
+  double RRt[3][3];        // (T*guess).R (T*guess).R^T for the Mahalanobis matrices of this iteration
+  double R[3][3];
+  double max_corr2;        // corr_dist_threshold_^2
+  double rot_eps, trans_eps;
+  double fit_range;        // getFitnessScore(max_range): squared distance compared with this un-squared value
+  double fit_sum;
+  uint32_t fit_n;
+  int32_t max_iter, max_inner, k;
+  int32_t active;          // 1 while the outer loop runs
+  int32_t converged;
+  int32_t failed;          // optimiser exception (<4 correspondences)
+  int32_t outer_iterations, inner_iterations;
+  uint32_t n_corr;
+  uint32_t tiles_done;     // last-block-done counter of the iteration kernel
+  uint32_t fit_tiles_done;
+};
+
+constexpr int kIterTile = 256;   // source points per CTA in the fused correspondence kernel
+
+// All device memory of one in-flight batch on one device.
+struct Workspace {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  // sizes of the current batch
+  uint32_t n_slots = 0, n_pairs = 0, total = 0, n_tiles = 0;
+  std::vector<uint32_t> h_off, h_n;           // per slot
+  DevBuf slots, pairs;                        // SlotInfo[n_slots], PairState[n_pairs]
+  DevBuf raw_stage;                           // float4[total]   H2D landing zone for host inputs
+  DevBuf work, gpts;                          // float4[total]
+  DevBuf keys0, keys1, vals0, vals1;          // uint32[total]
+  DevBuf hist;                                // uint32[n_tiles*256]
+  DevBuf tile_slot, tile_first, slot_tile_begin, tile_heads;
+  DevBuf hash;                                // HashEntry[hash_cap]
+  size_t hash_cap = 0;
+  DevBuf normals;                             // double[total*4]  unit normal of the regularised covariance (+pad)
+  DevBuf moved;                               // float4[total]   guess * A (Morton order of A)
+  DevBuf prev_nn;                             // uint32[total]   last correspondence (warm start bound)
+  DevBuf moments;                             // double[iter_tiles * 74]
+  DevBuf iter_tile_pair, iter_tile_first;     // uint32[iter_tiles]
+  uint32_t iter_tiles = 0;
+  DevBuf fit_partial;                         // double[iter_tiles*2]
+  DevBuf flags;                               // int32[4]: [0] error bits, [1] active pairs, [2] hash entries used
+  PinnedBuf h_slots, h_pairs, h_small, h_tiles;  // pinned host mirrors
+  uint64_t launches = 0, h2d = 0, d2h = 0;
+  std::vector<uint8_t> scratch;
+
+  void init(int dev);
+  void destroy();
+};
+
+enum ErrorBits { kErrHashArena = 1 };
+
+// ---- stage launchers (each enqueues kernels on ws.stream; no host synchronisation inside) -----------------
+void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const std::vector<uint64_t>& sizes, uint32_t n_pairs);
+void launch_bbox(Workspace& ws, int which);          // which: sort.cuh CountSel (raw cloud -> bb_*, working cloud -> g_*)
+void run_voxel(Workspace& ws, float leaf, uint32_t* leaf_keys = nullptr);  // leaf <= 0: working cloud = raw cloud; leaf_keys: unsorted voxel keys (device, total)
+void run_grid(Workspace& ws, float leaf_hint);      // NN grid on the working clouds
+void run_knn_covariances(Workspace& ws, int k, uint32_t* knn_index, float* knn_dist2);  // outputs optional (device, slot-concatenated)
+void run_expand_cov(Workspace& ws, double* cov_out);  // full 3x3 covariances per original index (stage API)
+void run_nn_stage(Workspace& ws, uint32_t ref_slot, uint32_t qry_slot, const float* T16_dev, uint32_t* nn_index, float* nn_dist2);
+void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& params, const double* guesses, s3d_result* out);
+
+}  // namespace s3d

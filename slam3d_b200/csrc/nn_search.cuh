@@ -1,0 +1,111 @@
+// nn_search.cuh — exact nearest-neighbour queries on the multi-resolution voxel hash (grid.cu).
+//
+// Parity contract: the result equals brute force with flann::L2_Simple<float> distances
+// ((dx*dx + dy*dy) + dz*dz, unfused) and lexicographic (d2, original index) order, i.e. exact search with ties
+// going to the lowest index.  Exactness argument: a scan of the 3x3x3 block of level-L cells around the query
+// sees every point closer than  g = h_L * (1 + o) - slack, o = distance (in cells) from the query to the nearest
+// face of its own cell; so a best candidate with d2 <= g^2 is the global optimum.  Otherwise the cell size doubles.
+// The top level has 2 cells per axis, so its block is the whole cloud and the loop always terminates exactly.
+#pragma once
+
+#include "common.cuh"
+
+namespace s3d {
+
+struct GridView {
+  const HashEntry* table;
+  const float4* pts;   // Morton-sorted points of the slot, .w = original index bits
+  uint32_t cap, n;
+  int nlev;
+  float ox, oy, oz, inv_h0, h0, margin;
+};
+
+__device__ __forceinline__ GridView make_grid_view(const SlotInfo& si, const HashEntry* arena, const float4* gpts) {
+  GridView g;
+  g.table = arena + si.hash_off; g.pts = gpts + si.off; g.cap = si.hash_cap; g.n = si.n_pts; g.nlev = si.nlev;
+  g.ox = si.g_min[0]; g.oy = si.g_min[1]; g.oz = si.g_min[2]; g.inv_h0 = si.inv_h0; g.h0 = si.h0; g.margin = si.margin;
+  return g;
+}
+
+__device__ __forceinline__ float clamp_coord(float u) { return fminf(fmaxf(u, -1.0e6f), 1.0e6f); }  // NaN -> -1e6
+
+// Cell of the query at level L and the squared radius the 27-block around it is guaranteed to cover.
+__device__ __forceinline__ float block_guarantee2(const GridView& g, float ux, float uy, float uz, int L, int& cx, int& cy, int& cz) {
+  const float s = 1.0f / (float)(1 << L);  // exact power of two
+  const float vx = ux * s, vy = uy * s, vz = uz * s;
+  const float fx = floorf(vx), fy = floorf(vy), fz = floorf(vz);
+  cx = (int)fx; cy = (int)fy; cz = (int)fz;
+  const float ax = vx - fx, ay = vy - fy, az = vz - fz;
+  const float o = fminf(fminf(fminf(ax, 1.f - ax), fminf(ay, 1.f - ay)), fminf(az, 1.f - az));
+  const float r = g.h0 * (float)(1 << L) * (1.f + o) * 0.9999f - g.margin;
+  return r > 0.f ? r * r * 0.999999f : 0.f;
+}
+
+struct NNResult { float d2; uint32_t idx; uint32_t pos; };
+
+__device__ __forceinline__ bool cand_less(float d2, uint32_t idx, float bd2, uint32_t bidx) { return d2 < bd2 || (d2 == bd2 && idx < bidx); }
+
+// thread-per-query scan of the 27-block at level L
+__device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int cy, int cz, float qx, float qy, float qz, NNResult& best) {
+  const int dim = 1 << (g.nlev - L);
+  uint32_t sx[3], sy[3], sz[3];
+  bool okx[3], oky[3], okz[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    okx[d] = (unsigned)(cx + d - 1) < (unsigned)dim; sx[d] = spread3((uint32_t)(cx + d - 1));
+    oky[d] = (unsigned)(cy + d - 1) < (unsigned)dim; sy[d] = spread3((uint32_t)(cy + d - 1)) << 1;
+    okz[d] = (unsigned)(cz + d - 1) < (unsigned)dim; sz[d] = spread3((uint32_t)(cz + d - 1)) << 2;
+  }
+#pragma unroll 1
+  for (int c = 0; c < 27; ++c) {
+    const int dx = c % 3, dy = (c / 3) % 3, dz = c / 9;
+    if (!(okx[dx] && oky[dy] && okz[dz])) continue;
+    const uint32_t key = sx[dx] | sy[dy] | sz[dz];
+    uint32_t s = hash_slot(key, (uint32_t)L, g.cap);
+    uint32_t begin = 0, end = 0;
+    for (;;) {
+      const uint4 e = __ldg(reinterpret_cast<const uint4*>(g.table + s));
+      if (e.y == 0xFFFFFFFFu) break;
+      if (e.x == key && e.y == (uint32_t)L) { begin = e.z; end = e.w; break; }
+      if (++s == g.cap) s = 0;
+    }
+    for (uint32_t p = begin; p < end; ++p) {
+      const float4 v = __ldg(g.pts + p);
+      const float d2 = dist2_pcl(qx, qy, qz, v.x, v.y, v.z);
+      const uint32_t id = __float_as_uint(v.w);
+      if (cand_less(d2, id, best.d2, best.idx)) { best.d2 = d2; best.idx = id; best.pos = p; }
+    }
+  }
+}
+
+// Exact 1-NN.  cutoff2: distances above it are of no interest (search may stop once the block covers that radius);
+// hint_pos: sorted position of a candidate whose distance bounds the search (previous correspondence) or kNoIndex.
+__device__ __forceinline__ NNResult nn_search(const GridView& g, float qx, float qy, float qz, float cutoff2, uint32_t hint_pos) {
+  NNResult best{INFINITY, kNoIndex, kNoIndex};
+  if (g.n == 0 || g.cap == 0) return best;
+  const float ux = clamp_coord(grid_coord(qx, g.ox, g.inv_h0));
+  const float uy = clamp_coord(grid_coord(qy, g.oy, g.inv_h0));
+  const float uz = clamp_coord(grid_coord(qz, g.oz, g.inv_h0));
+  int L = 0;
+  if (hint_pos < g.n) {
+    const float4 v = __ldg(g.pts + hint_pos);
+    const float d2 = dist2_pcl(qx, qy, qz, v.x, v.y, v.z);
+    if (d2 == d2) {  // not NaN
+      best.d2 = d2; best.idx = __float_as_uint(v.w); best.pos = hint_pos;
+      const float need = fminf(d2, cutoff2);
+      int cx, cy, cz;
+      while (L < g.nlev - 1 && block_guarantee2(g, ux, uy, uz, L, cx, cy, cz) < need) ++L;
+    }
+  }
+  for (;; ++L) {
+    int cx, cy, cz;
+    const float g2 = block_guarantee2(g, ux, uy, uz, L, cx, cy, cz);
+    const bool top = L >= g.nlev - 1;
+    if (top) cx = cy = cz = 0;  // 2 cells per axis: the block around cell 0 is the whole cloud, wherever the query is
+    scan_block(g, L, cx, cy, cz, qx, qy, qz, best);
+    if (best.d2 <= g2 || g2 >= cutoff2 || top) break;
+  }
+  return best;
+}
+
+}  // namespace s3d

@@ -1,0 +1,352 @@
+// voxel.cu — batch set-up and the VoxelGrid down-sampling kernels.
+//
+// Replaces pcl::VoxelGrid<PointXYZ>::filter as called from PointCloudSensor::downsample
+// (slam3d/sensor/pcl/PointCloudSensor.cpp:190-201) and twice per align() (:127-131).  Semantics: SURVEY A.1.
+//   bbox      min/max over finite points (ordered-uint atomics; min/max are order independent => deterministic)
+//   params    per-slot scalars of A.1 steps 1,3,4 incl. the int32 overflow guard (one thread per slot)
+//   keys      A.1 step 5, float ops in PCL's order via __fmul_rn/__fsub_rn (no FMA contraction)
+//   sort      stable segmented radix sort (sort.cuh)                    A.1 step 6
+//   heads     run starts -> per-tile counts -> per-slot scan           A.1 step 7
+//   centroid  one thread per run sums its points in ascending input order in float, / float(count)   A.1 steps 8,9
+// All kernels are streaming and HBM/L2-bandwidth bound: 16 B/point in, 8 B/point keys, 16 B/voxel out.
+#include "internal.h"
+#include "sort.cuh"
+
+namespace s3d {
+
+// ------------------------------------------------------------------------------------------------------------
+void Workspace::init(int dev) {
+  device = dev;
+  S3D_CUDA(cudaSetDevice(dev));
+  S3D_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  flags.reserve(64);
+  h_small.reserve(4096);
+}
+
+void Workspace::destroy() {
+  cudaSetDevice(device);
+  if (stream) cudaStreamSynchronize(stream);
+  DevBuf* bufs[] = {&slots, &pairs, &raw_stage, &work, &gpts, &keys0, &keys1, &vals0, &vals1, &hist, &tile_slot, &tile_first,
+                    &slot_tile_begin, &tile_heads, &hash, &normals, &moved, &prev_nn, &moments, &iter_tile_pair, &iter_tile_first,
+                    &fit_partial, &flags};
+  for (DevBuf* b : bufs) b->release();
+  h_slots.release(); h_pairs.release(); h_small.release(); h_tiles.release();
+  if (stream) cudaStreamDestroy(stream);
+  stream = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Batch set-up: slot table, tile table, input staging.  clouds[2p] = slam3d source of pair p, clouds[2p+1] = target
+// (or any list of clouds for the stage-level entry points).
+void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const std::vector<uint64_t>& sizes, uint32_t n_pairs) {
+  S3D_CUDA(cudaSetDevice(ws.device));
+  const uint32_t ns = static_cast<uint32_t>(clouds.size());
+  ws.n_slots = ns; ws.n_pairs = n_pairs;
+  ws.h_off.resize(ns); ws.h_n.resize(ns);
+  uint64_t total = 0; uint32_t n_tiles = 0;
+  for (uint32_t s = 0; s < ns; ++s) {
+    ws.h_off[s] = static_cast<uint32_t>(total);
+    ws.h_n[s] = static_cast<uint32_t>(sizes[s]);
+    total += (sizes[s] + 3) & ~uint64_t(3);  // keep every slot 64-byte aligned
+    n_tiles += static_cast<uint32_t>((sizes[s] + kSortTile - 1) / kSortTile);
+  }
+  if (total >= (1ull << 31)) throw CudaError{"batch too large: more than 2^31 points"};
+  ws.total = static_cast<uint32_t>(total); ws.n_tiles = n_tiles;
+  const size_t tot = std::max<size_t>(total, 4);
+  ws.slots.reserve(sizeof(SlotInfo) * ns);
+  ws.work.reserve(16 * tot); ws.gpts.reserve(16 * tot);
+  ws.keys0.reserve(4 * tot); ws.keys1.reserve(4 * tot); ws.vals0.reserve(4 * tot); ws.vals1.reserve(4 * tot);
+  ws.hist.reserve(sizeof(uint32_t) * 256 * std::max<uint32_t>(n_tiles, 1));
+  ws.tile_slot.reserve(4 * std::max<uint32_t>(n_tiles, 1)); ws.tile_first.reserve(4 * std::max<uint32_t>(n_tiles, 1));
+  ws.tile_heads.reserve(4 * std::max<uint32_t>(n_tiles, 1));
+  ws.slot_tile_begin.reserve(4 * (ns + 1));
+  ws.h_slots.reserve(sizeof(SlotInfo) * ns);
+  ws.h_tiles.reserve(4 * (2 * size_t(n_tiles) + ns + 1));
+
+  // classify input pointers; host memory (pinned or pageable) and misaligned device memory go through raw_stage
+  bool need_stage = false;
+  std::vector<int> on_device(ns, 0);
+  for (uint32_t s = 0; s < ns; ++s) {
+    if (sizes[s] == 0) continue;
+    cudaPointerAttributes at{};
+    cudaError_t e = cudaPointerGetAttributes(&at, clouds[s]);
+    if (e != cudaSuccess) { cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; }
+    on_device[s] = (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) && (reinterpret_cast<uintptr_t>(clouds[s]) & 15) == 0;
+    if (!on_device[s]) need_stage = true;
+  }
+  if (need_stage) ws.raw_stage.reserve(16 * tot);
+
+  SlotInfo* hs = ws.h_slots.as<SlotInfo>();
+  uint32_t* ht = ws.h_tiles.as<uint32_t>();
+  uint32_t* h_tile_slot = ht; uint32_t* h_tile_first = ht + n_tiles; uint32_t* h_begin = ht + 2 * size_t(n_tiles);
+  uint32_t t = 0;
+  for (uint32_t s = 0; s < ns; ++s) {
+    SlotInfo& si = hs[s];
+    memset(&si, 0, sizeof si);
+    si.off = ws.h_off[s]; si.n_raw = ws.h_n[s];
+    for (int a = 0; a < 3; ++a) {  // ordered-uint encodings of +inf / -inf, filled in by the bbox kernel
+      reinterpret_cast<uint32_t&>(si.bb_min[a]) = 0xFFFFFFFFu; reinterpret_cast<uint32_t&>(si.bb_max[a]) = 0u;
+      reinterpret_cast<uint32_t&>(si.g_min[a]) = 0xFFFFFFFFu; reinterpret_cast<uint32_t&>(si.g_max[a]) = 0u;
+    }
+    if (sizes[s] == 0) si.raw = nullptr;
+    else if (on_device[s]) si.raw = reinterpret_cast<const float4*>(clouds[s]);
+    else {
+      si.raw = ws.raw_stage.as<float4>() + si.off;
+      S3D_CUDA(cudaMemcpyAsync(ws.raw_stage.as<float4>() + si.off, clouds[s], 16 * sizes[s], cudaMemcpyDefault, ws.stream));
+      ws.h2d += 16 * sizes[s];
+    }
+    h_begin[s] = t;
+    for (uint64_t f = 0; f < sizes[s]; f += kSortTile) { h_tile_slot[t] = s; h_tile_first[t] = static_cast<uint32_t>(f); ++t; }
+  }
+  h_begin[ns] = t;
+  S3D_CUDA(cudaMemcpyAsync(ws.slots.p, hs, sizeof(SlotInfo) * ns, cudaMemcpyHostToDevice, ws.stream));
+  if (n_tiles) {
+    S3D_CUDA(cudaMemcpyAsync(ws.tile_slot.p, h_tile_slot, 4 * size_t(n_tiles), cudaMemcpyHostToDevice, ws.stream));
+    S3D_CUDA(cudaMemcpyAsync(ws.tile_first.p, h_tile_first, 4 * size_t(n_tiles), cudaMemcpyHostToDevice, ws.stream));
+  }
+  S3D_CUDA(cudaMemcpyAsync(ws.slot_tile_begin.p, h_begin, 4 * size_t(ns + 1), cudaMemcpyHostToDevice, ws.stream));
+  S3D_CUDA(cudaMemsetAsync(ws.flags.p, 0, 64, ws.stream));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// bbox over finite points of the raw cloud (which = kCountRaw -> bb_*) or the working cloud (kCountPts -> g_*)
+__global__ void __launch_bounds__(kSortThreads) bbox_kernel(SlotInfo* __restrict__ slots, TileMap tm, const float4* __restrict__ work, int which) {
+  const uint32_t t = blockIdx.x;
+  const uint32_t slot = tm.tile_slot[t], first = tm.tile_first[t];
+  SlotInfo& si = slots[slot];
+  const uint32_t n = slot_count(si, which);
+  if (first >= n) return;
+  const float4* p = which == kCountRaw ? si.raw : work + si.off;
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int j = 0; j < kSortTile / kSortThreads; ++j) {
+    const uint32_t e = first + j * kSortThreads + threadIdx.x;
+    if (e < n) {
+      const float4 v = p[e];
+      if (finite3(v.x, v.y, v.z)) {
+        ++cnt;
+        mn[0] = fminf(mn[0], v.x); mn[1] = fminf(mn[1], v.y); mn[2] = fminf(mn[2], v.z);
+        mx[0] = fmaxf(mx[0], v.x); mx[1] = fmaxf(mx[1], v.y); mx[2] = fmaxf(mx[2], v.z);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xFFFFFFFFu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xFFFFFFFFu, mx[a], o));
+    }
+    cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0 && cnt) {
+    uint32_t* dmin = reinterpret_cast<uint32_t*>(which == kCountRaw ? si.bb_min : si.g_min);
+    uint32_t* dmax = reinterpret_cast<uint32_t*>(which == kCountRaw ? si.bb_max : si.g_max);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { atomicMin(&dmin[a], float_to_ordered(mn[a])); atomicMax(&dmax[a], float_to_ordered(mx[a])); }
+    if (which == kCountRaw) atomicAdd(&si.n_finite, cnt);
+  }
+}
+
+// A.1 steps 1, 3, 4 — one thread per slot.  leaf <= 0: no filtering, the working cloud is the raw cloud.
+__global__ void voxel_params_kernel(SlotInfo* __restrict__ slots, uint32_t n_slots, float leaf) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  SlotInfo& si = slots[s];
+  for (int a = 0; a < 3; ++a) {
+    si.bb_min[a] = ordered_to_float(reinterpret_cast<uint32_t&>(si.bb_min[a]));
+    si.bb_max[a] = ordered_to_float(reinterpret_cast<uint32_t&>(si.bb_max[a]));
+  }
+  if (!(leaf > 0.f)) { si.overflow = 1; si.n_pts = si.n_raw; return; }  // pass-through (treated like the overflow copy)
+  if (si.n_finite == 0) { si.n_pts = 0; si.overflow = 0; return; }
+  const float inv = __fdiv_rn(1.0f, leaf);
+  si.inv_leaf = inv;
+  const long long dx = (long long)__fmul_rn(__fsub_rn(si.bb_max[0], si.bb_min[0]), inv) + 1;
+  const long long dy = (long long)__fmul_rn(__fsub_rn(si.bb_max[1], si.bb_min[1]), inv) + 1;
+  const long long dz = (long long)__fmul_rn(__fsub_rn(si.bb_max[2], si.bb_min[2]), inv) + 1;
+  if (dx * dy * dz > 2147483647ll) { si.overflow = 1; si.n_pts = si.n_raw; return; }  // "output = *input_"
+  int div_b[3];
+  for (int a = 0; a < 3; ++a) {
+    si.min_b[a] = (int)floorf(__fmul_rn(si.bb_min[a], inv));
+    const int max_b = (int)floorf(__fmul_rn(si.bb_max[a], inv));
+    div_b[a] = max_b - si.min_b[a] + 1;
+  }
+  si.mul1 = (uint32_t)div_b[0];
+  si.mul2 = (uint32_t)div_b[0] * (uint32_t)div_b[1];
+  si.overflow = 0;
+}
+
+// A.1 step 5
+__global__ void __launch_bounds__(kSortThreads) voxel_keys_kernel(const SlotInfo* __restrict__ slots, TileMap tm, uint32_t* __restrict__ keys) {
+  const uint32_t t = blockIdx.x;
+  const uint32_t slot = tm.tile_slot[t], first = tm.tile_first[t];
+  const SlotInfo& si = slots[slot];
+  if (si.overflow) return;
+  const float inv = si.inv_leaf;
+  const float mb0 = (float)si.min_b[0], mb1 = (float)si.min_b[1], mb2 = (float)si.min_b[2];
+#pragma unroll
+  for (int j = 0; j < kSortTile / kSortThreads; ++j) {
+    const uint32_t e = first + j * kSortThreads + threadIdx.x;
+    if (e < si.n_raw) {
+      const float4 v = si.raw[e];
+      uint32_t key = kInvalidKey;
+      if (finite3(v.x, v.y, v.z)) {
+        const int i0 = (int)__fsub_rn(floorf(__fmul_rn(v.x, inv)), mb0);
+        const int i1 = (int)__fsub_rn(floorf(__fmul_rn(v.y, inv)), mb1);
+        const int i2 = (int)__fsub_rn(floorf(__fmul_rn(v.z, inv)), mb2);
+        key = (uint32_t)i0 + (uint32_t)i1 * si.mul1 + (uint32_t)i2 * si.mul2;
+      }
+      keys[si.off + e] = key;
+    }
+  }
+}
+
+// run starts among the first n_finite sorted keys -> count per tile
+__global__ void __launch_bounds__(kSortThreads) voxel_heads_kernel(const SlotInfo* __restrict__ slots, TileMap tm,
+                                                                    const uint32_t* __restrict__ keys, uint32_t* __restrict__ tile_heads) {
+  __shared__ uint32_t wsum[8];
+  const uint32_t t = blockIdx.x;
+  const uint32_t slot = tm.tile_slot[t], first = tm.tile_first[t];
+  const SlotInfo& si = slots[slot];
+  if (si.overflow) return;
+  const uint32_t n = si.n_finite;
+  const uint32_t* k = keys + si.off;
+  uint32_t c = 0;
+#pragma unroll
+  for (int j = 0; j < kSortTile / kSortThreads; ++j) {
+    const uint32_t e = first + j * kSortThreads + threadIdx.x;
+    if (e < n) c += (e == 0 || k[e] != k[e - 1]) ? 1u : 0u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t s = 0; for (int i = 0; i < 8; ++i) s += wsum[i]; tile_heads[t] = s; }
+}
+
+// exclusive scan of the tile counts of each slot (one warp per slot); n_pts = number of voxels
+__global__ void voxel_scan_kernel(SlotInfo* __restrict__ slots, uint32_t n_slots, const uint32_t* __restrict__ slot_tile_begin,
+                                  uint32_t* __restrict__ tile_heads) {
+  const uint32_t s = blockIdx.x;
+  if (s >= n_slots) return;
+  SlotInfo& si = slots[s];
+  if (si.overflow) return;
+  const uint32_t ntiles = (si.n_finite + kSortTile - 1) / kSortTile;
+  uint32_t* h = tile_heads + slot_tile_begin[s];
+  const int lane = threadIdx.x;
+  uint32_t running = 0;
+  for (uint32_t b = 0; b < ntiles; b += 32) {
+    const uint32_t t = b + lane;
+    const uint32_t v = t < ntiles ? h[t] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += u; }
+    if (t < ntiles) h[t] = running + incl - v;
+    running += __shfl_sync(0xFFFFFFFFu, incl, 31);
+  }
+  if (lane == 0) si.n_pts = running;
+}
+
+// A.1 steps 8-9: float centroid per run, in ascending input order, written in ascending key order.
+__global__ void __launch_bounds__(kSortThreads) voxel_centroid_kernel(const SlotInfo* __restrict__ slots, TileMap tm,
+                                                                       const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                                       const uint32_t* __restrict__ tile_heads, float4* __restrict__ work) {
+  __shared__ uint32_t wsum[8];
+  const uint32_t t = blockIdx.x;
+  const uint32_t slot = tm.tile_slot[t], first = tm.tile_first[t];
+  const SlotInfo& si = slots[slot];
+  if (si.overflow) return;
+  const uint32_t n = si.n_finite;
+  if (first >= n) return;
+  const uint32_t* k = keys + si.off;
+  const uint32_t* v = vals + si.off;
+  const float4* raw = si.raw;
+  constexpr int kPer = kSortTile / kSortThreads;
+  const uint32_t e0 = first + threadIdx.x * kPer;  // kPer consecutive sorted positions per thread
+  uint32_t head_mask = 0, cnt = 0;
+  uint32_t prev = (e0 > 0 && e0 < n) ? k[e0 - 1] : 0u;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const uint32_t e = e0 + j;
+    if (e < n) {
+      const uint32_t kk = k[e];
+      if (e == 0 || kk != prev) { head_mask |= 1u << j; ++cnt; }
+      prev = kk;
+    }
+  }
+  // block exclusive scan of cnt
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += u; }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  uint32_t rank = tile_heads[t] + incl - cnt;
+  for (int i = 0; i < w; ++i) rank += wsum[i];
+  float4* out = work + si.off;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    if (!(head_mask & (1u << j))) continue;
+    const uint32_t e = e0 + j;
+    const uint32_t kk = k[e];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    uint32_t l = e;
+    do {
+      const float4 p = raw[v[l]];
+      sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z);
+      ++l;
+    } while (l < n && k[l] == kk);
+    const float c = (float)(l - e);
+    out[rank++] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), 1.0f);
+  }
+}
+
+// overflow / pass-through slots: working cloud = raw cloud verbatim
+__global__ void __launch_bounds__(kSortThreads) voxel_passthrough_kernel(const SlotInfo* __restrict__ slots, TileMap tm, float4* __restrict__ work) {
+  const uint32_t t = blockIdx.x;
+  const uint32_t slot = tm.tile_slot[t], first = tm.tile_first[t];
+  const SlotInfo& si = slots[slot];
+  if (!si.overflow) return;
+#pragma unroll
+  for (int j = 0; j < kSortTile / kSortThreads; ++j) {
+    const uint32_t e = first + j * kSortThreads + threadIdx.x;
+    if (e < si.n_raw) work[si.off + e] = si.raw[e];
+  }
+}
+
+void launch_bbox(Workspace& ws, int which) {
+  TileMap tm{ws.tile_slot.as<uint32_t>(), ws.tile_first.as<uint32_t>(), ws.n_tiles};
+  bbox_kernel<<<ws.n_tiles, kSortThreads, 0, ws.stream>>>(ws.slots.as<SlotInfo>(), tm, ws.work.as<float4>(), which);
+  ++ws.launches;
+}
+
+void run_voxel(Workspace& ws, float leaf, uint32_t* leaf_keys) {
+  if (ws.n_tiles == 0) {  // all clouds empty: n_pts stays 0
+    return;
+  }
+  cudaStream_t st = ws.stream;
+  SlotInfo* slots = ws.slots.as<SlotInfo>();
+  TileMap tm{ws.tile_slot.as<uint32_t>(), ws.tile_first.as<uint32_t>(), ws.n_tiles};
+  launch_bbox(ws, kCountRaw);
+  voxel_params_kernel<<<(ws.n_slots + 63) / 64, 64, 0, st>>>(slots, ws.n_slots, leaf);
+  ++ws.launches;
+  if (leaf > 0.f) {
+    uint32_t* keys[2] = {ws.keys0.as<uint32_t>(), ws.keys1.as<uint32_t>()};
+    uint32_t* vals[2] = {ws.vals0.as<uint32_t>(), ws.vals1.as<uint32_t>()};
+    if (leaf_keys) S3D_CUDA(cudaMemsetAsync(keys[0], 0xFF, 4 * size_t(ws.total), st));  // skipped / overflow points report 0xFFFFFFFF
+    voxel_keys_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, keys[0]);
+    ++ws.launches;
+    if (leaf_keys) S3D_CUDA(cudaMemcpyAsync(leaf_keys, keys[0], 4 * size_t(ws.total), cudaMemcpyDeviceToDevice, st));
+    radix_sort_segmented(st, slots, ws.n_slots, tm, ws.slot_tile_begin.as<uint32_t>(), keys, vals, ws.hist.as<uint32_t>(), 4, kCountRaw, &ws.launches);
+    voxel_heads_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, keys[0], ws.tile_heads.as<uint32_t>());
+    voxel_scan_kernel<<<ws.n_slots, 32, 0, st>>>(slots, ws.n_slots, ws.slot_tile_begin.as<uint32_t>(), ws.tile_heads.as<uint32_t>());
+    voxel_centroid_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, keys[0], vals[0], ws.tile_heads.as<uint32_t>(), ws.work.as<float4>());
+    ws.launches += 3;
+  }
+  voxel_passthrough_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.work.as<float4>());
+  ++ws.launches;
+  S3D_CUDA(cudaGetLastError());
+}
+
+}  // namespace s3d

@@ -1,0 +1,121 @@
+"""CUDA align() (s3d_gicp_align / _batch) against the CPU oracle and the frozen fixtures.
+
+Gates (BASELINE.json north_star / SURVEY 8d): pose within 1e-4 m / 1e-4 rad, fitness relative error <= 1e-4,
+identical accept/reject decision."""
+import numpy as np
+import pytest
+
+from conftest import pose_delta
+from slam3d_b200 import _abi
+from slam3d_b200._abi import RegistrationParameters
+
+pytestmark = pytest.mark.gpu
+TOL_T, TOL_R, TOL_FIT = 1e-4, 1e-4, 1e-4
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import slam3d_b200
+    c = slam3d_b200.Context()
+    yield c
+    c.close()
+
+
+def check(got, want):
+    assert got.status == want.status
+    assert (got.n_source, got.n_target) == (want.n_source, want.n_target)
+    if want.status == _abi.S3D_TOO_FEW_POINTS:
+        return
+    dt, dr = pose_delta(want.pose(), got.pose())
+    assert dt < TOL_T and dr < TOL_R, (dt, dr)
+    assert abs(got.fitness - want.fitness) <= TOL_FIT * max(abs(want.fitness), 1e-12)
+    assert got.converged == want.converged
+
+
+@pytest.mark.parametrize("density", [0.1, 0.2])
+def test_kitti_pairs_vs_golden(ctx, kitti, golden, density):
+    p = RegistrationParameters.defaults(point_cloud_density=density)
+    for a, b in ((0, 1), (1, 2), (2, 3)):
+        g = golden["align"][f"cloud{a+1}->cloud{b+1}@{density}"]
+        r = ctx.gicp_align(kitti[a], kitti[b], None, p)
+        assert r.status == g["status"] and r.converged == g["converged"]
+        assert (r.n_source, r.n_target) == (g["n_source"], g["n_target"])
+        dt, dr = pose_delta(g["T"], r.pose())
+        assert dt < TOL_T and dr < TOL_R, (dt, dr)
+        assert abs(r.fitness - g["fitness"]) <= TOL_FIT * g["fitness"]
+        assert abs(r.outer_iterations - g["outer_iterations"]) <= 1
+        assert abs(int(r.n_correspondences) - g["n_correspondences"]) <= 3
+
+
+def test_synthetic_pair_vs_oracle(ctx, oracle_mod):
+    from slam3d_b200 import synth
+    src, tgt, truth = synth.scan_pair(seed=20260117)
+    p = RegistrationParameters.defaults(point_cloud_density=0.1)
+    got = ctx.gicp_align(src, tgt, None, p)
+    want = oracle_mod.gicp_align(src, tgt, None, p)
+    check(got, want)
+    dt, dr = pose_delta(truth, got.pose())
+    assert dt < 0.02 and dr < 3e-3
+    guess = truth.copy(); guess[:3, 3] += [0.05, -0.03, 0.01]
+    check(ctx.gicp_align(src, tgt, guess, p), oracle_mod.gicp_align(src, tgt, guess, p))
+
+
+def test_gates_match_oracle(ctx, oracle_mod, kitti):
+    src, tgt = kitti[0][::4], kitti[1][::4]
+    cases = [
+        dict(point_cloud_density=0.5),
+        dict(point_cloud_density=0.5, max_fitness_score=1e-6),
+        dict(point_cloud_density=0.5, max_translation=0.1),
+        dict(point_cloud_density=0.5, maximum_iterations=1),
+        dict(point_cloud_density=0.5, maximum_iterations=3, max_correspondence_distance=1.0),
+        dict(point_cloud_density=0.5, correspondence_randomness=10),
+        dict(point_cloud_density=0.5, maximum_optimizer_iterations=1),
+        dict(point_cloud_density=0.5, rotation_epsilon=1e-5, transformation_epsilon=1e-7),
+    ]
+    for kw in cases:
+        p = RegistrationParameters.defaults(**kw)
+        check(ctx.gicp_align(src, tgt, None, p), oracle_mod.gicp_align(src, tgt, None, p))
+    r = ctx.gicp_align(src[:500], tgt[:500], None, RegistrationParameters.defaults(point_cloud_density=20.0))
+    assert r.status == _abi.S3D_TOO_FEW_POINTS
+    for alg in (_abi.ALG_ICP, _abi.ALG_GICP_OMP, _abi.ALG_NDT, _abi.ALG_NDT_OMP, 17):
+        r = ctx.gicp_align(src, tgt, None, RegistrationParameters.defaults(point_cloud_density=0.5, registration_algorithm=alg))
+        assert r.status == _abi.S3D_UNKNOWN_ALGORITHM
+    # too few points wins over the algorithm switch (:134 before :139)
+    r = ctx.gicp_align(src[:500], tgt[:500], None, RegistrationParameters.defaults(point_cloud_density=20.0, registration_algorithm=_abi.ALG_NDT))
+    assert r.status == _abi.S3D_TOO_FEW_POINTS
+    # density <= 0 skips the filter (:127)
+    p = RegistrationParameters.defaults(point_cloud_density=0.0)
+    got, want = ctx.gicp_align(src[::8], tgt[::8], None, p), oracle_mod.gicp_align(src[::8], tgt[::8], None, p)
+    check(got, want)
+    assert got.n_source == src[::8].shape[0]
+    # empty input
+    r = ctx.gicp_align(np.zeros((0, 3), np.float32), tgt, None, RegistrationParameters.defaults())
+    assert r.status == _abi.S3D_TOO_FEW_POINTS
+
+
+def test_batch_equals_single_and_is_deterministic(ctx, kitti):
+    p = RegistrationParameters.defaults(point_cloud_density=0.2)
+    srcs = [kitti[0], kitti[1], kitti[2], kitti[0][:50], kitti[1][::2]]
+    tgts = [kitti[1], kitti[2], kitti[3], kitti[1], kitti[2][::2]]
+    batch = ctx.gicp_align_batch(srcs, tgts, None, p)
+    again = ctx.gicp_align_batch(srcs[::-1], tgts[::-1], None, p)[::-1]
+    for i, (s, t) in enumerate(zip(srcs, tgts)):
+        one = ctx.gicp_align(s, t, None, p)
+        for r in (batch[i], again[i]):
+            assert r.status == one.status and r.outer_iterations == one.outer_iterations
+            assert np.array_equal(r.pose(), one.pose())   # bit-identical, independent of batch composition
+            assert r.fitness == one.fitness
+    assert batch[3].status == _abi.S3D_TOO_FEW_POINTS
+
+
+def test_loop_closure_style_coarse_then_fine(ctx, oracle_mod):
+    """createConstraint(loop=true): coarse align feeds the fine align (PointCloudSensor.cpp:286-292)."""
+    from slam3d_b200 import synth
+    src, tgt, truth = synth.scan_pair(seed=5, loop=True)
+    coarse = RegistrationParameters.defaults(point_cloud_density=0.5, max_correspondence_distance=5.0, max_translation=5.0, max_rotation=1.0)
+    fine = RegistrationParameters.defaults(point_cloud_density=0.2, max_translation=5.0)
+    gc, oc = ctx.gicp_align(src, tgt, None, coarse), oracle_mod.gicp_align(src, tgt, None, coarse)
+    check(gc, oc)
+    gf, of = ctx.gicp_align(src, tgt, gc.pose(), fine), oracle_mod.gicp_align(src, tgt, oc.pose(), fine)
+    if of.status == 0:
+        check(gf, of)
