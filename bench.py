@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py — GICP registrations/s on 131 072-point synthetic LiDAR scan pairs (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            our arm  (libs3d_b200.so, hand-written sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  reference arm (the CPU oracle on the box's host cores)
+
+One "step" = one call of s3d_gicp_align_batch on `--pairs` independent scan pairs (consecutive-scan odometry:
+voxel filter 0.1 m x2, NN grids, kNN-20 covariances x2, GICP loop, fitness, gates — the whole align()).
+  value  whole-job registrations/s with the raw scans already resident in HBM (device pointers);
+  e2e    the same call with HOST (pinned) scan buffers: H2D of both scans and D2H of the results inside the timing.
+Multi-GPU (torchrun): every rank runs the same per-GPU batch on its own GPU (independent registrations, no data-path
+collective; weak scaling); elapsed = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gicp_registrations_per_s_131k_pt_pairs"
+UNIT = "registrations/s"
+N_POINTS = 131072
+VOXEL = 0.1
+
+
+def make_pairs(n_distinct, seed0=20260117):
+    from slam3d_b200 import synth
+    pairs = []
+    for i in range(n_distinct):
+        s, t, truth = synth.scan_pair(seed=seed0 + i)
+        pairs.append((s, t, truth))
+    return pairs
+
+
+def params():
+    from slam3d_b200._abi import RegistrationParameters
+    return RegistrationParameters.defaults(point_cloud_density=VOXEL)  # 2.5 m corr. distance, 50 iterations, default epsilons
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.stop = threading.Event()
+        self.th = None
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the CPU implementation of the path (oracle port; real PCL is not installable)."""
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    threads = oracle.max_threads()
+    n = max(1, min(threads, 8))
+    pairs = make_pairs(min(n, 4))
+    srcs = [pairs[i % len(pairs)][0] for i in range(n)]
+    tgts = [pairs[i % len(pairs)][1] for i in range(n)]
+    p = params()
+    for _ in range(min(args.warmup, 1)):
+        oracle.gicp_align_batch(srcs, tgts, None, p, n_threads=threads)
+    t0 = time.perf_counter()
+    done = 0
+    steps = max(1, args.steps)
+    for _ in range(steps):
+        res = oracle.gicp_align_batch(srcs, tgts, None, p, n_threads=threads)
+        done += len(res)
+        if time.perf_counter() - t0 > 120:
+            steps = _ + 1
+            break
+    dt = time.perf_counter() - t0
+    value = done / dt
+    sample = f"{n} pairs per step on {threads} host threads (one pair per thread), {steps} steps, oracle port of PCL GICP"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64",
+        "data": "synthetic", "config": {"workload": "synthetic 64-beam LiDAR scan pair, 131072 points, 0.1 m voxel, GICP odometry",
+                                        "pairs_per_step": n, "ms_per_align_per_thread": 1e3 * dt * min(threads, n) / done},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline_leg():
+    """Bounded CPU sample of the same workload on the host cores (rank 0, N=1 only)."""
+    import oracle
+    oracle.build()
+    threads = oracle.max_threads()
+    n = max(1, min(threads, 8))
+    pairs = make_pairs(2, seed0=20260117)
+    srcs = [pairs[i % 2][0] for i in range(n)]
+    tgts = [pairs[i % 2][1] for i in range(n)]
+    p = params()
+    t0 = time.perf_counter()
+    one = oracle.gicp_align(srcs[0], tgts[0], None, p)
+    t1 = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    rounds = 0
+    while True:
+        oracle.gicp_align_batch(srcs, tgts, None, p, n_threads=threads)
+        rounds += 1
+        if time.perf_counter() - t0 > 8 or rounds >= 4:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": rounds * n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{rounds} x {n} pairs, one pair per host thread ({threads} threads); single-thread align = {1e3 * t1:.0f} ms "
+                      f"({one.outer_iterations} outer iterations)",
+            "single_thread_ms_per_align": 1e3 * t1}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--pairs", type=int, default=32, help="scan pairs per step and per GPU")
+    ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic scenes to cycle through")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import slam3d_b200
+    from slam3d_b200 import _abi
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = slam3d_b200.Context([local_rank])
+    p = params()
+
+    # ---- synthetic input: `distinct` scenes, cycled to `pairs` per step; every rank gets different scenes -----------------
+    pairs = make_pairs(args.distinct, seed0=20260117 + 1000 * rank)
+    B = args.pairs
+    host_src, host_tgt, dev_src, dev_tgt = [], [], [], []
+    for i in range(B):
+        s, t, _ = pairs[i % len(pairs)]
+        hs = torch.from_numpy(slam3d_b200.as_xyzw(s)).pin_memory()
+        ht = torch.from_numpy(slam3d_b200.as_xyzw(t)).pin_memory()
+        host_src.append(hs); host_tgt.append(ht)
+        dev_src.append(hs.cuda()); dev_tgt.append(ht.cuda())
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(0), device=torch.device("cuda", local_rank))
+
+    def timed(srcs, tgts, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0 = ctx.counters()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        last = None
+        for _ in range(steps):
+            last = ctx.gicp_align_batch(srcs, tgts, None, p)
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        c1 = ctx.counters()
+        el = torch.tensor([max(ms, 1e3 * wall)], device="cuda", dtype=torch.float64)  # the call is synchronous: device span <= wall
+        ev = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ev, op=dist.ReduceOp.MAX)
+        return float(ev.item()), float(el.item()), {k: c1[k] - c0[k] for k in c0}, last
+
+    # ---- warm-up, then EXACTLY K timed steps with device-resident inputs --------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        ctx.gicp_align_batch(dev_src, dev_tgt, None, p)
+    ctx.set_profiling(True)
+    ctx.stage_times(reset=True)
+    with ClockSampler(local_rank) as clk:
+        ev_ms, wall_ms, cnt, last = timed(dev_src, dev_tgt, args.steps)
+    stages = ctx.stage_times(reset=True)
+    ctx.set_profiling(False)
+    ok = sum(1 for r in last if r.status == _abi.S3D_OK)
+    value = world * B * args.steps / (wall_ms / 1e3)
+
+    # ---- end to end: host (pinned) buffers in, results out, same call --------------------------------------------------------
+    for _ in range(2):
+        ctx.gicp_align_batch(host_src, host_tgt, None, p)
+    e2e_ev, e2e_wall, e2e_cnt, _ = timed(host_src, host_tgt, args.steps)
+    e2e_value = world * B * args.steps / (e2e_wall / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    dom = max(stages, key=lambda k: stages[k]["ms"])
+    iters_total = sum(r.outer_iterations for r in last) * args.steps       # iter-kernel work units (pair-iterations) in the region
+    m_tgt = float(np.mean([r.n_target for r in last]))
+    m_src = float(np.mean([r.n_source for r in last]))
+    # algorithmic bytes (SURVEY 8d with 24-byte normals instead of 48-byte covariances):
+    bytes_by_stage = {
+        "gicp_iter": 80.0 * m_tgt * iters_total,                                  # 16+24 moving point/normal, 16+24 gathered fixed point/normal
+        "knn_cov": 40.0 * (m_tgt + m_src) * B * args.steps,                      # 16 read + 24 written per point
+        "voxel": (16.0 * 2 * N_POINTS + 16.0 * (m_tgt + m_src)) * B * args.steps,
+        "grid": 36.0 * (m_tgt + m_src) * B * args.steps,
+        "fitness": 32.0 * m_tgt * B * args.steps,
+        "gicp_solve": 74 * 8.0 * (m_tgt / 256.0) * iters_total,
+    }
+    dom_ms = stages[dom]["ms"]
+    dom_launches = max(stages[dom]["launches"], 1)
+    achieved = bytes_by_stage[dom] / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "avg_launch_us": 1e3 * dom_ms / dom_launches, "launches": dom_launches,
+                "algorithmic_bytes_per_launch": bytes_by_stage[dom] / dom_launches,
+                "stage_ms_per_step": {k: v["ms"] / args.steps for k, v in stages.items()},
+                "note": "working set of a pair (~10 MB) is L2 resident; kernels are latency/L2 bound, see DESIGN.md"}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64",
+        "data": "synthetic",
+        "config": {"workload": "synthetic 64-beam LiDAR scan pair, 131072 points, 0.1 m voxel, GICP odometry (BASELINE.json configs[1])",
+                   "pairs_per_step_per_gpu": B, "distinct_scenes": args.distinct, "ms_per_align": wall_ms / args.steps / B,
+                   "l2": f"inputs larger than L2: {B} pairs x 4.2 MB raw + ~50 MB working set per pair per step",
+                   "registrations_ok": ok, "mean_outer_iterations": float(np.mean([r.outer_iterations for r in last])),
+                   "filtered_points": [int(m_src), int(m_tgt)], "device_event_ms_per_step": ev_ms / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_cnt["h2d_bytes"] // args.steps,
+                "d2h_bytes_per_step": e2e_cnt["d2h_bytes"] // args.steps, "ms_per_step": e2e_wall / args.steps},
+        "gpu_launches": cnt["kernel_launches"],
+        "clocks": clk.summary(),
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_leg()
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -132,6 +132,13 @@ void* s3d_context_stream(s3d_context* ctx, int device_slot);
 typedef struct s3d_counters { uint64_t kernel_launches, h2d_bytes, d2h_bytes; } s3d_counters;
 int s3d_get_counters(s3d_context* ctx, s3d_counters* out);
 
+/* Optional per-stage device timing (CUDA events on the launching stream, read back at the call's final
+ * synchronisation).  Stage ids: 0 voxel filter, 1 NN grid build, 2 kNN+covariances, 3 GICP correspondence/
+ * linearisation kernel, 4 GICP solve kernel, 5 fitness.  ms[i] / launches[i] accumulate since the last reset. */
+#define S3D_N_STAGES 6
+int s3d_set_profiling(s3d_context* ctx, int enabled);
+int s3d_get_stage_times(s3d_context* ctx, double ms[S3D_N_STAGES], uint64_t launches[S3D_N_STAGES], int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,8 @@ def lib():
         L.s3d_create_context.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.s3d_destroy_context.argtypes = [C.c_void_p]
         L.s3d_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+        L.s3d_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.s3d_get_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.s3d_voxel_downsample.argtypes = [C.c_void_p, Cloud, C.c_float, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_int32)]
         L.s3d_knn_covariances.argtypes = [C.c_void_p, Cloud, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.s3d_nearest_neighbors.argtypes = [C.c_void_p, Cloud, Cloud, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -105,6 +107,17 @@ class Context:
 
     def stream_handle(self, slot=0):
         return lib().s3d_context_stream(self._h, slot)
+
+    STAGES = ("voxel", "grid", "knn_cov", "gicp_iter", "gicp_solve", "fitness")
+
+    def set_profiling(self, enabled):
+        lib().s3d_set_profiling(self._h, int(bool(enabled)))
+
+    def stage_times(self, reset=True):
+        ms = (C.c_double * 6)()
+        n = (C.c_uint64 * 6)()
+        lib().s3d_get_stage_times(self._h, ms, n, int(reset))
+        return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(self.STAGES)}
 
     def counters(self):
         c = Counters()

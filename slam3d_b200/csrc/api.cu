@@ -32,6 +32,9 @@ struct s3d_context {
   std::vector<std::unique_ptr<s3d::DeviceCtx>> devs;
   std::mutex mu;
   uint64_t launches = 0, h2d = 0, d2h = 0;
+  bool profiling = false;
+  double stage_ms[S3D_N_STAGES] = {0, 0, 0, 0, 0, 0};
+  uint64_t stage_launches[S3D_N_STAGES] = {0, 0, 0, 0, 0, 0};
   int max_pairs_per_launch = 32;
 };
 
@@ -46,12 +49,18 @@ struct WsLease {
       if (!dc->pool.empty()) { ws = std::move(dc->pool.back()); dc->pool.pop_back(); }
     }
     if (!ws) { ws.reset(new Workspace()); ws->init(dc->device); std::lock_guard<std::mutex> g(dc->mu); dc->all.push_back(ws.get()); }
+    ws->profiling = ctx->profiling;
   }
   ~WsLease() {
     {
       std::lock_guard<std::mutex> g(ctx->mu);
       ctx->launches += ws->launches; ctx->h2d += ws->h2d; ctx->d2h += ws->d2h;
       ws->launches = ws->h2d = ws->d2h = 0;
+      if (ws->profiling) { cudaStreamSynchronize(ws->stream); ws->collect_spans(); }
+      for (int i = 0; i < S3D_N_STAGES; ++i) {
+        ctx->stage_ms[i] += ws->stage_ms[i]; ctx->stage_launches[i] += ws->stage_launches[i];
+        ws->stage_ms[i] = 0; ws->stage_launches[i] = 0;
+      }
     }
     std::lock_guard<std::mutex> g(dc->mu);
     dc->pool.push_back(std::move(ws));
@@ -203,6 +212,24 @@ int s3d_get_counters(s3d_context* ctx, s3d_counters* out) {
   if (!ctx || !out) return S3D_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(ctx->mu);
   out->kernel_launches = ctx->launches; out->h2d_bytes = ctx->h2d; out->d2h_bytes = ctx->d2h;
+  return S3D_OK;
+}
+
+int s3d_set_profiling(s3d_context* ctx, int enabled) {
+  if (!ctx) return S3D_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->profiling = enabled != 0;
+  return S3D_OK;
+}
+
+int s3d_get_stage_times(s3d_context* ctx, double ms[S3D_N_STAGES], uint64_t launches[S3D_N_STAGES], int reset) {
+  if (!ctx) return S3D_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  for (int i = 0; i < S3D_N_STAGES; ++i) {
+    if (ms) ms[i] = ctx->stage_ms[i];
+    if (launches) launches[i] = ctx->stage_launches[i];
+    if (reset) { ctx->stage_ms[i] = 0; ctx->stage_launches[i] = 0; }
+  }
   return S3D_OK;
 }
 

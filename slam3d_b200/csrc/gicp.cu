@@ -14,6 +14,9 @@
 // are bit-reproducible run to run and independent of batch composition.
 // Roofline: per iteration 16 B (moving point) + 32 B (its normal) + gathered 16 B + 32 B (fixed point + normal) per
 // correspondence; the working set is L2 resident, the kernel is latency bound on the hash probes.
+#include <cstdio>
+#include <cstdlib>
+
 #include "internal.h"
 #include "nn_search.cuh"
 
@@ -334,26 +337,45 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   ++ws.launches;
   // PCL's loop is a do-while: with maximum_iterations <= 0 it still runs one iteration
   const int iters = std::max(max_iter, 1);
+  const bool trace = getenv("S3D_TRACE") != nullptr;
   for (int it = 0; it < iters; ++it) {
-    gicp_iter_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.hash.as<HashEntry>(), ws.gpts.as<float4>(), ws.moved.as<float4>(),
-                                                 ws.normals.as<double4>(), ws.prev_nn.as<uint32_t>(), ws.moments.as<double>());
-    gicp_solve_kernel<<<np, 256, 0, st>>>(slots, pairs, ws.moments.as<double>(), tiles_per_pair, flags);
-    ws.launches += 2;
+    {
+      StageTimer timer(ws, kStageIter);
+      gicp_iter_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.hash.as<HashEntry>(), ws.gpts.as<float4>(), ws.moved.as<float4>(),
+                                                   ws.normals.as<double4>(), ws.prev_nn.as<uint32_t>(), ws.moments.as<double>());
+      ++ws.launches;
+    }
+    {
+      StageTimer timer(ws, kStageSolve);
+      gicp_solve_kernel<<<np, 256, 0, st>>>(slots, pairs, ws.moments.as<double>(), tiles_per_pair, flags);
+      ++ws.launches;
+    }
     S3D_CUDA(cudaMemcpyAsync(h_flags, flags, 16, cudaMemcpyDeviceToHost, st));
     S3D_CUDA(cudaStreamSynchronize(st));
     ws.d2h += 16;
+    if (trace) {
+      S3D_CUDA(cudaMemcpy(hp, pairs, sizeof(PairState) * np, cudaMemcpyDeviceToHost));
+      for (uint32_t p = 0; p < np; ++p)
+        fprintf(stderr, "[s3d trace] it=%d pair=%u active=%d outer=%d inner=%d ncorr=%u t=(%.9g %.9g %.9g) r10=%.9g r20=%.9g r21=%.9g\n", it, p,
+                hp[p].active, hp[p].outer_iterations, hp[p].inner_iterations, hp[p].n_corr, hp[p].T[12], hp[p].T[13], hp[p].T[14], hp[p].T[1],
+                hp[p].T[2], hp[p].T[6]);
+    }
     if (h_flags[1] <= 0) break;
   }
-  gicp_fitness_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.hash.as<HashEntry>(), ws.gpts.as<float4>(), ws.prev_nn.as<uint32_t>(),
-                                                  ws.fit_partial.as<double>());
-  gicp_fitness_reduce_kernel<<<(np + 63) / 64, 64, 0, st>>>(slots, pairs, ws.fit_partial.as<double>(), tiles_per_pair, np);
-  ws.launches += 2;
+  {
+    StageTimer timer(ws, kStageFitness);
+    gicp_fitness_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.hash.as<HashEntry>(), ws.gpts.as<float4>(), ws.prev_nn.as<uint32_t>(),
+                                                    ws.fit_partial.as<double>());
+    gicp_fitness_reduce_kernel<<<(np + 63) / 64, 64, 0, st>>>(slots, pairs, ws.fit_partial.as<double>(), tiles_per_pair, np);
+    ws.launches += 2;
+  }
   S3D_CUDA(cudaMemcpyAsync(hp, pairs, sizeof(PairState) * np, cudaMemcpyDeviceToHost, st));
   SlotInfo* hs = ws.h_slots.as<SlotInfo>();
   S3D_CUDA(cudaMemcpyAsync(hs, slots, sizeof(SlotInfo) * ws.n_slots, cudaMemcpyDeviceToHost, st));
   S3D_CUDA(cudaMemcpyAsync(h_flags, flags, 16, cudaMemcpyDeviceToHost, st));
   S3D_CUDA(cudaStreamSynchronize(st));
   ws.d2h += sizeof(PairState) * np + sizeof(SlotInfo) * ws.n_slots + 16;
+  ws.collect_spans();
   if (h_flags[0] & kErrHashArena) throw CudaError{"hash arena too small"};
   for (uint32_t p = 0; p < np; ++p) {
     const s3d_registration_parameters& cfg = params[p];

@@ -12,8 +12,10 @@
 // B200-first design note: f is a quadratic form in the 12 entries of W = [R | t]:
 //     m f = sum_ab w_a^T S_ab w_b - 2 sum_a v_a^T w_a + s0,   w_a = row a of W,  phi = (p, 1)
 //     S_ab = sum_i M_i[a][b] phi_i phi_i^T  (6 x 10 unique),  v_a = sum_i (M_i q_i)[a] phi_i  (3 x 4),  s0 = sum q^T M q.
-// Deviation from PCL (documented in DESIGN.md): PCL forms r from a float32 transform of p; here r is exact in
-// double.  Effect on the final pose < 1e-6 m (sensitivity probe 2).
+// PCL evaluates r with T(x) rounded to float32 (applyState builds a Matrix4f).  That rounding is systematic over all
+// points and decides when PCL's inner loop stops (gradient tolerance 1e-2, "no improvement"), so it is mirrored:
+// W is rounded to float before the quadratic form is evaluated.  Not mirrored (documented in DESIGN.md): the
+// per-point float rounding of T*p itself, which is zero-mean and contributes < 2e-5 to the gradient norm.
 #pragma once
 
 #include <math.h>
@@ -127,10 +129,12 @@ S3D_HD void matrix_from_state(const double x[6], float T[16]) {
   T[12] = (float)x[0]; T[13] = (float)x[1]; T[14] = (float)x[2]; T[15] = 1.f;
 }
 
-// G[a][c] = d(m f)/dW[a][c] and F = m f from the moments, for W = [R | t].
+// G[a][c] = d(m f)/dW[a][c] and F = m f from the moments, for W = float([R | t]) (PCL's Matrix4f transformation).
 S3D_HD double moments_value_grad(const double* mom, const double (&R)[3][3], const double t[3], double (&G)[3][4], bool want_grad) {
   double W[3][4];
-  for (int a = 0; a < 3; ++a) { W[a][0] = R[a][0]; W[a][1] = R[a][1]; W[a][2] = R[a][2]; W[a][3] = t[a]; }
+  for (int a = 0; a < 3; ++a) {
+    W[a][0] = (double)(float)R[a][0]; W[a][1] = (double)(float)R[a][1]; W[a][2] = (double)(float)R[a][2]; W[a][3] = (double)(float)t[a];
+  }
   double F = mom[72];
   for (int a = 0; a < 3; ++a) {
     double SW[4] = {0, 0, 0, 0};  // sum_b S_ab w_b

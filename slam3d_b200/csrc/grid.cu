@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(kSortThreads) hash_insert_kernel(const SlotInf
 void run_grid(Workspace& ws, float leaf_hint) {
   if (ws.n_tiles == 0) return;
   cudaStream_t st = ws.stream;
+  StageTimer timer(ws, kStageGrid);
   SlotInfo* slots = ws.slots.as<SlotInfo>();
   TileMap tm{ws.tile_slot.as<uint32_t>(), ws.tile_first.as<uint32_t>(), ws.n_tiles};
   // arena: ~1.2 cells per point is typical for lidar scans; 3 entries/point leaves 25% head-room at load factor 1/2

@@ -102,13 +102,33 @@ struct Workspace {
   DevBuf flags;                               // int32[4]: [0] error bits, [1] active pairs, [2] hash entries used
   PinnedBuf h_slots, h_pairs, h_small, h_tiles;  // pinned host mirrors
   uint64_t launches = 0, h2d = 0, d2h = 0;
-  std::vector<uint8_t> scratch;
+  // optional stage timing (s3d_set_profiling)
+  bool profiling = false;
+  struct Span { int stage; cudaEvent_t a, b; uint32_t n_launch; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
+  double stage_ms[S3D_N_STAGES] = {0, 0, 0, 0, 0, 0};
+  uint64_t stage_launches[S3D_N_STAGES] = {0, 0, 0, 0, 0, 0};
+  cudaEvent_t get_event();
+  void collect_spans();  // after a stream synchronise
 
   void init(int dev);
   void destroy();
 };
 
 enum ErrorBits { kErrHashArena = 1 };
+enum Stage { kStageVoxel = 0, kStageGrid = 1, kStageKnn = 2, kStageIter = 3, kStageSolve = 4, kStageFitness = 5 };
+
+// RAII: brackets the kernels launched in its scope with two events when profiling is on
+struct StageTimer {
+  Workspace& ws; int stage; uint64_t l0; cudaEvent_t a = nullptr;
+  StageTimer(Workspace& w, int s) : ws(w), stage(s), l0(w.launches) {
+    if (ws.profiling) { a = ws.get_event(); cudaEventRecord(a, ws.stream); }
+  }
+  ~StageTimer() {
+    if (a) { cudaEvent_t b = ws.get_event(); cudaEventRecord(b, ws.stream); ws.spans.push_back({stage, a, b, (uint32_t)(ws.launches - l0)}); }
+  }
+};
 
 // ---- stage launchers (each enqueues kernels on ws.stream; no host synchronisation inside) -----------------
 void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const std::vector<uint64_t>& sizes, uint32_t n_pairs);

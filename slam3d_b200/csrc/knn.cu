@@ -181,6 +181,7 @@ void run_knn_covariances(Workspace& ws, int k, uint32_t* knn_index, float* knn_d
   uint32_t max_n = 0;
   for (uint32_t s = 0; s < ws.n_slots; ++s) max_n = std::max(max_n, ws.h_n[s]);
   ws.normals.reserve(sizeof(double4) * std::max<size_t>(ws.total, 4));
+  StageTimer timer(ws, kStageKnn);
   dim3 grid((max_n + kKnnTile - 1) / kKnnTile, ws.n_slots);
   knn_cov_kernel<<<grid, kKnnWarps * 32, 0, ws.stream>>>(ws.slots.as<SlotInfo>(), ws.hash.as<HashEntry>(), ws.gpts.as<float4>(),
                                                          ws.work.as<float4>(), ws.normals.as<double4>(), k, knn_index, knn_dist2);

@@ -23,9 +23,29 @@ void Workspace::init(int dev) {
   h_small.reserve(4096);
 }
 
+cudaEvent_t Workspace::get_event() {
+  if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  S3D_CUDA(cudaEventCreate(&e));
+  return e;
+}
+
+void Workspace::collect_spans() {
+  for (Span& sp : spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { stage_ms[sp.stage] += ms; stage_launches[sp.stage] += sp.n_launch; }
+    else cudaGetLastError();
+    event_pool.push_back(sp.a); event_pool.push_back(sp.b);
+  }
+  spans.clear();
+}
+
 void Workspace::destroy() {
   cudaSetDevice(device);
   if (stream) cudaStreamSynchronize(stream);
+  collect_spans();
+  for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
+  event_pool.clear();
   DevBuf* bufs[] = {&slots, &pairs, &raw_stage, &work, &gpts, &keys0, &keys1, &vals0, &vals1, &hist, &tile_slot, &tile_first,
                     &slot_tile_begin, &tile_heads, &hash, &normals, &moved, &prev_nn, &moments, &iter_tile_pair, &iter_tile_first,
                     &fit_partial, &flags};
@@ -326,6 +346,7 @@ void run_voxel(Workspace& ws, float leaf, uint32_t* leaf_keys) {
     return;
   }
   cudaStream_t st = ws.stream;
+  StageTimer timer(ws, kStageVoxel);
   SlotInfo* slots = ws.slots.as<SlotInfo>();
   TileMap tm{ws.tile_slot.as<uint32_t>(), ws.tile_first.as<uint32_t>(), ws.n_tiles};
   launch_bbox(ws, kCountRaw);
