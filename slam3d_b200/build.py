@@ -42,7 +42,22 @@ def build(force=False, verbose=False):
                     raise RuntimeError("nvcc failed: " + " ".join(r.args))
     if jobs or not os.path.exists(LIB):
         subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"])
+    build_host(force or bool(jobs))
     return LIB
+
+
+HOST_LIB = os.path.join(HERE, "libs3d_host.so")
+
+
+def build_host(force=False):
+    """C++ host mirror of slam3d::PointCloudSensor (slam3d_b200/host) on top of the C-ABI library."""
+    hdir = os.path.join(HERE, "host")
+    srcs = [os.path.join(hdir, f) for f in ("PointCloudSensor.cpp", "host_capi.cpp")]
+    newest = max(os.path.getmtime(os.path.join(hdir, f)) for f in os.listdir(hdir))
+    if force or not os.path.exists(HOST_LIB) or os.path.getmtime(HOST_LIB) < newest:
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", HOST_LIB] + srcs +
+                              ["-L" + HERE, "-ls3d_b200", "-Wl,-rpath,$ORIGIN"])
+    return HOST_LIB
 
 
 if __name__ == "__main__":

@@ -1,0 +1,117 @@
+// PointCloudSensor.cpp — host mirror bodies; all arithmetic goes through the C-ABI (libs3d_b200.so, CUDA sm_100a).
+// Reference behaviour cited per function (slam3d/sensor/pcl/PointCloudSensor.cpp).
+#include "PointCloudSensor.hpp"
+
+#include <stdexcept>
+
+namespace slam3d_b200 {
+
+s3d_context* defaultContext() {
+  static std::once_flag once;
+  static s3d_context* ctx = nullptr;
+  static int status = S3D_OK;
+  static std::string err;
+  std::call_once(once, [] {
+    status = s3d_create_context(nullptr, 0, &ctx);
+    if (status != S3D_OK) err = s3d_last_error();
+  });
+  if (!ctx) throw std::runtime_error("slam3d_b200: cannot create CUDA context: " + err);
+  return ctx;
+}
+
+static s3d_cloud asCloud(const PointCloud::Ptr& c) {
+  s3d_cloud o;
+  o.xyzw = c && c->size() ? &c->points[0].x : nullptr;
+  o.n = c ? c->size() : 0;
+  return o;
+}
+
+// :119-174
+Transform align(PointCloudMeasurement::Ptr source, PointCloudMeasurement::Ptr target, const Transform& guess,
+                const RegistrationParameters& config, s3d_result* result_info) {
+  const s3d_registration_parameters c = config.toC();
+  s3d_result res;
+  const int st = s3d_gicp_align(defaultContext(), asCloud(source->getPointCloud()), asCloud(target->getPointCloud()), guess.data(), &c, &res);
+  if (result_info) *result_info = res;
+  switch (st) {
+    case S3D_OK: break;
+    case S3D_TOO_FEW_POINTS:        // :134-135
+    case S3D_NOT_CONVERGED:         // :74-77
+    case S3D_TOO_FAR_FROM_GUESS:    // :167-172
+      throw NoMatch(s3d_last_error());
+    case S3D_UNKNOWN_ALGORITHM:     // :158-164
+    default:
+      throw std::runtime_error(s3d_last_error());
+  }
+  Transform result;
+  for (int i = 0; i < 16; ++i) result.m[i] = res.T[i];
+  return result;
+}
+
+PointCloudSensor::PointCloudSensor(const std::string& n, Logger* l) : mName(n), mLogger(l), mCovarianceScale(1.0) {
+  mScanResolution = 0.1;  // :179
+}
+
+PointCloudSensor::~PointCloudSensor() {}
+
+// :190-201
+PointCloud::Ptr PointCloudSensor::downsample(PointCloud::Ptr in, double leaf_size) {
+  PointCloud::Ptr out(new PointCloud);
+  if (in->size() > 0) {
+    out->points.resize(in->size());
+    uint64_t n_out = 0;
+    const int st = s3d_voxel_downsample(defaultContext(), asCloud(in), static_cast<float>(leaf_size), &out->points[0].x, &n_out, nullptr, nullptr);
+    if (st != S3D_OK) throw std::runtime_error(s3d_last_error());
+    out->points.resize(n_out);
+  }
+  return out;
+}
+
+// :203-209
+PointCloud::Ptr PointCloudSensor::downsampleScan(PointCloud::Ptr source) {
+  if (mScanResolution > 0) return downsample(source, mScanResolution);
+  return source;
+}
+
+// :228-233  pcl::transformPointCloud(*source, *out, tf.matrix()) — double matrix, float points
+PointCloud::Ptr PointCloudSensor::transform(PointCloud::ConstPtr source, const Transform tf) const {
+  PointCloud::Ptr out(new PointCloud);
+  out->points.resize(source->size());
+  for (size_t i = 0; i < source->size(); ++i) {
+    const PointType& p = source->points[i];
+    PointType q;
+    q.x = static_cast<float>(tf(0, 0) * p.x + tf(0, 1) * p.y + tf(0, 2) * p.z + tf(0, 3));
+    q.y = static_cast<float>(tf(1, 0) * p.x + tf(1, 1) * p.y + tf(1, 2) * p.z + tf(1, 3));
+    q.z = static_cast<float>(tf(2, 0) * p.x + tf(2, 1) * p.y + tf(2, 2) * p.z + tf(2, 3));
+    out->points[i] = q;
+  }
+  return out;
+}
+
+// :269-299
+Constraint::Ptr PointCloudSensor::createConstraint(const Measurement::Ptr& source, const Measurement::Ptr& target, const Transform& odometry, bool loop) {
+  // Transform guess in sensor frame  (:274)
+  Transform guess = source->getInverseSensorPose() * odometry * target->getSensorPose();
+  PointCloudMeasurement::Ptr sourceCloud = std::dynamic_pointer_cast<PointCloudMeasurement>(source);
+  PointCloudMeasurement::Ptr targetCloud = std::dynamic_pointer_cast<PointCloudMeasurement>(target);
+  if (!sourceCloud || !targetCloud) {  // :279-283
+    if (mLogger) mLogger->message(ERROR, "Measurement given to createConstraint() is not a PointCloud!");
+    throw BadMeasurementType();
+  }
+  if (loop) guess = align(sourceCloud, targetCloud, guess, mCoarseConfiguration);  // :286-289
+  Transform icp_result = align(sourceCloud, targetCloud, guess, mFineConfiguration);  // :292
+  Transform tf = source->getSensorPose() * icp_result * target->getInverseSensorPose();  // :295
+  Covariance<6> covariance = Covariance<6>::Identity() * mCovarianceScale;  // :296
+  return Constraint::Ptr(new SE3Constraint(mName, tf, covariance.inverseDiagonal()));
+}
+
+// :320-340
+void PointCloudSensor::setRegistrationParameters(const RegistrationParameters& conf, bool coarse) {
+  if (coarse) mCoarseConfiguration = conf; else mFineConfiguration = conf;
+  if (mLogger) mLogger->message(INFO, coarse ? " = RegistrationParameters (Coarse) =" : " = RegistrationParameters (Fine) =");
+}
+
+// :342-346
+void PointCloudSensor::setScanResolution(double r) { mScanResolution = r; }
+
+}  // namespace slam3d_b200

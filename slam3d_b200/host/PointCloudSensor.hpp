@@ -1,0 +1,54 @@
+// PointCloudSensor.hpp — host-side mirror of slam3d::PointCloudSensor's scan-matching interface
+// (slam3d/sensor/pcl/PointCloudSensor.hpp:106-244) on top of the C-ABI of include/s3d_b200.h.
+//
+// Same method names, argument meaning and exception behaviour as the reference for the hot path:
+//   createConstraint(source, target, odometry, loop)   PointCloudSensor.cpp:269-299
+//   setRegistrationParameters(param, coarse)           :320-340
+//   setScanResolution / downsample / downsampleScan    :342-346, :190-209
+//   transform                                          :228-233
+// plus the free function align() (:119-174).  Everything that needs the graph (createCombinedMeasurement,
+// getAccumulatedCloud, buildMap, loadPLY) or other PCL modules (removeOutliers, fillGroundPlane) is outside the
+// hot path and not declared here.  In a real slam3d build the same bodies replace
+// PointCloudSensor.cpp's downsample()/align() — see INTEGRATION.md.
+#pragma once
+
+#include <mutex>
+
+#include "RegistrationParameters.hpp"
+#include "Types.hpp"
+
+namespace slam3d_b200 {
+
+// Process-wide C-ABI context (created on first use; re-entrant, see s3d_b200.h).
+s3d_context* defaultContext();
+
+// align(source, target, guess, config) — PointCloudSensor.cpp:119-174.  Throws NoMatch / std::runtime_error exactly
+// where the reference does.  `result_info` (optional) receives the C-ABI result (fitness, iterations...).
+Transform align(PointCloudMeasurement::Ptr source, PointCloudMeasurement::Ptr target, const Transform& guess,
+                const RegistrationParameters& config, s3d_result* result_info = nullptr);
+
+class PointCloudSensor {
+ public:
+  PointCloudSensor(const std::string& n, Logger* l);
+  virtual ~PointCloudSensor();
+
+  const std::string& getName() const { return mName; }
+  void setCovarianceScale(ScalarType s) { mCovarianceScale = s; }  // core/Sensor.hpp:138
+
+  virtual Constraint::Ptr createConstraint(const Measurement::Ptr& source, const Measurement::Ptr& target, const Transform& odometry, bool loop);
+  void setRegistrationParameters(const RegistrationParameters& param, bool coarse);
+  void setScanResolution(double r);
+  static PointCloud::Ptr downsample(PointCloud::Ptr source, double resolution);
+  PointCloud::Ptr downsampleScan(PointCloud::Ptr source);
+  PointCloud::Ptr transform(PointCloud::ConstPtr source, const Transform tf) const;
+
+ protected:
+  std::string mName;
+  Logger* mLogger;
+  ScalarType mCovarianceScale;
+  RegistrationParameters mFineConfiguration;
+  RegistrationParameters mCoarseConfiguration;
+  double mScanResolution;
+};
+
+}  // namespace slam3d_b200

@@ -60,3 +60,9 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "s3d_oracle" not in txt and "oracle/" not in txt.replace("the oracle's", ""), f
+
+
+def test_host_mirror_library_loads(built):
+    lib = C.CDLL(os.path.join(ROOT, "slam3d_b200", "libs3d_host.so"))
+    for n in ("s3dhost_sensor_create", "s3dhost_create_constraint", "s3dhost_downsample", "s3dhost_run_odometry"):
+        assert hasattr(lib, n)

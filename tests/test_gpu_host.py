@@ -1,0 +1,153 @@
+"""The C++ host mirror of slam3d::PointCloudSensor (slam3d_b200/host) driven the way slam3d drives the reference:
+createConstraint with sensor poses, NoMatch / BadMeasurementType / runtime_error mapping, link-to-previous through the
+mini-host, and concurrent entry from two threads (ScanSensor.cpp:209-210)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import pose_delta
+from slam3d_b200 import _abi
+from slam3d_b200._abi import RegistrationParameters
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def host():
+    import slam3d_b200
+    slam3d_b200.lib()
+    lib = C.CDLL(os.path.join(ROOT, "slam3d_b200", "libs3d_host.so"))
+    lib.s3dhost_last_message.restype = C.c_char_p
+    lib.s3dhost_sensor_create.restype = C.c_void_p
+    lib.s3dhost_sensor_destroy.argtypes = [C.c_void_p]
+    lib.s3dhost_sensor_set_params.argtypes = [C.c_void_p, C.POINTER(RegistrationParameters), C.c_int]
+    lib.s3dhost_sensor_set_covariance_scale.argtypes = [C.c_void_p, C.c_double]
+    lib.s3dhost_create_constraint.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                              C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.s3dhost_downsample.restype = C.c_int64
+    lib.s3dhost_downsample.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_void_p]
+    lib.s3dhost_run_odometry.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    return lib
+
+
+def cm(T):
+    return np.ascontiguousarray(np.asarray(T, np.float64).T)
+
+
+def rot_z(a):
+    T = np.eye(4); T[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+    return T
+
+
+def create_constraint(host, sensor, src, tgt, src_pose, tgt_pose, odom, loop=False, bad=False):
+    import slam3d_b200
+    s, t = slam3d_b200.as_xyzw(src), slam3d_b200.as_xyzw(tgt)
+    T = np.zeros(16); info = np.zeros(36)
+    sp, tp, od = cm(src_pose), cm(tgt_pose), cm(odom)
+    st = host.s3dhost_create_constraint(sensor, s.ctypes.data, s.shape[0], sp.ctypes.data, t.ctypes.data, t.shape[0], tp.ctypes.data,
+                                        od.ctypes.data, int(loop), int(bad), T.ctypes.data, info.ctypes.data)
+    return st, T.reshape(4, 4).T.copy(), info.reshape(6, 6).T.copy(), host.s3dhost_last_message().decode()
+
+
+def test_create_constraint_frames_and_information(host, oracle_mod, kitti):
+    sensor = host.s3dhost_sensor_create(b"velodyne")
+    fine = RegistrationParameters.defaults(point_cloud_density=0.5)
+    host.s3dhost_sensor_set_params(sensor, C.byref(fine), 0)
+    host.s3dhost_sensor_set_covariance_scale(sensor, 0.25)
+    src, tgt = kitti[0][::2], kitti[1][::2]
+    sensor_pose = rot_z(0.3); sensor_pose[:3, 3] = [1.0, 0.2, 1.7]      # lidar mounted on the robot
+    odom = np.eye(4); odom[:3, 3] = [0.6, 0.0, 0.0]
+    odom = sensor_pose @ odom @ np.linalg.inv(sensor_pose)               # robot-frame odometry
+    st, T, info, msg = create_constraint(host, sensor, src, tgt, sensor_pose, sensor_pose, odom)
+    assert st == 0, msg
+    # expected: PointCloudSensor.cpp:274,292,295 with the oracle's align()
+    guess = np.linalg.inv(sensor_pose) @ odom @ sensor_pose
+    want = oracle_mod.gicp_align(src, tgt, guess, fine)
+    assert want.status == 0
+    expect = sensor_pose @ want.pose() @ np.linalg.inv(sensor_pose)
+    dt, dr = pose_delta(expect, T)
+    assert dt < 1e-4 and dr < 1e-4
+    assert np.allclose(info, np.eye(6) / 0.25)                           # :296-298  (I * scale)^-1
+    host.s3dhost_sensor_destroy(sensor)
+
+
+def test_exception_mapping(host, kitti):
+    sensor = host.s3dhost_sensor_create(b"velodyne")
+    src, tgt = kitti[0][::4], kitti[1][::4]
+    I = np.eye(4)
+    cases = [
+        (RegistrationParameters.defaults(point_cloud_density=20.0), 1, "Too few points after filtering"),
+        (RegistrationParameters.defaults(point_cloud_density=0.5, max_fitness_score=1e-6), 1, "ICP failed with Fitness-Score"),
+        (RegistrationParameters.defaults(point_cloud_density=0.5, max_translation=0.05), 1, "ICP result is to far away from guess"),
+        (RegistrationParameters.defaults(point_cloud_density=0.5, registration_algorithm=_abi.ALG_GICP_OMP), 3, "OMP is not available"),
+        (RegistrationParameters.defaults(point_cloud_density=0.5, registration_algorithm=_abi.ALG_ICP), 3, "Unknown registration algorithm"),
+    ]
+    for p, code, text in cases:
+        host.s3dhost_sensor_set_params(sensor, C.byref(p), 0)
+        st, T, info, msg = create_constraint(host, sensor, src, tgt, I, I, I)
+        assert st == code and text in msg, (st, msg)
+    st, T, info, msg = create_constraint(host, sensor, src, tgt, I, I, I, bad=True)
+    assert st == 2  # BadMeasurementType (:279-283)
+    host.s3dhost_sensor_destroy(sensor)
+
+
+def test_loop_closure_runs_coarse_then_fine(host, oracle_mod):
+    from slam3d_b200 import synth
+    src, tgt, truth = synth.scan_pair(seed=5, loop=True)
+    src, tgt = src[::2], tgt[::2]
+    sensor = host.s3dhost_sensor_create(b"velodyne")
+    coarse = RegistrationParameters.defaults(point_cloud_density=0.5, max_correspondence_distance=5.0, max_translation=5.0)
+    fine = RegistrationParameters.defaults(point_cloud_density=0.2, max_translation=5.0)
+    host.s3dhost_sensor_set_params(sensor, C.byref(coarse), 1)
+    host.s3dhost_sensor_set_params(sensor, C.byref(fine), 0)
+    I = np.eye(4)
+    st, T, info, msg = create_constraint(host, sensor, src, tgt, I, I, I, loop=True)
+    oc = oracle_mod.gicp_align(src, tgt, None, coarse)
+    of = oracle_mod.gicp_align(src, tgt, oc.pose(), fine) if oc.status == 0 else oc
+    assert (st == 0) == (of.status == 0), msg
+    if st == 0:
+        dt, dr = pose_delta(of.pose(), T)
+        assert dt < 1e-4 and dr < 1e-4
+        dt, dr = pose_delta(truth, T)
+        assert dt < 0.03 and dr < 5e-3
+    host.s3dhost_sensor_destroy(sensor)
+
+
+def test_minihost_odometry_and_two_threads(host, oracle_mod, kitti):
+    import slam3d_b200
+    sensor = host.s3dhost_sensor_create(b"velodyne")
+    fine = RegistrationParameters.defaults(point_cloud_density=0.5)
+    host.s3dhost_sensor_set_params(sensor, C.byref(fine), 0)
+    scans = [slam3d_b200.as_xyzw(k[::2]) for k in kitti]
+    ptrs = (C.c_void_p * 4)(*[s.ctypes.data for s in scans])
+    sizes = (C.c_uint64 * 4)(*[s.shape[0] for s in scans])
+    odoms = np.zeros((4, 4, 4))
+    for i in range(4):
+        o = np.eye(4); o[0, 3] = 0.65 * i
+        odoms[i] = o.T  # column-major
+    out = np.zeros((3, 16)); nw = C.c_int(0)
+    n1 = host.s3dhost_run_odometry(sensor, ptrs, sizes, 4, odoms.ctypes.data, 1, out.ctypes.data, C.byref(nw))
+    assert n1 == 3 and nw.value == 0
+    single = out.copy()
+    n2 = host.s3dhost_run_odometry(sensor, ptrs, sizes, 4, odoms.ctypes.data, 2, out.ctypes.data, C.byref(nw))
+    assert n2 == 3                      # two concurrent threads: identical edges in both (checked inside) ...
+    assert np.array_equal(out, single)  # ... and identical to the single-threaded run
+    guess = np.eye(4); guess[0, 3] = 0.65
+    for i in range(3):
+        want = oracle_mod.gicp_align(kitti[i][::2], kitti[i + 1][::2], guess, fine)
+        dt, dr = pose_delta(want.pose(), single[i].reshape(4, 4).T)
+        assert want.status == 0 and dt < 1e-4 and dr < 1e-4
+    host.s3dhost_sensor_destroy(sensor)
+
+
+def test_host_downsample(host, oracle_mod, kitti):
+    import slam3d_b200
+    a = slam3d_b200.as_xyzw(kitti[2])
+    out = np.zeros_like(a)
+    m = host.s3dhost_downsample(a.ctypes.data, a.shape[0], 0.1, out.ctypes.data)
+    eo, _, _ = oracle_mod.voxel_downsample(kitti[2], 0.1)
+    assert m == eo.shape[0] and np.array_equal(out[:m].view(np.uint32), eo.view(np.uint32))
+    assert host.s3dhost_downsample(a.ctypes.data, 0, 0.1, out.ctypes.data) == 0  # empty in, empty out (:193)
