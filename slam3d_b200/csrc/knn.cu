@@ -62,8 +62,12 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_cov_kernel(const SlotInfo*
       if (m) L = __ffs(m) - 1;
     }
 
-    float ld = INFINITY; uint32_t li = kNoIndex;      // lane l holds the l-th best (d2, idx)
-    float bd = INFINITY; uint32_t bi = kNoIndex;      // inclusive bound carried over from a finer level
+    // lane l holds the l-th best candidate as one 64-bit key: (float bits of d2) << 32 | original index.
+    // d2 >= +0 so the bit pattern orders like the value; lexicographic (d2, idx) == unsigned key order.
+    const uint64_t KMAX = 0xFFFFFFFFFFFFFFFFull;
+    uint64_t lk = KMAX;        // sorted ascending over lanes; lanes >= kk stay KMAX
+    uint64_t bound = KMAX;     // inclusive bound carried over from a finer level
+    uint64_t tau = KMAX;       // current k-th best (KMAX while the list is not full)
     for (;; ++L) {
       int cx, cy, cz;
       const float g2 = block_guarantee2(g, ux, uy, uz, L, cx, cy, cz);
@@ -81,8 +85,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_cov_kernel(const SlotInfo*
       const uint32_t total = __shfl_sync(FULL, incl, 31);
       const uint32_t excl = incl - cn;
       const int32_t seg_base = (int32_t)cb - (int32_t)excl;  // sorted position = candidate number + seg_base
-      ld = INFINITY; li = kNoIndex;
-      float td = INFINITY; uint32_t ti = kNoIndex;  // current k-th best
+      lk = KMAX; tau = KMAX;
       for (uint32_t base = 0; base < total; base += 32) {
         const uint32_t c = base + lane;
         // segment of candidate c: last lane whose exclusive offset <= c (binary search over lanes by shuffles)
@@ -93,61 +96,86 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_cov_kernel(const SlotInfo*
           if (v <= c) seg += step;
         }
         const int32_t sb = __shfl_sync(FULL, seg_base, seg);
-        float cd = INFINITY; uint32_t ci = kNoIndex;
-        bool pending = false;
+        uint64_t ck = KMAX;
         if (c < total) {
           const float4 v = __ldg(g.pts + (int32_t)c + sb);
-          cd = dist2_pcl(qv.x, qv.y, qv.z, v.x, v.y, v.z);
-          ci = __float_as_uint(v.w);
-          pending = (cd < bd || (cd == bd && ci <= bi));
+          const float cd = dist2_pcl(qv.x, qv.y, qv.z, v.x, v.y, v.z);
+          if (cd == cd) {  // NaN never enters
+            ck = ((uint64_t)__float_as_uint(cd) << 32) | (uint64_t)__float_as_uint(v.w);
+            if (ck > bound) ck = KMAX;
+          }
         }
-        for (;;) {
-          const uint32_t m = __ballot_sync(FULL, pending && cand_less(cd, ci, td, ti));
-          if (!m) break;
-          const int src = __ffs(m) - 1;
-          const float xd = __shfl_sync(FULL, cd, src);
-          const uint32_t xi = __shfl_sync(FULL, ci, src);
-          if (lane == src) pending = false;
-          const int pos = __popc(__ballot_sync(FULL, cand_less(ld, li, xd, xi)));
-          const float ud = __shfl_up_sync(FULL, ld, 1);
-          const uint32_t ui = __shfl_up_sync(FULL, li, 1);
-          if (lane == pos) { ld = xd; li = xi; }
-          else if (lane > pos) { ld = ud; li = ui; }
-          if (lane >= kk) { ld = INFINITY; li = kNoIndex; }
-          td = __shfl_sync(FULL, ld, kk - 1);
-          ti = __shfl_sync(FULL, li, kk - 1);
+        uint32_t m = __ballot_sync(FULL, ck < tau);
+        if (!m) continue;
+        if (__popc(m) <= 3) {
+          // few newcomers: insert one by one
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint64_t x = __shfl_sync(FULL, ck, src);
+            if (x >= tau) continue;  // tau moved
+            const int pos = __popc(__ballot_sync(FULL, lk < x));
+            const uint64_t up = __shfl_up_sync(FULL, lk, 1);
+            if (lane == pos) lk = x; else if (lane > pos) lk = up;
+            if (lane >= kk) lk = KMAX;
+            tau = __shfl_sync(FULL, lk, kk - 1);
+          }
+        } else {
+          // many newcomers: bitonic-sort the 32 candidates, then one bitonic merge with the list
+          uint64_t v = ck;
+#pragma unroll
+          for (int kb = 2; kb <= 32; kb <<= 1) {
+#pragma unroll
+            for (int j = kb >> 1; j > 0; j >>= 1) {
+              const uint64_t o = __shfl_xor_sync(FULL, v, j);
+              const bool keep_min = ((lane & j) == 0) == ((lane & kb) == 0);
+              v = keep_min ? (v < o ? v : o) : (v < o ? o : v);
+            }
+          }
+          const uint64_t r = __shfl_sync(FULL, v, 31 - lane);  // descending
+          v = lk < r ? lk : r;                                  // the 32 smallest of the union, bitonic
+#pragma unroll
+          for (int j = 16; j > 0; j >>= 1) {
+            const uint64_t o = __shfl_xor_sync(FULL, v, j);
+            v = ((lane & j) == 0) ? (v < o ? v : o) : (v < o ? o : v);
+          }
+          lk = lane < kk ? v : KMAX;
+          tau = __shfl_sync(FULL, lk, kk - 1);
         }
       }
-      const bool full = ti != kNoIndex || td < INFINITY;  // k-th entry present
+      const bool full = tau != KMAX;
+      const float td = __uint_as_float((uint32_t)(tau >> 32));
       if ((full && td <= g2) || top) break;
-      if (full) { bd = td; bi = ti; }
+      if (full) bound = tau;
     }
+    const uint32_t li = (uint32_t)lk;                           // neighbour `lane`: original index
+    const float ld = lk == KMAX ? INFINITY : __uint_as_float((uint32_t)(lk >> 32));
 
     // ---- moments in neighbour order, float products accumulated in double (A.3 step 2) ------------------------------
+    // lane a (< 9) owns one accumulator: mean x,y,z | cov 00,10,11,20,21,22; every lane walks the neighbours in order.
     float px = 0.f, py = 0.f, pz = 0.f;
-    if (lane < kk && li != kNoIndex) { const float4 v = __ldg(cloud + li); px = v.x; py = v.y; pz = v.z; }
-    double mean[3] = {0, 0, 0}, cov[6] = {0, 0, 0, 0, 0, 0};  // cov: 00,10,11,20,21,22
+    if (lane < kk && lk != KMAX) { const float4 v = __ldg(cloud + li); px = v.x; py = v.y; pz = v.z; }
+    const int ia = lane < 3 ? lane : (lane == 3 ? 0 : (lane <= 5 ? 1 : 2));
+    const int ib = lane < 3 ? 3 : (lane == 3 || lane == 4 || lane == 6 ? 0 : (lane == 5 || lane == 7 ? 1 : 2));
+    double acc = 0.0;
     for (int j = 0; j < kk; ++j) {
       const float x = __shfl_sync(FULL, px, j), y = __shfl_sync(FULL, py, j), z = __shfl_sync(FULL, pz, j);
-      mean[0] += (double)x; mean[1] += (double)y; mean[2] += (double)z;
-      cov[0] += (double)__fmul_rn(x, x);
-      cov[1] += (double)__fmul_rn(y, x);
-      cov[2] += (double)__fmul_rn(y, y);
-      cov[3] += (double)__fmul_rn(z, x);
-      cov[4] += (double)__fmul_rn(z, y);
-      cov[5] += (double)__fmul_rn(z, z);
+      const float u = ia == 0 ? x : (ia == 1 ? y : z);
+      const float w = ib == 0 ? x : (ib == 1 ? y : (ib == 2 ? z : 1.0f));
+      acc += (double)__fmul_rn(u, w);
     }
-    const double dk = (double)k;  // PCL divides by k_correspondences_
-    mean[0] /= dk; mean[1] /= dk; mean[2] /= dk;
-    cov[0] = cov[0] / dk - mean[0] * mean[0];
-    cov[1] = cov[1] / dk - mean[1] * mean[0];
-    cov[2] = cov[2] / dk - mean[1] * mean[1];
-    cov[3] = cov[3] / dk - mean[2] * mean[0];
-    cov[4] = cov[4] / dk - mean[2] * mean[1];
-    cov[5] = cov[5] / dk - mean[2] * mean[2];
-    if (lane == qi) {
+    double s9[9];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) my_cov[i] = cov[i];
+    for (int a = 0; a < 9; ++a) s9[a] = __shfl_sync(FULL, acc, a);
+    if (lane == qi) {
+      const double dk = (double)k;  // PCL divides by k_correspondences_
+      const double m0 = s9[0] / dk, m1 = s9[1] / dk, m2 = s9[2] / dk;
+      my_cov[0] = s9[3] / dk - m0 * m0;
+      my_cov[1] = s9[4] / dk - m1 * m0;
+      my_cov[2] = s9[5] / dk - m1 * m1;
+      my_cov[3] = s9[6] / dk - m2 * m0;
+      my_cov[4] = s9[7] / dk - m2 * m1;
+      my_cov[5] = s9[8] / dk - m2 * m2;
     }
     if (knn_index && lane < k) knn_index[((size_t)si.off + q_orig) * k + lane] = li;
     if (knn_dist2 && lane < k) knn_dist2[((size_t)si.off + q_orig) * k + lane] = ld;

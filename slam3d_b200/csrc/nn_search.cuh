@@ -29,38 +29,48 @@ __device__ __forceinline__ GridView make_grid_view(const SlotInfo& si, const Has
 
 __device__ __forceinline__ float clamp_coord(float u) { return fminf(fmaxf(u, -1.0e6f), 1.0e6f); }  // NaN -> -1e6
 
-// Cell of the query at level L and the squared radius the 27-block around it is guaranteed to cover.
-__device__ __forceinline__ float block_guarantee2(const GridView& g, float ux, float uy, float uz, int L, int& cx, int& cy, int& cz) {
+// Cell of the query at level L, its fractional position inside that cell, and the squared radius the 27-block
+// around it is guaranteed to cover.
+__device__ __forceinline__ float block_guarantee2(const GridView& g, float ux, float uy, float uz, int L, int& cx, int& cy, int& cz,
+                                                  float& ax, float& ay, float& az) {
   const float s = 1.0f / (float)(1 << L);  // exact power of two
   const float vx = ux * s, vy = uy * s, vz = uz * s;
   const float fx = floorf(vx), fy = floorf(vy), fz = floorf(vz);
   cx = (int)fx; cy = (int)fy; cz = (int)fz;
-  const float ax = vx - fx, ay = vy - fy, az = vz - fz;
+  ax = vx - fx; ay = vy - fy; az = vz - fz;
   const float o = fminf(fminf(fminf(ax, 1.f - ax), fminf(ay, 1.f - ay)), fminf(az, 1.f - az));
   const float r = g.h0 * (float)(1 << L) * (1.f + o) * 0.9999f - g.margin;
   return r > 0.f ? r * r * 0.999999f : 0.f;
+}
+__device__ __forceinline__ float block_guarantee2(const GridView& g, float ux, float uy, float uz, int L, int& cx, int& cy, int& cz) {
+  float ax, ay, az;
+  return block_guarantee2(g, ux, uy, uz, L, cx, cy, cz, ax, ay, az);
 }
 
 struct NNResult { float d2; uint32_t idx; uint32_t pos; };
 
 __device__ __forceinline__ bool cand_less(float d2, uint32_t idx, float bd2, uint32_t bidx) { return d2 < bd2 || (d2 == bd2 && idx < bidx); }
 
-// thread-per-query scan of the 27-block at level L
-__device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int cy, int cz, float qx, float qy, float qz, NNResult& best) {
+// thread-per-query scan of the 27-block at level L.  The query's own cell goes first; a neighbour cell is skipped
+// when a lower bound of its distance (gap along each axis, shrunk by the float slack) already exceeds the best
+// candidate — with a warm start that leaves 1-4 of the 27 cells.  (ax,ay,az) = position of the query inside its
+// cell in [0,1); prune = false at the top level, where the block is anchored at cell 0 instead of the query.
+__device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int cy, int cz, float ax, float ay, float az, bool prune,
+                                           float qx, float qy, float qz, NNResult& best) {
   const int dim = 1 << (g.nlev - L);
-  uint32_t sx[3], sy[3], sz[3];
-  bool okx[3], oky[3], okz[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    okx[d] = (unsigned)(cx + d - 1) < (unsigned)dim; sx[d] = spread3((uint32_t)(cx + d - 1));
-    oky[d] = (unsigned)(cy + d - 1) < (unsigned)dim; sy[d] = spread3((uint32_t)(cy + d - 1)) << 1;
-    okz[d] = (unsigned)(cz + d - 1) < (unsigned)dim; sz[d] = spread3((uint32_t)(cz + d - 1)) << 2;
-  }
+  const float hl = g.h0 * (float)(1 << L) * 0.9999f;
 #pragma unroll 1
-  for (int c = 0; c < 27; ++c) {
+  for (int i = 0; i < 27; ++i) {
+    const int c = i == 0 ? 13 : (i <= 13 ? i - 1 : i);  // own cell first
     const int dx = c % 3, dy = (c / 3) % 3, dz = c / 9;
-    if (!(okx[dx] && oky[dy] && okz[dz])) continue;
-    const uint32_t key = sx[dx] | sy[dy] | sz[dz];
+    const int ix = cx + dx - 1, iy = cy + dy - 1, iz = cz + dz - 1;
+    if ((unsigned)ix >= (unsigned)dim || (unsigned)iy >= (unsigned)dim || (unsigned)iz >= (unsigned)dim) continue;
+    if (prune) {
+      const float fx = dx == 0 ? ax : (dx == 1 ? 0.f : 1.f - ax), fy = dy == 0 ? ay : (dy == 1 ? 0.f : 1.f - ay), fz = dz == 0 ? az : (dz == 1 ? 0.f : 1.f - az);
+      const float rx = fmaxf(fx * hl - g.margin, 0.f), ry = fmaxf(fy * hl - g.margin, 0.f), rz = fmaxf(fz * hl - g.margin, 0.f);
+      if ((rx * rx + ry * ry + rz * rz) * 0.99999f > best.d2) continue;
+    }
+    const uint32_t key = morton3((uint32_t)ix, (uint32_t)iy, (uint32_t)iz);
     uint32_t s = hash_slot(key, (uint32_t)L, g.cap);
     uint32_t begin = 0, end = 0;
     for (;;) {
@@ -99,10 +109,11 @@ __device__ __forceinline__ NNResult nn_search(const GridView& g, float qx, float
   }
   for (;; ++L) {
     int cx, cy, cz;
-    const float g2 = block_guarantee2(g, ux, uy, uz, L, cx, cy, cz);
+    float ax, ay, az;
+    const float g2 = block_guarantee2(g, ux, uy, uz, L, cx, cy, cz, ax, ay, az);
     const bool top = L >= g.nlev - 1;
     if (top) cx = cy = cz = 0;  // 2 cells per axis: the block around cell 0 is the whole cloud, wherever the query is
-    scan_block(g, L, cx, cy, cz, qx, qy, qz, best);
+    scan_block(g, L, cx, cy, cz, ax, ay, az, !top, qx, qy, qz, best);
     if (best.d2 <= g2 || g2 >= cutoff2 || top) break;
   }
   return best;
