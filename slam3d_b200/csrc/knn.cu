@@ -2,15 +2,16 @@
 //
 // Replaces GeneralizedIterativeClosestPoint::computeCovariances (reached from icp.align(), PointCloudSensor.cpp:70;
 // SURVEY A.3, 8a row a4.2 — the largest single block of CPU time, ~270 ms per cloud).
-//   * one warp per query, 32 consecutive (Morton-adjacent) queries per warp;
-//   * lanes 0..26 probe the 27 cells of the block, a warp prefix sum flattens their point ranges, and the 32 lanes
-//     stream the candidates as coalesced float4 loads; the k best are kept as a sorted list distributed over the lanes
-//     in lexicographic (d2, original index) order — FLANN's exact search with ties to the lowest index;
+//   * one thread per query; the 128 queries of a CTA are Morton-adjacent, so the cell walks of a warp touch the same
+//     L1 lines (a warp-cooperative variant, one warp per query with a shuffle-merged top-k, cost 6x more instructions
+//     per query: profiles/r01a_summary.md);
+//   * candidates are 64-bit keys (d2 bits << 32 | original index): unsigned order == lexicographic (d2, index) order,
+//     i.e. FLANN's exact search with ties to the lowest index; the k best sit in a per-thread max-heap in shared memory;
 //   * the level (cell size) is picked per query from the occupancy of its own ancestors and widened until the k-th
-//     distance is certified by the block's coverage radius (nn_search.cuh);
+//     distance is certified by the block's coverage radius (nn_search.cuh); cells farther than the k-th best are skipped;
 //   * moments exactly as PCL: float products accumulated in double, in neighbour order (A.3 step 2);
 //   * the neighbour list never leaves the SM: per query only a 32-byte unit normal is written, because
-//     C = U diag(1,1,eps) U^T = I - (1-eps) n n^T;  the 3x3 eigen-decompositions run one query per lane.
+//     C = U diag(1,1,eps) U^T = I - (1-eps) n n^T.
 // Bound: L2/latency (the working set of a scan, ~2 MB, is L2 resident); algorithmic bytes 16 B read + 32 B written
 // per point.
 #include "internal.h"
@@ -18,177 +19,155 @@
 
 namespace s3d {
 
-constexpr int kKnnQueriesPerWarp = 32;
-constexpr int kKnnWarps = 8;
-constexpr int kKnnTile = kKnnQueriesPerWarp * kKnnWarps;  // 256 queries per CTA
+constexpr int kKnnThreads = 128;  // queries per CTA (one thread per query)
 
-__global__ void __launch_bounds__(kKnnWarps * 32) knn_cov_kernel(const SlotInfo* __restrict__ slots, const HashEntry* __restrict__ arena,
-                                                                 const float4* __restrict__ gpts, const float4* __restrict__ work,
-                                                                 double4* __restrict__ normals, int k, uint32_t* __restrict__ knn_index,
-                                                                 float* __restrict__ knn_dist2) {
+// max-heap of 64-bit keys in shared memory, element j of thread t at h[j * kKnnThreads]
+__device__ __forceinline__ void heap_push(uint64_t* h, int& n, uint64_t x) {
+  int i = n++;
+  while (i > 0) {
+    const int p = (i - 1) >> 1;
+    const uint64_t hp = h[p * kKnnThreads];
+    if (hp >= x) break;
+    h[i * kKnnThreads] = hp;
+    i = p;
+  }
+  h[i * kKnnThreads] = x;
+}
+// replaces the root by x (x < root) and restores the heap
+__device__ __forceinline__ void heap_sift_down(uint64_t* h, int n, uint64_t x) {
+  int i = 0;
+  for (;;) {
+    int c = 2 * i + 1;
+    if (c >= n) break;
+    uint64_t hc = h[c * kKnnThreads];
+    if (c + 1 < n) { const uint64_t hr = h[(c + 1) * kKnnThreads]; if (hr > hc) { hc = hr; ++c; } }
+    if (hc <= x) break;
+    h[i * kKnnThreads] = hc;
+    i = c;
+  }
+  h[i * kKnnThreads] = x;
+}
+
+// One thread per query (Morton-adjacent queries share a warp, so their cell walks hit the same L1 lines).
+// Candidates are (d2, original index) packed into one 64-bit key — d2 >= +0, so unsigned key order is the
+// lexicographic (d2, idx) order of the parity contract — and the k best live in a per-thread max-heap in shared
+// memory (bank-conflict free: element j of thread t at [j][t]).  A cell is skipped when the lower bound of its distance
+// exceeds the current k-th best.  Heapsort at the end yields FLANN's ascending neighbour order for the moments.
+__global__ void __launch_bounds__(kKnnThreads) knn_cov_kernel(const SlotInfo* __restrict__ slots, const HashEntry* __restrict__ arena,
+                                                              const float4* __restrict__ gpts, const float4* __restrict__ work,
+                                                              double4* __restrict__ normals, int k, uint32_t* __restrict__ knn_index,
+                                                              float* __restrict__ knn_dist2) {
+  extern __shared__ uint64_t heap_smem[];  // k * kKnnThreads keys
   const SlotInfo& si = slots[blockIdx.y];
   const uint32_t n = si.n_pts;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t q0 = blockIdx.x * kKnnTile + warp * kKnnQueriesPerWarp;
-  if (q0 >= n) return;
+  const uint32_t r = blockIdx.x * kKnnThreads + threadIdx.x;
+  if (r >= n) return;
   const GridView g = make_grid_view(si, arena, gpts);
   const float4* cloud = work + si.off;  // original (voxel-key) order
-  const uint32_t FULL = 0xFFFFFFFFu;
   const int kk = k < (int)n ? k : (int)n;  // FLANN clamps k to the cloud size
+  uint64_t* h = heap_smem + threadIdx.x;
+  const uint64_t KMAX = 0xFFFFFFFFFFFFFFFFull;
 
-  double my_cov[6] = {0, 0, 0, 0, 0, 0};  // covariance of query q0 + lane, filled in as the warp walks its queries
+  const float4 qv = g.pts[r];
+  const uint32_t q_orig = __float_as_uint(qv.w);
+  const float ux = clamp_coord(grid_coord(qv.x, g.ox, g.inv_h0));
+  const float uy = clamp_coord(grid_coord(qv.y, g.oy, g.inv_h0));
+  const float uz = clamp_coord(grid_coord(qv.z, g.oz, g.inv_h0));
 
+  // ---- start level: smallest L whose parent cell (level L+1) already holds >= 12 points ------------------------------
+  int L = g.nlev - 1;
+  {
+    const int c0x = (int)floorf(ux), c0y = (int)floorf(uy), c0z = (int)floorf(uz);
+    for (int lv = 1; lv < g.nlev; ++lv) {
+      uint32_t b, e;
+      if (cell_range(g.table, g.cap, g.nlev, lv, c0x >> lv, c0y >> lv, c0z >> lv, b, e) && (e - b) >= 12u) { L = lv - 1; break; }
+    }
+  }
+
+  uint64_t bound = KMAX;  // inclusive bound carried over from a finer level
+  int cnt = 0;
+  for (;; ++L) {
+    int cx, cy, cz;
+    float ax, ay, az;
+    const float g2 = block_guarantee2(g, ux, uy, uz, L, cx, cy, cz, ax, ay, az);
+    const bool top = L >= g.nlev - 1;
+    if (top) cx = cy = cz = 0;
+    const int dim = 1 << (g.nlev - L);
+    const float hl = g.h0 * (float)(1 << L) * 0.9999f;
+    cnt = 0;
+    uint64_t tau = bound;                                   // current admission threshold (inclusive while not full)
+    float tau_d2 = __uint_as_float((uint32_t)(tau >> 32));  // KMAX -> NaN bits: comparisons below stay false, nothing is pruned
 #pragma unroll 1
-  for (int qi = 0; qi < kKnnQueriesPerWarp; ++qi) {
-    const uint32_t r = q0 + qi;
-    if (r >= n) break;
-    const float4 qv = g.pts[r];
-    const uint32_t q_orig = __float_as_uint(qv.w);
-    const float ux = clamp_coord(grid_coord(qv.x, g.ox, g.inv_h0));
-    const float uy = clamp_coord(grid_coord(qv.y, g.oy, g.inv_h0));
-    const float uz = clamp_coord(grid_coord(qv.z, g.oz, g.inv_h0));
-
-    // ---- start level: smallest L whose parent cell (level L+1) already holds >= 12 points --------------------------
-    int L = g.nlev - 1;
-    {
-      const int lv = lane + 1;  // lane probes level lane+1
-      bool enough = false;
-      if (lv < g.nlev) {
-        uint32_t b, e;
-        const int cx = (int)floorf(ux) >> lv, cy = (int)floorf(uy) >> lv, cz = (int)floorf(uz) >> lv;
-        if (cell_range(g.table, g.cap, g.nlev, lv, cx, cy, cz, b, e)) enough = (e - b) >= 12u;
+    for (int i = 0; i < 27; ++i) {
+      const int c = i == 0 ? 13 : (i <= 13 ? i - 1 : i);  // own cell first
+      const int dx = c % 3, dy = (c / 3) % 3, dz = c / 9;
+      const int ix = cx + dx - 1, iy = cy + dy - 1, iz = cz + dz - 1;
+      if ((unsigned)ix >= (unsigned)dim || (unsigned)iy >= (unsigned)dim || (unsigned)iz >= (unsigned)dim) continue;
+      if (!top) {
+        const float fx = dx == 0 ? ax : (dx == 1 ? 0.f : 1.f - ax), fy = dy == 0 ? ay : (dy == 1 ? 0.f : 1.f - ay), fz = dz == 0 ? az : (dz == 1 ? 0.f : 1.f - az);
+        const float rx = fmaxf(fx * hl - g.margin, 0.f), ry = fmaxf(fy * hl - g.margin, 0.f), rz = fmaxf(fz * hl - g.margin, 0.f);
+        if ((rx * rx + ry * ry + rz * rz) * 0.99999f > tau_d2) continue;  // the whole cell is farther than the k-th best / the bound
       }
-      const uint32_t m = __ballot_sync(FULL, enough);
-      if (m) L = __ffs(m) - 1;
-    }
-
-    // lane l holds the l-th best candidate as one 64-bit key: (float bits of d2) << 32 | original index.
-    // d2 >= +0 so the bit pattern orders like the value; lexicographic (d2, idx) == unsigned key order.
-    const uint64_t KMAX = 0xFFFFFFFFFFFFFFFFull;
-    uint64_t lk = KMAX;        // sorted ascending over lanes; lanes >= kk stay KMAX
-    uint64_t bound = KMAX;     // inclusive bound carried over from a finer level
-    uint64_t tau = KMAX;       // current k-th best (KMAX while the list is not full)
-    for (;; ++L) {
-      int cx, cy, cz;
-      const float g2 = block_guarantee2(g, ux, uy, uz, L, cx, cy, cz);
-      const bool top = L >= g.nlev - 1;
-      if (top) cx = cy = cz = 0;
-      // lanes 0..26: one cell each
-      uint32_t cb = 0, cn = 0;
-      if (lane < 27) {
-        uint32_t b, e;
-        if (cell_range(g.table, g.cap, g.nlev, L, cx + lane % 3 - 1, cy + (lane / 3) % 3 - 1, cz + lane / 9 - 1, b, e)) { cb = b; cn = e - b; }
-      }
-      uint32_t incl = cn;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-      const uint32_t total = __shfl_sync(FULL, incl, 31);
-      const uint32_t excl = incl - cn;
-      const int32_t seg_base = (int32_t)cb - (int32_t)excl;  // sorted position = candidate number + seg_base
-      lk = KMAX; tau = KMAX;
-      for (uint32_t base = 0; base < total; base += 32) {
-        const uint32_t c = base + lane;
-        // segment of candidate c: last lane whose exclusive offset <= c (binary search over lanes by shuffles)
-        int seg = 0;
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-          const uint32_t v = __shfl_sync(FULL, excl, seg + step);
-          if (v <= c) seg += step;
-        }
-        const int32_t sb = __shfl_sync(FULL, seg_base, seg);
-        uint64_t ck = KMAX;
-        if (c < total) {
-          const float4 v = __ldg(g.pts + (int32_t)c + sb);
-          const float cd = dist2_pcl(qv.x, qv.y, qv.z, v.x, v.y, v.z);
-          if (cd == cd) {  // NaN never enters
-            ck = ((uint64_t)__float_as_uint(cd) << 32) | (uint64_t)__float_as_uint(v.w);
-            if (ck > bound) ck = KMAX;
+      uint32_t begin, end;
+      if (!cell_range(g.table, g.cap, g.nlev, L, ix, iy, iz, begin, end)) continue;
+      for (uint32_t p = begin; p < end; ++p) {
+        const float4 v = __ldg(g.pts + p);
+        const float cd = dist2_pcl(qv.x, qv.y, qv.z, v.x, v.y, v.z);
+        if (!(cd == cd)) continue;  // NaN never enters
+        const uint64_t ck = ((uint64_t)__float_as_uint(cd) << 32) | (uint64_t)__float_as_uint(v.w);
+        if (cnt < kk) {
+          if (ck <= bound) {
+            heap_push(h, cnt, ck);
+            if (cnt == kk) { tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32)); }
           }
-        }
-        uint32_t m = __ballot_sync(FULL, ck < tau);
-        if (!m) continue;
-        if (__popc(m) <= 3) {
-          // few newcomers: insert one by one
-          while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const uint64_t x = __shfl_sync(FULL, ck, src);
-            if (x >= tau) continue;  // tau moved
-            const int pos = __popc(__ballot_sync(FULL, lk < x));
-            const uint64_t up = __shfl_up_sync(FULL, lk, 1);
-            if (lane == pos) lk = x; else if (lane > pos) lk = up;
-            if (lane >= kk) lk = KMAX;
-            tau = __shfl_sync(FULL, lk, kk - 1);
-          }
-        } else {
-          // many newcomers: bitonic-sort the 32 candidates, then one bitonic merge with the list
-          uint64_t v = ck;
-#pragma unroll
-          for (int kb = 2; kb <= 32; kb <<= 1) {
-#pragma unroll
-            for (int j = kb >> 1; j > 0; j >>= 1) {
-              const uint64_t o = __shfl_xor_sync(FULL, v, j);
-              const bool keep_min = ((lane & j) == 0) == ((lane & kb) == 0);
-              v = keep_min ? (v < o ? v : o) : (v < o ? o : v);
-            }
-          }
-          const uint64_t r = __shfl_sync(FULL, v, 31 - lane);  // descending
-          v = lk < r ? lk : r;                                  // the 32 smallest of the union, bitonic
-#pragma unroll
-          for (int j = 16; j > 0; j >>= 1) {
-            const uint64_t o = __shfl_xor_sync(FULL, v, j);
-            v = ((lane & j) == 0) ? (v < o ? v : o) : (v < o ? o : v);
-          }
-          lk = lane < kk ? v : KMAX;
-          tau = __shfl_sync(FULL, lk, kk - 1);
+        } else if (ck < tau) {
+          heap_sift_down(h, kk, ck);
+          tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
         }
       }
-      const bool full = tau != KMAX;
-      const float td = __uint_as_float((uint32_t)(tau >> 32));
-      if ((full && td <= g2) || top) break;
-      if (full) bound = tau;
     }
-    const uint32_t li = (uint32_t)lk;                           // neighbour `lane`: original index
-    const float ld = lk == KMAX ? INFINITY : __uint_as_float((uint32_t)(lk >> 32));
-
-    // ---- moments in neighbour order, float products accumulated in double (A.3 step 2) ------------------------------
-    // lane a (< 9) owns one accumulator: mean x,y,z | cov 00,10,11,20,21,22; every lane walks the neighbours in order.
-    float px = 0.f, py = 0.f, pz = 0.f;
-    if (lane < kk && lk != KMAX) { const float4 v = __ldg(cloud + li); px = v.x; py = v.y; pz = v.z; }
-    const int ia = lane < 3 ? lane : (lane == 3 ? 0 : (lane <= 5 ? 1 : 2));
-    const int ib = lane < 3 ? 3 : (lane == 3 || lane == 4 || lane == 6 ? 0 : (lane == 5 || lane == 7 ? 1 : 2));
-    double acc = 0.0;
-    for (int j = 0; j < kk; ++j) {
-      const float x = __shfl_sync(FULL, px, j), y = __shfl_sync(FULL, py, j), z = __shfl_sync(FULL, pz, j);
-      const float u = ia == 0 ? x : (ia == 1 ? y : z);
-      const float w = ib == 0 ? x : (ib == 1 ? y : (ib == 2 ? z : 1.0f));
-      acc += (double)__fmul_rn(u, w);
-    }
-    double s9[9];
-#pragma unroll
-    for (int a = 0; a < 9; ++a) s9[a] = __shfl_sync(FULL, acc, a);
-    if (lane == qi) {
-      const double dk = (double)k;  // PCL divides by k_correspondences_
-      const double m0 = s9[0] / dk, m1 = s9[1] / dk, m2 = s9[2] / dk;
-      my_cov[0] = s9[3] / dk - m0 * m0;
-      my_cov[1] = s9[4] / dk - m1 * m0;
-      my_cov[2] = s9[5] / dk - m1 * m1;
-      my_cov[3] = s9[6] / dk - m2 * m0;
-      my_cov[4] = s9[7] / dk - m2 * m1;
-      my_cov[5] = s9[8] / dk - m2 * m2;
-    }
-    if (knn_index && lane < k) knn_index[((size_t)si.off + q_orig) * k + lane] = li;
-    if (knn_dist2 && lane < k) knn_dist2[((size_t)si.off + q_orig) * k + lane] = ld;
+    const bool full = cnt == kk;
+    if ((full && tau_d2 <= g2) || top) break;
+    if (full) bound = tau;
   }
-
-  // ---- one eigen-decomposition per lane ---------------------------------------------------------------------------
-  const uint32_t r = q0 + lane;
-  if (r < n) {
-    double c[3][3] = {{my_cov[0], my_cov[1], my_cov[3]}, {my_cov[1], my_cov[2], my_cov[4]}, {my_cov[3], my_cov[4], my_cov[5]}};
-    double nrm[3];
-    smallest_eigenvector3(c, nrm);
-    normals[si.off + r] = make_double4(nrm[0], nrm[1], nrm[2], 0.0);
+  // ---- heapsort: ascending (d2, idx) = FLANN's sorted result order --------------------------------------------------------
+  for (int m = cnt - 1; m > 0; --m) {
+    const uint64_t last = h[m * kKnnThreads];
+    h[m * kKnnThreads] = h[0];
+    heap_sift_down(h, m, last);
   }
+  // ---- moments in neighbour order, float products accumulated in double (A.3 step 2) ------------------------------
+  double mean[3] = {0, 0, 0}, cov[6] = {0, 0, 0, 0, 0, 0};  // cov: 00,10,11,20,21,22
+  for (int j = 0; j < cnt; ++j) {
+    const uint64_t key = h[j * kKnnThreads];
+    const uint32_t id = (uint32_t)key;
+    const float4 pt = __ldg(cloud + id);
+    mean[0] += (double)pt.x; mean[1] += (double)pt.y; mean[2] += (double)pt.z;
+    cov[0] += (double)__fmul_rn(pt.x, pt.x);
+    cov[1] += (double)__fmul_rn(pt.y, pt.x);
+    cov[2] += (double)__fmul_rn(pt.y, pt.y);
+    cov[3] += (double)__fmul_rn(pt.z, pt.x);
+    cov[4] += (double)__fmul_rn(pt.z, pt.y);
+    cov[5] += (double)__fmul_rn(pt.z, pt.z);
+    if (knn_index) knn_index[((size_t)si.off + q_orig) * k + j] = id;
+    if (knn_dist2) knn_dist2[((size_t)si.off + q_orig) * k + j] = __uint_as_float((uint32_t)(key >> 32));
+  }
+  for (int j = cnt; j < k; ++j) {
+    if (knn_index) knn_index[((size_t)si.off + q_orig) * k + j] = kNoIndex;
+    if (knn_dist2) knn_dist2[((size_t)si.off + q_orig) * k + j] = INFINITY;
+  }
+  const double dk = (double)k;  // PCL divides by k_correspondences_
+  mean[0] /= dk; mean[1] /= dk; mean[2] /= dk;
+  double c3[3][3];
+  c3[0][0] = cov[0] / dk - mean[0] * mean[0];
+  c3[1][0] = c3[0][1] = cov[1] / dk - mean[1] * mean[0];
+  c3[1][1] = cov[2] / dk - mean[1] * mean[1];
+  c3[2][0] = c3[0][2] = cov[3] / dk - mean[2] * mean[0];
+  c3[2][1] = c3[1][2] = cov[4] / dk - mean[2] * mean[1];
+  c3[2][2] = cov[5] / dk - mean[2] * mean[2];
+  double nrm[3];
+  smallest_eigenvector3(c3, nrm);
+  normals[si.off + r] = make_double4(nrm[0], nrm[1], nrm[2], 0.0);
 }
 
 // stage-API helper: full regularised covariance per ORIGINAL index, column-major 3x3
@@ -210,8 +189,8 @@ void run_knn_covariances(Workspace& ws, int k, uint32_t* knn_index, float* knn_d
   for (uint32_t s = 0; s < ws.n_slots; ++s) max_n = std::max(max_n, ws.h_n[s]);
   ws.normals.reserve(sizeof(double4) * std::max<size_t>(ws.total, 4));
   StageTimer timer(ws, kStageKnn);
-  dim3 grid((max_n + kKnnTile - 1) / kKnnTile, ws.n_slots);
-  knn_cov_kernel<<<grid, kKnnWarps * 32, 0, ws.stream>>>(ws.slots.as<SlotInfo>(), ws.hash.as<HashEntry>(), ws.gpts.as<float4>(),
+  dim3 grid((max_n + kKnnThreads - 1) / kKnnThreads, ws.n_slots);
+  knn_cov_kernel<<<grid, kKnnThreads, sizeof(uint64_t) * k * kKnnThreads, ws.stream>>>(ws.slots.as<SlotInfo>(), ws.hash.as<HashEntry>(), ws.gpts.as<float4>(),
                                                          ws.work.as<float4>(), ws.normals.as<double4>(), k, knn_index, knn_dist2);
   ++ws.launches;
   S3D_CUDA(cudaGetLastError());
