@@ -92,14 +92,14 @@ __global__ void __launch_bounds__(kKnnThreads) knn_cov_kernel(const SlotInfo* __
     const float g2 = block_guarantee2(g, ux, uy, uz, L, cx, cy, cz, ax, ay, az);
     const bool top = L >= g.nlev - 1;
     if (top) cx = cy = cz = 0;
-    const int dim = 1 << (g.nlev - L);
-    const float hl = g.h0 * (float)(1 << L) * 0.9999f;
     cnt = 0;
     uint64_t tau = bound;                                   // current admission threshold (inclusive while not full)
-    float tau_d2 = __uint_as_float((uint32_t)(tau >> 32));  // KMAX -> NaN bits: comparisons below stay false, nothing is pruned
+    float tau_d2 = __uint_as_float((uint32_t)(tau >> 32));  // KMAX -> NaN bits: comparisons stay false, nothing is pruned
+    const int dim = 1 << (g.nlev - L);
+    const float hl = g.h0 * (float)(1 << L) * 0.9999f;
 #pragma unroll 1
     for (int i = 0; i < 27; ++i) {
-      const int c = i == 0 ? 13 : (i <= 13 ? i - 1 : i);  // own cell first
+      const int c = cell_order(i);  // own cell, faces, edges, corners
       const int dx = c % 3, dy = (c / 3) % 3, dz = c / 9;
       const int ix = cx + dx - 1, iy = cy + dy - 1, iz = cz + dz - 1;
       if ((unsigned)ix >= (unsigned)dim || (unsigned)iy >= (unsigned)dim || (unsigned)iz >= (unsigned)dim) continue;
