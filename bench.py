@@ -153,7 +153,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--pairs", type=int, default=32, help="scan pairs per step and per GPU")
+    ap.add_argument("--pairs", type=int, default=64, help="scan pairs per step and per GPU")
     ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic scenes to cycle through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -7,6 +7,7 @@
 // (device buffers + stream) out of the context's pool; there is no global mutable state.
 // There is NO CPU fallback: without a CUDA device every entry point returns S3D_INTERNAL_ERROR.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -36,6 +37,7 @@ struct s3d_context {
   double stage_ms[S3D_N_STAGES] = {0, 0, 0, 0, 0, 0};
   uint64_t stage_launches[S3D_N_STAGES] = {0, 0, 0, 0, 0, 0};
   int max_pairs_per_launch = 32;
+  int streams_per_device = 3;
 };
 
 namespace s3d {
@@ -186,6 +188,7 @@ int s3d_create_context(const int* devices, int n_devices, s3d_context** out) {
       ctx->devs.push_back(std::move(dc));
     }
     if (const char* env = getenv("S3D_MAX_PAIRS_PER_LAUNCH")) ctx->max_pairs_per_launch = std::max(1, atoi(env));
+    if (const char* env = getenv("S3D_STREAMS_PER_DEVICE")) ctx->streams_per_device = std::max(1, atoi(env));
     *out = ctx.release();
     return S3D_OK;
   });
@@ -320,32 +323,39 @@ int s3d_gicp_align_batch(s3d_context* ctx, const s3d_cloud* sources, const s3d_c
   if (!ctx || !params || !out || n_pairs < 0 || (n_pairs > 0 && (!sources || !targets || !guesses))) return S3D_INVALID_ARGUMENT;
   if (n_pairs == 0) return S3D_OK;
   const int nd = (int)ctx->devs.size();
-  // contiguous shards, one host thread per device; no device-to-device traffic (registrations are independent)
-  std::vector<int> st(nd, S3D_OK);
-  std::vector<std::string> errs(nd);
-  auto work = [&](int d) {
+  // Contiguous shards, one per device; no device-to-device traffic (registrations are independent).  Inside a device the
+  // shard is cut into chunks that `streams_per_device` host threads push through their own workspace/stream, so the H2D
+  // copies and the per-iteration host polls of one chunk overlap with the kernels of another.
+  const int W = std::max(1, ctx->streams_per_device);
+  std::vector<int> st(nd * W, S3D_OK);
+  std::vector<std::string> errs(nd * W);
+  std::vector<std::atomic<int>> next(nd);
+  for (auto& a : next) a.store(0);
+  auto worker = [&](int d, int w) {
     const int lo = (int)((int64_t)n_pairs * d / nd), hi = (int)((int64_t)n_pairs * (d + 1) / nd);
-    st[d] = guarded([&]() -> int {
-      for (int b = lo; b < hi; b += ctx->max_pairs_per_launch) {
-        const int n = std::min(ctx->max_pairs_per_launch, hi - b);
+    const int shard = hi - lo;
+    if (shard <= 0) return;
+    const int chunk = std::max(1, std::min(ctx->max_pairs_per_launch, (shard + W - 1) / W));
+    st[d * W + w] = guarded([&]() -> int {
+      for (;;) {
+        const int c = next[d].fetch_add(1);
+        const int b = lo + c * chunk;
+        if (b >= hi) break;
+        const int n = std::min(chunk, hi - b);
         align_chunk(ctx, d, sources + b, targets + b, guesses + 16 * (size_t)b, *params, n, out + b);
       }
       return S3D_OK;
     });
-    if (st[d] != S3D_OK) errs[d] = g_last_error;
+    if (st[d * W + w] != S3D_OK) errs[d * W + w] = g_last_error;
   };
-  if (nd == 1) work(0);
+  if (nd * W == 1 || n_pairs == 1) worker(0, 0);
   else {
     std::vector<std::thread> th;
-    for (int d = 0; d < nd; ++d) th.emplace_back(work, d);
+    for (int d = 0; d < nd; ++d) for (int w = 0; w < W; ++w) th.emplace_back(worker, d, w);
     for (auto& t : th) t.join();
   }
-  for (int d = 0; d < nd; ++d)
-    if (st[d] != S3D_OK) {
-      set_error(errs[d]);
-      for (int i = 0; i < n_pairs; ++i) if (out[i].status == S3D_OK && st[d] == S3D_INTERNAL_ERROR) { /* results of other shards stay valid */ }
-      return st[d];
-    }
+  for (int i = 0; i < nd * W; ++i)
+    if (st[i] != S3D_OK) { set_error(errs[i]); return st[i]; }
   return S3D_OK;
 }
 
