@@ -168,7 +168,7 @@ def main():
     import torch
     import torch.distributed as dist
     import slam3d_b200
-    from slam3d_b200 import _abi
+    from slam3d_b200 import _abi, sharding
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -210,12 +210,10 @@ def main():
         wall = time.perf_counter() - t0
         ms = max(e0.elapsed_time(e1), 0.0)
         c1 = ctx.counters()
-        el = torch.tensor([max(ms, 1e3 * wall)], device="cuda", dtype=torch.float64)  # the call is synchronous: device span <= wall
-        ev = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(el, op=dist.ReduceOp.MAX)
-            dist.all_reduce(ev, op=dist.ReduceOp.MAX)
-        return float(ev.item()), float(el.item()), {k: c1[k] - c0[k] for k in c0}, last
+        # the call is synchronous and uses several streams: the wall span covers the device span; max over ranks
+        el = sharding.max_over_ranks(max(ms, 1e3 * wall), device="cuda")
+        ev = sharding.max_over_ranks(ms, device="cuda")
+        return ev, el, {k: c1[k] - c0[k] for k in c0}, last
 
     # ---- warm-up, then EXACTLY K timed steps with device-resident inputs --------------------------------------------------
     for _ in range(max(args.warmup, 3)):
