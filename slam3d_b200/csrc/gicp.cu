@@ -68,7 +68,8 @@ __device__ void mat4f_mul(const float* A, const float* B, float* C) {
 
 // Registration::align set-up: gates of align() :134-135, output = guess * input (transformPointCloud), state reset.
 __global__ void __launch_bounds__(256) gicp_prepare_kernel(const SlotInfo* __restrict__ slots, PairState* __restrict__ pairs, const float4* __restrict__ gpts,
-                                                           float4* __restrict__ moved, uint32_t* __restrict__ prev_nn, int32_t* __restrict__ flags) {
+                                                           float4* __restrict__ moved, uint32_t* __restrict__ prev_nn, float* __restrict__ sec_lb,
+                                                           int32_t* __restrict__ flags) {
   const uint32_t p = blockIdx.y;
   PairState& ps = pairs[p];
   const SlotInfo& sb = slots[2 * p];      // fixed cloud B  (slam3d source = PCL target)
@@ -85,12 +86,31 @@ __global__ void __launch_bounds__(256) gicp_prepare_kernel(const SlotInfo* __res
   const float3 m = transform_se3(ps.guess, v.x, v.y, v.z);
   moved[sa.off + r] = make_float4(m.x, m.y, m.z, v.w);
   prev_nn[sa.off + r] = kNoIndex;
+  sec_lb[sa.off + r] = 0.f;
+}
+
+// Temporal-coherence certificate (exactness preserving).  The last search for this point ran at position q_old and left
+// (j, lb): every fixed point other than j was at least `lb` away from q_old.  If the query moved by m and
+// dist(q_new, p_j) < lb - m, then j is still the unique nearest neighbour at q_new and no search is needed; the bound for
+// the next iteration becomes lb - m.  Generous relative slack (1e-5) covers the float rounding of dist2_pcl (4e-7).
+__device__ __forceinline__ bool certified_same_nn(const GridView& g, float3 q, float3 q_old, uint32_t j, float lb, NNResult& nn, float& lb_new) {
+  if (j >= g.n || !(lb > 0.f)) return false;
+  const float mx = q.x - q_old.x, my = q.y - q_old.y, mz = q.z - q_old.z;
+  const float m = sqrtf(mx * mx + my * my + mz * mz) * 1.00001f + 1e-7f;
+  const float rest = (lb - m) * 0.99999f;
+  if (!(rest > 0.f)) return false;
+  const float4 v = __ldg(g.pts + j);
+  const float d2 = dist2_pcl(q.x, q.y, q.z, v.x, v.y, v.z);
+  if (!(d2 * 1.00001f < rest * rest)) return false;
+  nn.d2 = d2; nn.idx = __float_as_uint(v.w); nn.pos = j; nn.lb2 = rest * rest;
+  lb_new = rest;
+  return true;
 }
 
 __global__ void __launch_bounds__(kIterTile) gicp_iter_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
                                                               const HashEntry* __restrict__ arena, const float4* __restrict__ gpts,
                                                               const float4* __restrict__ moved, const double4* __restrict__ normals,
-                                                              uint32_t* __restrict__ prev_nn, double* __restrict__ moments) {
+                                                              uint32_t* __restrict__ prev_nn, float* __restrict__ sec_lb, double* __restrict__ moments) {
   __shared__ double feat[kIterTile][kFeat];
   __shared__ double part[3][kNumMoments];
   const uint32_t p = blockIdx.y;
@@ -110,8 +130,15 @@ __global__ void __launch_bounds__(kIterTile) gicp_iter_kernel(const SlotInfo* __
     const float3 q = transform_mv(ps.T, mv.x, mv.y, mv.z);
     const double thr = ps.max_corr2;
     const float cutoff = __double2float_ru(thr);
-    const NNResult nn = nn_search(g, q.x, q.y, q.z, cutoff, prev_nn[sa.off + r]);
-    prev_nn[sa.off + r] = nn.pos;
+    const uint32_t hint = prev_nn[sa.off + r];
+    NNResult nn;
+    float lb_new;
+    if (!certified_same_nn(g, q, transform_mv(ps.T_search, mv.x, mv.y, mv.z), hint, sec_lb[sa.off + r], nn, lb_new)) {
+      nn = nn_search(g, q.x, q.y, q.z, cutoff, hint);
+      prev_nn[sa.off + r] = nn.pos;
+      lb_new = sqrtf(nn.lb2) * 0.99999f;
+    }
+    sec_lb[sa.off + r] = lb_new;
     if (nn.pos != kNoIndex && (double)nn.d2 < thr) {
       const double4 n1 = normals[sa.off + r];
       const double4 n2 = normals[sb.off + nn.pos];
@@ -176,7 +203,7 @@ __global__ void __launch_bounds__(256) gicp_solve_kernel(const SlotInfo* __restr
   double lm[kNumMoments];
   for (int i = 0; i < kNumMoments; ++i) lm[i] = mom[i];
   ps.n_corr = (uint32_t)lm[73];
-  for (int i = 0; i < 16; ++i) ps.prev[i] = ps.T[i];  // previous_transformation_ = transformation_
+  for (int i = 0; i < 16; ++i) { ps.prev[i] = ps.T[i]; ps.T_search[i] = ps.T[i]; }  // previous_transformation_ = transformation_
   int inner = 0;
   float T[16];
   for (int i = 0; i < 16; ++i) T[i] = ps.T[i];
@@ -211,7 +238,8 @@ __global__ void __launch_bounds__(256) gicp_solve_kernel(const SlotInfo* __restr
 // getFitnessScore(max_range): transformPointCloud(input, final), 1-NN, d2 <= max_range (sic), mean of d2   (A.6)
 __global__ void __launch_bounds__(kIterTile) gicp_fitness_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
                                                                  const HashEntry* __restrict__ arena, const float4* __restrict__ gpts,
-                                                                 const uint32_t* __restrict__ prev_nn, double* __restrict__ fit_partial) {
+                                                                 const float4* __restrict__ moved, const uint32_t* __restrict__ prev_nn,
+                                                                 const float* __restrict__ sec_lb, double* __restrict__ fit_partial) {
   __shared__ double ssum[kIterTile];
   __shared__ uint32_t scnt[kIterTile];
   const uint32_t p = blockIdx.y;
@@ -227,7 +255,12 @@ __global__ void __launch_bounds__(kIterTile) gicp_fitness_kernel(const SlotInfo*
     const GridView g = make_grid_view(sb, arena, gpts);
     const float4 v = gpts[sa.off + r];
     const float3 q = transform_se3(ps.final_T, v.x, v.y, v.z);
-    const NNResult nn = nn_search(g, q.x, q.y, q.z, __double2float_ru(ps.fit_range), prev_nn[sa.off + r]);
+    const float4 mv = moved[sa.off + r];
+    const uint32_t hint = prev_nn[sa.off + r];
+    NNResult nn;
+    float lb_new;
+    if (!certified_same_nn(g, q, transform_mv(ps.T_search, mv.x, mv.y, mv.z), hint, sec_lb[sa.off + r], nn, lb_new))
+      nn = nn_search(g, q.x, q.y, q.z, __double2float_ru(ps.fit_range), hint);
     if (nn.pos != kNoIndex && (double)nn.d2 <= ps.fit_range) { s = (double)nn.d2; c = 1; }
   }
   ssum[threadIdx.x] = s; scnt[threadIdx.x] = c;
@@ -309,6 +342,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   ws.h_pairs.reserve(sizeof(PairState) * np);
   ws.moved.reserve(16 * std::max<size_t>(ws.total, 4));
   ws.prev_nn.reserve(4 * std::max<size_t>(ws.total, 4));
+  ws.sec_lb.reserve(4 * std::max<size_t>(ws.total, 4));
   ws.moments.reserve(sizeof(double) * kNumMoments * size_t(tiles_per_pair) * np);
   ws.fit_partial.reserve(sizeof(double) * 2 * size_t(tiles_per_pair) * np);
   PairState* hp = ws.h_pairs.as<PairState>();
@@ -333,7 +367,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   int32_t* flags = ws.flags.as<int32_t>();
   int32_t* h_flags = ws.h_small.as<int32_t>();
   dim3 grid(tiles_per_pair, np);
-  gicp_prepare_kernel<<<grid, 256, 0, st>>>(slots, pairs, ws.gpts.as<float4>(), ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), flags);
+  gicp_prepare_kernel<<<grid, 256, 0, st>>>(slots, pairs, ws.gpts.as<float4>(), ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), flags);
   ++ws.launches;
   // PCL's loop is a do-while: with maximum_iterations <= 0 it still runs one iteration
   const int iters = std::max(max_iter, 1);
@@ -342,7 +376,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
     {
       StageTimer timer(ws, kStageIter);
       gicp_iter_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.hash.as<HashEntry>(), ws.gpts.as<float4>(), ws.moved.as<float4>(),
-                                                   ws.normals.as<double4>(), ws.prev_nn.as<uint32_t>(), ws.moments.as<double>());
+                                                   ws.normals.as<double4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), ws.moments.as<double>());
       ++ws.launches;
     }
     {
@@ -364,8 +398,8 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   }
   {
     StageTimer timer(ws, kStageFitness);
-    gicp_fitness_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.hash.as<HashEntry>(), ws.gpts.as<float4>(), ws.prev_nn.as<uint32_t>(),
-                                                    ws.fit_partial.as<double>());
+    gicp_fitness_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.hash.as<HashEntry>(), ws.gpts.as<float4>(), ws.moved.as<float4>(),
+                                                    ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), ws.fit_partial.as<double>());
     gicp_fitness_reduce_kernel<<<(np + 63) / 64, 64, 0, st>>>(slots, pairs, ws.fit_partial.as<double>(), tiles_per_pair, np);
     ws.launches += 2;
   }

@@ -58,6 +58,7 @@ struct PairState {
   float  T[16];            // transformation_
   float  prev[16];         // previous_transformation_
   float  final_T[16];      // final_transformation_ = previous * guess
+  float  T_search[16];     // the transformation_ the last correspondence search ran with (temporal-coherence certificate)
   double RRt[3][3];        // (T*guess).R (T*guess).R^T for the Mahalanobis matrices of this iteration
   double R[3][3];
   double max_corr2;        // corr_dist_threshold_^2
@@ -95,6 +96,7 @@ struct Workspace {
   DevBuf normals;                             // double[total*4]  unit normal of the regularised covariance (+pad)
   DevBuf moved;                               // float4[total]   guess * A (Morton order of A)
   DevBuf prev_nn;                             // uint32[total]   last correspondence (warm start bound)
+  DevBuf sec_lb;                              // float[total]    lower bound of the distance to every OTHER fixed point at the last search position
   DevBuf moments;                             // double[iter_tiles * 74]
   DevBuf iter_tile_pair, iter_tile_first;     // uint32[iter_tiles]
   uint32_t iter_tiles = 0;

@@ -47,7 +47,9 @@ __device__ __forceinline__ float block_guarantee2(const GridView& g, float ux, f
   return block_guarantee2(g, ux, uy, uz, L, cx, cy, cz, ax, ay, az);
 }
 
-struct NNResult { float d2; uint32_t idx; uint32_t pos; };
+// lb2: lower bound of the squared distance from the query to every reference point OTHER than the winner
+// (second-best scanned candidate, pruned cells, and the coverage radius of the last block).
+struct NNResult { float d2; uint32_t idx; uint32_t pos; float lb2; };
 
 __device__ __forceinline__ bool cand_less(float d2, uint32_t idx, float bd2, uint32_t bidx) { return d2 < bd2 || (d2 == bd2 && idx < bidx); }
 
@@ -80,7 +82,8 @@ __device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int
     if (prune) {
       const float fx = dx == 0 ? ax : (dx == 1 ? 0.f : 1.f - ax), fy = dy == 0 ? ay : (dy == 1 ? 0.f : 1.f - ay), fz = dz == 0 ? az : (dz == 1 ? 0.f : 1.f - az);
       const float rx = fmaxf(fx * hl - g.margin, 0.f), ry = fmaxf(fy * hl - g.margin, 0.f), rz = fmaxf(fz * hl - g.margin, 0.f);
-      if ((rx * rx + ry * ry + rz * rz) * 0.99999f > best.d2) continue;
+      const float cell_lb = (rx * rx + ry * ry + rz * rz) * 0.99999f;
+      if (cell_lb > best.d2) { best.lb2 = fminf(best.lb2, cell_lb); continue; }
     }
     uint32_t begin, end;
     if (!cell_range(g.table, g.cap, g.nlev, L, ix, iy, iz, begin, end)) continue;
@@ -88,7 +91,8 @@ __device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int
       const float4 v = __ldg(g.pts + p);
       const float d2 = dist2_pcl(qx, qy, qz, v.x, v.y, v.z);
       const uint32_t id = __float_as_uint(v.w);
-      if (cand_less(d2, id, best.d2, best.idx)) { best.d2 = d2; best.idx = id; best.pos = p; }
+      if (cand_less(d2, id, best.d2, best.idx)) { best.lb2 = fminf(best.lb2, best.d2); best.d2 = d2; best.idx = id; best.pos = p; }
+      else if (id != best.idx) best.lb2 = fminf(best.lb2, d2);  // the winner itself is met again when a level is rescanned
     }
   }
 }
@@ -96,7 +100,7 @@ __device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int
 // Exact 1-NN.  cutoff2: distances above it are of no interest (search may stop once the block covers that radius);
 // hint_pos: sorted position of a candidate whose distance bounds the search (previous correspondence) or kNoIndex.
 __device__ __forceinline__ NNResult nn_search(const GridView& g, float qx, float qy, float qz, float cutoff2, uint32_t hint_pos) {
-  NNResult best{INFINITY, kNoIndex, kNoIndex};
+  NNResult best{INFINITY, kNoIndex, kNoIndex, INFINITY};
   if (g.n == 0 || g.cap == 0) return best;
   const float ux = clamp_coord(grid_coord(qx, g.ox, g.inv_h0));
   const float uy = clamp_coord(grid_coord(qy, g.oy, g.inv_h0));
@@ -119,7 +123,8 @@ __device__ __forceinline__ NNResult nn_search(const GridView& g, float qx, float
     const bool top = L >= g.nlev - 1;
     if (top) cx = cy = cz = 0;  // 2 cells per axis: the block around cell 0 is the whole cloud, wherever the query is
     scan_block(g, L, cx, cy, cz, ax, ay, az, !top, qx, qy, qz, best);
-    if (best.d2 <= g2 || g2 >= cutoff2 || top) break;
+    if (top) break;                                   // the block was the whole cloud
+    if (best.d2 <= g2 || g2 >= cutoff2) { best.lb2 = fminf(best.lb2, g2); break; }  // everything outside the block is farther than sqrt(g2)
   }
   return best;
 }
