@@ -21,6 +21,13 @@ namespace s3d {
 
 constexpr int kKnnThreads = 128;  // queries per CTA (one thread per query)
 
+#ifdef S3D_KNN_STATS
+__device__ unsigned long long g_knn_stats[8];  // queries, level scans, cells probed, cells pruned, candidates, pushes, sift-downs, start-level probes
+#define KSTAT(i, v) atomicAdd(&g_knn_stats[i], (unsigned long long)(v))
+#else
+#define KSTAT(i, v)
+#endif
+
 // max-heap of 64-bit keys in shared memory, element j of thread t at h[j * kKnnThreads]
 __device__ __forceinline__ void heap_push(uint64_t* h, int& n, uint64_t x) {
   int i = n++;
@@ -74,12 +81,14 @@ __global__ void __launch_bounds__(kKnnThreads) knn_cov_kernel(const SlotInfo* __
   const float uy = clamp_coord(grid_coord(qv.y, g.oy, g.inv_h0));
   const float uz = clamp_coord(grid_coord(qv.z, g.oz, g.inv_h0));
 
+  KSTAT(0, 1);
   // ---- start level: smallest L whose parent cell (level L+1) already holds >= 12 points ------------------------------
   int L = g.nlev - 1;
   {
     const int c0x = (int)floorf(ux), c0y = (int)floorf(uy), c0z = (int)floorf(uz);
     for (int lv = 1; lv < g.nlev; ++lv) {
       uint32_t b, e;
+      KSTAT(7, 1);
       if (cell_range(g.table, g.cap, g.nlev, lv, c0x >> lv, c0y >> lv, c0z >> lv, b, e) && (e - b) >= 12u) { L = lv - 1; break; }
     }
   }
@@ -93,6 +102,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_cov_kernel(const SlotInfo* __
     const bool top = L >= g.nlev - 1;
     if (top) cx = cy = cz = 0;
     cnt = 0;
+    KSTAT(1, 1);
     uint64_t tau = bound;                                   // current admission threshold (inclusive while not full)
     float tau_d2 = __uint_as_float((uint32_t)(tau >> 32));  // KMAX -> NaN bits: comparisons stay false, nothing is pruned
     const int dim = 1 << (g.nlev - L);
@@ -106,10 +116,12 @@ __global__ void __launch_bounds__(kKnnThreads) knn_cov_kernel(const SlotInfo* __
       if (!top) {
         const float fx = dx == 0 ? ax : (dx == 1 ? 0.f : 1.f - ax), fy = dy == 0 ? ay : (dy == 1 ? 0.f : 1.f - ay), fz = dz == 0 ? az : (dz == 1 ? 0.f : 1.f - az);
         const float rx = fmaxf(fx * hl - g.margin, 0.f), ry = fmaxf(fy * hl - g.margin, 0.f), rz = fmaxf(fz * hl - g.margin, 0.f);
-        if ((rx * rx + ry * ry + rz * rz) * 0.99999f > tau_d2) continue;  // the whole cell is farther than the k-th best / the bound
+        if ((rx * rx + ry * ry + rz * rz) * 0.99999f > tau_d2) { KSTAT(3, 1); continue; }  // the whole cell is farther than the k-th best / the bound
       }
       uint32_t begin, end;
+      KSTAT(2, 1);
       if (!cell_range(g.table, g.cap, g.nlev, L, ix, iy, iz, begin, end)) continue;
+      KSTAT(4, end - begin);
       for (uint32_t p = begin; p < end; ++p) {
         const float4 v = __ldg(g.pts + p);
         const float cd = dist2_pcl(qv.x, qv.y, qv.z, v.x, v.y, v.z);
@@ -117,11 +129,11 @@ __global__ void __launch_bounds__(kKnnThreads) knn_cov_kernel(const SlotInfo* __
         const uint64_t ck = ((uint64_t)__float_as_uint(cd) << 32) | (uint64_t)__float_as_uint(v.w);
         if (cnt < kk) {
           if (ck <= bound) {
-            heap_push(h, cnt, ck);
+            heap_push(h, cnt, ck); KSTAT(5, 1);
             if (cnt == kk) { tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32)); }
           }
         } else if (ck < tau) {
-          heap_sift_down(h, kk, ck);
+          heap_sift_down(h, kk, ck); KSTAT(6, 1);
           tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
         }
       }
@@ -195,6 +207,14 @@ void run_knn_covariances(Workspace& ws, int k, uint32_t* knn_index, float* knn_d
   ++ws.launches;
   S3D_CUDA(cudaGetLastError());
 }
+
+#ifdef S3D_KNN_STATS
+extern "C" void s3d_debug_knn_stats(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_knn_stats, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_knn_stats, z, sizeof z); }
+}
+#endif
 
 void run_expand_cov(Workspace& ws, double* cov_out) {
   uint32_t max_n = 0;
