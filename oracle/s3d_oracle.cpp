@@ -38,6 +38,8 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -636,6 +638,9 @@ static bool gicp_register(const std::vector<P4>& pcl_source, const std::vector<P
       if (cd > delta) delta = cd;
     }
     ++out.outer_iterations;
+    if (std::getenv("S3D_ORACLE_TRACE"))
+      std::fprintf(stderr, "[oracle trace] outer=%d inner=%d ncorr=%u delta=%.4g t=(%.9g %.9g %.9g) r10=%.9g r20=%.9g r21=%.9g\n", out.outer_iterations,
+                   out.inner_iterations, out.n_corr, delta, T(0, 3), T(1, 3), T(2, 3), T(1, 0), T(2, 0), T(2, 1));
     if (out.outer_iterations >= cfg.maximum_iterations || delta < 1) { out.converged = true; prev = T; }
   }
   out.final_T = m4f_mul(prev, guess);

@@ -1,19 +1,25 @@
 // gicp.cu — the Generalized-ICP loop of pcl::GeneralizedIterativeClosestPoint as driven by slam3d's doICP
 // (slam3d/sensor/pcl/PointCloudSensor.cpp:52-82) and the fitness score of :73.   Semantics: SURVEY A.4-A.6.
 //
-// Per outer iteration TWO launches for the whole batch of pairs, no host arithmetic:
-//   gicp_iter_kernel   one thread per moving point:  q = T_f32 * (guess_f32 * p)  ->  exact 1-NN in the fixed cloud
-//                      (nn_search.cuh, warm-started by the previous correspondence)  ->  d2 < max_corr^2  ->
-//                      M = (R C1 R^T + C2)^-1 (FP64)  ->  the point's 14 features go to shared memory and the CTA
-//                      reduces them to the 74 sufficient statistics of the GICP objective (gicp_math.h) in a fixed
-//                      order  ->  one 74-double partial per 256-point tile.
-//   gicp_solve_kernel  one CTA per pair: fixed-order sum of the tile partials, then ONE thread runs PCL's complete
-//                      inner optimiser (estimateRigidTransformationNewton, <= maximum_optimizer_iterations steps with
-//                      back-tracking) on the statistics, applies PCL's convergence test and updates the pair state.
-// The host only polls an "active pairs" counter.  Reductions use fixed trees (tile partials, ordered sums): results
-// are bit-reproducible run to run and independent of batch composition.
-// Roofline: per iteration 16 B (moving point) + 32 B (its normal) + gathered 16 B + 32 B (fixed point + normal) per
-// correspondence; the working set is L2 resident, the kernel is latency bound on the hash probes.
+// The loop runs in ROUNDS of four launches for the whole batch; every pair carries its own phase, so pairs advance
+// independently and the host only polls an "active pairs" counter:
+//   gicp_iter_kernel   pairs that start an outer iteration.  One thread per moving point:  q = T_f32 * (guess_f32 * p)  ->
+//                      exact 1-NN in the fixed cloud (nn_search.cuh; skipped when the previous correspondence is provably
+//                      still nearest)  ->  d2 < max_corr^2  ->  M = (R C1 R^T + C2)^-1 (FP64, stored)  ->  the CTA reduces
+//                      the point's 14 features to the 74 sums of gicp_math.h in a fixed order: 60 x-independent sums that
+//                      give the whole Hessian, and the 13 residual sums + count of PCL's first objective evaluation.
+//   gicp_ctrl_kernel   one CTA per pair: fixed-order sum of the tile partials, then ONE thread advances PCL's inner
+//                      optimiser (estimateRigidTransformationNewton as a resumable state machine) to its next objective
+//                      evaluation, or finishes the outer iteration (convergence test of computeTransformation).
+//   gicp_eval_kernel   pairs whose optimiser asked for f at a trial state: one pass over the stored correspondences with the
+//                      residual formed exactly as PCL forms it (float32 T(x)*p, float subtraction) -> 13 sums per tile.
+//   gicp_ctrl_kernel   again.
+// Because every float operation that PCL's decisions depend on is mirrored and the double sums differ only in order, the
+// GPU follows the oracle's iterate sequence (same inner/outer iteration counts, bit-identical poses in the test-suite).
+// Reductions use fixed trees: results are bit-reproducible run to run and independent of batch composition.
+// Roofline: per outer iteration 16 B (moving point) + 32 B (its normal) + gathered 16 B + 32 B (fixed point + normal) per
+// correspondence, + 48 B (M) written; per evaluation 16 + 16 + 48 B.  The working set is L2 resident; the search is latency
+// bound on the hash probes.
 #include <cstdio>
 #include <cstdlib>
 
@@ -22,7 +28,7 @@
 
 namespace s3d {
 
-constexpr int kFeat = 14;  // M00 M01 M02 M11 M12 M22 | px py pz | Mq0 Mq1 Mq2 | qMq | valid
+constexpr int kFeat = 14;  // M00 M01 M02 M11 M12 M22 | px py pz | (Md)0 (Md)1 (Md)2 | d^T M d | valid
 
 struct MomentSpec { uint8_t a, b, c; };  // moment = sum f[a]*f[b]*f[c]
 __constant__ MomentSpec c_spec[kNumMoments];
@@ -66,6 +72,14 @@ __device__ void mat4f_mul(const float* A, const float* B, float* C) {
                                __fmul_rn(A[12 + r], B[c * 4 + 3]));
 }
 
+// start of an outer iteration: x0 from transformation_, the float matrix PCL's first evaluation uses, and R for the Mahalanobis matrices
+__device__ void begin_outer(PairState& ps) {
+  newton_begin(ps.nst, ps.T);
+  matrix_from_state(ps.nst.xc, ps.T_eval);
+  update_rotation(ps);
+  ps.phase = kPhaseNeedNN;
+}
+
 // Registration::align set-up: gates of align() :134-135, output = guess * input (transformPointCloud), state reset.
 __global__ void __launch_bounds__(256) gicp_prepare_kernel(const SlotInfo* __restrict__ slots, PairState* __restrict__ pairs, const float4* __restrict__ gpts,
                                                            float4* __restrict__ moved, uint32_t* __restrict__ prev_nn, float* __restrict__ sec_lb,
@@ -77,7 +91,8 @@ __global__ void __launch_bounds__(256) gicp_prepare_kernel(const SlotInfo* __res
   const bool enough = sa.n_pts >= 100 && sb.n_pts >= 100;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ps.active = enough ? 1 : 0;
-    if (enough) { update_rotation(ps); atomicAdd(&flags[1], 1); }
+    ps.phase = kPhaseFinished;
+    if (enough) { begin_outer(ps); atomicAdd(&flags[1], 1); }
   }
   if (!enough) return;
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,12 +125,13 @@ __device__ __forceinline__ bool certified_same_nn(const GridView& g, float3 q, f
 __global__ void __launch_bounds__(kIterTile) gicp_iter_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
                                                               const HashEntry* __restrict__ arena, const float4* __restrict__ gpts,
                                                               const float4* __restrict__ moved, const double4* __restrict__ normals,
-                                                              uint32_t* __restrict__ prev_nn, float* __restrict__ sec_lb, double* __restrict__ moments) {
+                                                              uint32_t* __restrict__ prev_nn, float* __restrict__ sec_lb, uint32_t* __restrict__ corr,
+                                                              double* __restrict__ mahal, double* __restrict__ moments) {
   __shared__ double feat[kIterTile][kFeat];
   __shared__ double part[3][kNumMoments];
   const uint32_t p = blockIdx.y;
   const PairState& ps = pairs[p];
-  if (!ps.active) return;
+  if (ps.phase != kPhaseNeedNN) return;
   const SlotInfo& sb = slots[2 * p];
   const SlotInfo& sa = slots[2 * p + 1];
   const uint32_t first = blockIdx.x * kIterTile;
@@ -139,30 +155,38 @@ __global__ void __launch_bounds__(kIterTile) gicp_iter_kernel(const SlotInfo* __
       lb_new = sqrtf(nn.lb2) * 0.99999f;
     }
     sec_lb[sa.off + r] = lb_new;
+    uint32_t c = kNoIndex;
     if (nn.pos != kNoIndex && (double)nn.d2 < thr) {
+      c = nn.pos;
       const double4 n1 = normals[sa.off + r];
       const double4 n2 = normals[sb.off + nn.pos];
       double a[3], b[3] = {n2.x, n2.y, n2.z};
       for (int i = 0; i < 3; ++i) a[i] = ps.R[i][0] * n1.x + ps.R[i][1] * n1.y + ps.R[i][2] * n1.z;
       double M[6];
       mahalanobis6(ps.RRt, a, b, M);
+      double* mo = mahal + 6 * (size_t)(sa.off + r);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) mo[i] = M[i];
+      // PCL's first objective evaluation of this outer iteration: d = float(T(x0) * p) - q, float subtraction, then double
       const float4 qb = g.pts[nn.pos];
-      const double qx = qb.x, qy = qb.y, qz = qb.z;
-      const double Mq0 = M[0] * qx + M[1] * qy + M[2] * qz;
-      const double Mq1 = M[1] * qx + M[3] * qy + M[4] * qz;
-      const double Mq2 = M[2] * qx + M[4] * qy + M[5] * qz;
+      const float3 pp = transform_mv(ps.T_eval, mv.x, mv.y, mv.z);
+      const double d0 = (double)__fsub_rn(pp.x, qb.x), d1 = (double)__fsub_rn(pp.y, qb.y), d2 = (double)__fsub_rn(pp.z, qb.z);
+      const double Md0 = M[0] * d0 + M[1] * d1 + M[2] * d2;
+      const double Md1 = M[1] * d0 + M[3] * d1 + M[4] * d2;
+      const double Md2 = M[2] * d0 + M[4] * d1 + M[5] * d2;
 #pragma unroll
       for (int i = 0; i < 6; ++i) f[i] = M[i];
       f[6] = mv.x; f[7] = mv.y; f[8] = mv.z;
-      f[9] = Mq0; f[10] = Mq1; f[11] = Mq2;
-      f[12] = qx * Mq0 + qy * Mq1 + qz * Mq2;
+      f[9] = Md0; f[10] = Md1; f[11] = Md2;
+      f[12] = d0 * Md0 + d1 * Md1 + d2 * Md2;
       f[13] = 1.0;
     }
+    corr[sa.off + r] = c;
   }
 #pragma unroll
   for (int i = 0; i < kFeat; ++i) feat[threadIdx.x][i] = f[i];
   __syncthreads();
-  // 74 statistics x 3 sub-ranges of the tile, each summed in ascending point order
+  // 74 sums x 3 sub-ranges of the tile, each summed in ascending point order
   if (threadIdx.x < 3 * kNumMoments) {
     const int m = threadIdx.x % kNumMoments, sub = threadIdx.x / kNumMoments;
     const MomentSpec sp = c_spec[m];
@@ -178,40 +202,67 @@ __global__ void __launch_bounds__(kIterTile) gicp_iter_kernel(const SlotInfo* __
   }
 }
 
-// one CTA per pair: ordered reduction of the tile partials + PCL's inner optimiser + outer-loop bookkeeping (A.4)
-__global__ void __launch_bounds__(256) gicp_solve_kernel(const SlotInfo* __restrict__ slots, PairState* __restrict__ pairs,
-                                                         const double* __restrict__ moments, uint32_t tiles_per_pair, int32_t* __restrict__ flags) {
-  __shared__ double part[3][kNumMoments];
-  __shared__ double mom[kNumMoments];
-  const uint32_t p = blockIdx.x;
-  PairState& ps = pairs[p];
-  if (!ps.active) return;
-  const uint32_t n_tiles = (slots[2 * p + 1].n_pts + kIterTile - 1) / kIterTile;
-  if (threadIdx.x < 3 * kNumMoments) {
-    const int m = threadIdx.x % kNumMoments, sub = threadIdx.x / kNumMoments;
-    const uint32_t per = (n_tiles + 2) / 3;
-    const uint32_t lo = sub * per, hi = min(n_tiles, lo + per);
-    const double* src = moments + (size_t)p * tiles_per_pair * kNumMoments + m;
-    double s = 0.0;
-    for (uint32_t t = lo; t < hi; ++t) s += src[(size_t)t * kNumMoments];
-    part[sub][m] = s;
+// One objective evaluation at the trial state of every pair in kPhaseEval: the 13 residual sums per 256-point tile.
+__global__ void __launch_bounds__(kIterTile) gicp_eval_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
+                                                              const float4* __restrict__ gpts, const float4* __restrict__ moved,
+                                                              const uint32_t* __restrict__ corr, const double* __restrict__ mahal,
+                                                              double* __restrict__ eval_part) {
+  __shared__ double feat[kIterTile][8];  // px py pz | (Md)0..2 | d^T M d | 1
+  __shared__ double part[16][kEvalSums];
+  const uint32_t p = blockIdx.y;
+  const PairState& ps = pairs[p];
+  if (ps.phase != kPhaseEval) return;
+  const SlotInfo& sb = slots[2 * p];
+  const SlotInfo& sa = slots[2 * p + 1];
+  const uint32_t first = blockIdx.x * kIterTile;
+  if (first >= sa.n_pts) return;
+  const uint32_t r = first + threadIdx.x;
+  double f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (r < sa.n_pts) {
+    const uint32_t c = corr[sa.off + r];
+    if (c != kNoIndex) {
+      const float4 mv = moved[sa.off + r];
+      const float4 qb = gpts[sb.off + c];
+      const double* M = mahal + 6 * (size_t)(sa.off + r);
+      const float3 pp = transform_mv(ps.T_eval, mv.x, mv.y, mv.z);
+      const double d0 = (double)__fsub_rn(pp.x, qb.x), d1 = (double)__fsub_rn(pp.y, qb.y), d2 = (double)__fsub_rn(pp.z, qb.z);
+      const double Md0 = M[0] * d0 + M[1] * d1 + M[2] * d2;
+      const double Md1 = M[1] * d0 + M[3] * d1 + M[4] * d2;
+      const double Md2 = M[2] * d0 + M[4] * d1 + M[5] * d2;
+      f[0] = mv.x; f[1] = mv.y; f[2] = mv.z; f[3] = Md0; f[4] = Md1; f[5] = Md2;
+      f[6] = d0 * Md0 + d1 * Md1 + d2 * Md2; f[7] = 1.0;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) feat[threadIdx.x][i] = f[i];
+  __syncthreads();
+  // sum s (0..11: (Md)_a * phi_c with a = s / 4, c = s % 4; 12: d^T M d) over 16 sub-ranges of 16 points, ascending order
+  if (threadIdx.x < 16 * kEvalSums) {
+    const int sidx = threadIdx.x % kEvalSums, sub = threadIdx.x / kEvalSums;
+    const int ia = sidx < 12 ? 3 + sidx / 4 : 6;
+    const int ib = sidx < 12 ? (sidx % 4 < 3 ? sidx % 4 : 7) : 7;
+    double acc = 0.0;
+    for (int i = sub * 16; i < sub * 16 + 16; ++i) acc += feat[i][ia] * feat[i][ib];
+    part[sub][sidx] = acc;
   }
   __syncthreads();
-  if (threadIdx.x < kNumMoments) mom[threadIdx.x] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x];
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  double lm[kNumMoments];
-  for (int i = 0; i < kNumMoments; ++i) lm[i] = mom[i];
-  ps.n_corr = (uint32_t)lm[73];
-  for (int i = 0; i < 16; ++i) { ps.prev[i] = ps.T[i]; ps.T_search[i] = ps.T[i]; }  // previous_transformation_ = transformation_
-  int inner = 0;
-  float T[16];
-  for (int i = 0; i < 16; ++i) T[i] = ps.T[i];
+  if (threadIdx.x < kEvalSums) {
+    double acc = 0.0;
+    for (int sub = 0; sub < 16; ++sub) acc += part[sub][threadIdx.x];
+    const size_t tile = (size_t)p * gridDim.x + blockIdx.x;
+    eval_part[tile * kEvalSums + threadIdx.x] = acc;
+  }
+}
+
+// End of an outer iteration (computeTransformation): convergence test, counters, next iteration or final transform.
+__device__ void finish_outer(PairState& ps, bool optimiser_failed, int32_t* flags) {
   bool stop = false;
-  if (!newton_from_moments(lm, T, ps.max_inner, &inner)) {
+  if (optimiser_failed) {
     ps.failed = 1; ps.converged = 0; stop = true;  // optimiser exception: loop breaks, converged_ stays false, final = previous * guess
   } else {
-    ps.inner_iterations += inner;
+    float T[16];
+    matrix_from_state(ps.nst.x, T);  // transformation_matrix.setIdentity(); applyState(transformation_matrix, x)
+    ps.inner_iterations += ps.nst.it;
     double delta = 0.0;
     for (int r = 0; r < 4; ++r)
       for (int c = 0; c < 4; ++c) {
@@ -224,14 +275,55 @@ __global__ void __launch_bounds__(256) gicp_solve_kernel(const SlotInfo* __restr
     if (ps.outer_iterations >= ps.max_iter || delta < 1.0) {
       ps.converged = 1; stop = true;
       for (int i = 0; i < 16; ++i) ps.prev[i] = T[i];  // previous_transformation_ = transformation_
-    } else {
-      update_rotation(ps);
     }
   }
   if (stop) {
     mat4f_mul(ps.prev, ps.guess, ps.final_T);  // final_transformation_ = previous_transformation_ * guess
     ps.active = 0;
+    ps.phase = kPhaseFinished;
     atomicSub(&flags[1], 1);
+  } else {
+    begin_outer(ps);
+  }
+}
+
+// one CTA per pair: ordered reduction of the tile partials of the pass that just ran, then one thread advances the optimiser
+__global__ void __launch_bounds__(256) gicp_ctrl_kernel(const SlotInfo* __restrict__ slots, PairState* __restrict__ pairs,
+                                                        const double* __restrict__ moments, const double* __restrict__ eval_part,
+                                                        uint32_t tiles_per_pair, int after_eval, int32_t* __restrict__ flags) {
+  __shared__ double part[3][kNumMoments];
+  const uint32_t p = blockIdx.x;
+  PairState& ps = pairs[p];
+  // the first ctrl launch of a round serves pairs that just searched, the second one pairs that were just evaluated
+  if (ps.phase != (after_eval ? kPhaseEval : kPhaseNeedNN)) return;
+  const uint32_t n_tiles = (slots[2 * p + 1].n_pts + kIterTile - 1) / kIterTile;
+  const int n_sums = after_eval ? kEvalSums : kNumMoments;
+  const int stride = n_sums;
+  const double* src0 = after_eval ? eval_part + (size_t)p * tiles_per_pair * kEvalSums : moments + (size_t)p * tiles_per_pair * kNumMoments;
+  if ((int)threadIdx.x < 3 * n_sums) {
+    const int m = threadIdx.x % n_sums, sub = threadIdx.x / n_sums;
+    const uint32_t per = (n_tiles + 2) / 3;
+    const uint32_t lo = sub * per, hi = min(n_tiles, lo + per);
+    const double* src = src0 + m;
+    double s = 0.0;
+#pragma unroll 4
+    for (uint32_t t = lo; t < hi; ++t) s += src[(size_t)t * stride];
+    part[sub][m] = s;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < n_sums) ps.sums[(after_eval ? 60 : 0) + threadIdx.x] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  if (!after_eval) {
+    ps.n_corr = (uint32_t)ps.sums[73];
+    for (int i = 0; i < 16; ++i) { ps.prev[i] = ps.T[i]; ps.T_search[i] = ps.T[i]; }  // previous_transformation_ = transformation_
+    if (ps.sums[73] < 4.0) { finish_outer(ps, true, flags); return; }  // min_number_correspondences_: PCL throws
+  }
+  if (newton_advance(ps.nst, ps.sums, ps.max_inner)) {
+    matrix_from_state(ps.nst.xc, ps.T_eval);
+    ps.phase = kPhaseEval;
+  } else {
+    finish_outer(ps, false, flags);
   }
 }
 
@@ -344,6 +436,9 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   ws.prev_nn.reserve(4 * std::max<size_t>(ws.total, 4));
   ws.sec_lb.reserve(4 * std::max<size_t>(ws.total, 4));
   ws.moments.reserve(sizeof(double) * kNumMoments * size_t(tiles_per_pair) * np);
+  ws.eval_part.reserve(sizeof(double) * kEvalSums * size_t(tiles_per_pair) * np);
+  ws.corr.reserve(4 * std::max<size_t>(ws.total, 4));
+  ws.mahal.reserve(48 * std::max<size_t>(ws.total, 4));
   ws.fit_partial.reserve(sizeof(double) * 2 * size_t(tiles_per_pair) * np);
   PairState* hp = ws.h_pairs.as<PairState>();
   int max_iter = 0;
@@ -369,20 +464,25 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   dim3 grid(tiles_per_pair, np);
   gicp_prepare_kernel<<<grid, 256, 0, st>>>(slots, pairs, ws.gpts.as<float4>(), ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), flags);
   ++ws.launches;
-  // PCL's loop is a do-while: with maximum_iterations <= 0 it still runs one iteration
-  const int iters = std::max(max_iter, 1);
+  // Rounds: [search + first evaluation] -> ctrl -> [trial evaluation] -> ctrl.  A pair needs one round per outer iteration
+  // plus one per extra objective evaluation; PCL's loop is a do-while, so maximum_iterations <= 0 still runs one iteration.
   const bool trace = getenv("S3D_TRACE") != nullptr;
-  for (int it = 0; it < iters; ++it) {
+  const long max_rounds = (long)std::max(max_iter, 1) * 64 + 64;
+  for (long round = 0; round < max_rounds; ++round) {
     {
       StageTimer timer(ws, kStageIter);
       gicp_iter_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.hash.as<HashEntry>(), ws.gpts.as<float4>(), ws.moved.as<float4>(),
-                                                   ws.normals.as<double4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), ws.moments.as<double>());
+                                                   ws.normals.as<double4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), ws.corr.as<uint32_t>(),
+                                                   ws.mahal.as<double>(), ws.moments.as<double>());
       ++ws.launches;
     }
     {
       StageTimer timer(ws, kStageSolve);
-      gicp_solve_kernel<<<np, 256, 0, st>>>(slots, pairs, ws.moments.as<double>(), tiles_per_pair, flags);
-      ++ws.launches;
+      gicp_ctrl_kernel<<<np, 256, 0, st>>>(slots, pairs, ws.moments.as<double>(), ws.eval_part.as<double>(), tiles_per_pair, 0, flags);
+      gicp_eval_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.gpts.as<float4>(), ws.moved.as<float4>(), ws.corr.as<uint32_t>(),
+                                                   ws.mahal.as<double>(), ws.eval_part.as<double>());
+      gicp_ctrl_kernel<<<np, 256, 0, st>>>(slots, pairs, ws.moments.as<double>(), ws.eval_part.as<double>(), tiles_per_pair, 1, flags);
+      ws.launches += 3;
     }
     S3D_CUDA(cudaMemcpyAsync(h_flags, flags, 16, cudaMemcpyDeviceToHost, st));
     S3D_CUDA(cudaStreamSynchronize(st));
@@ -390,8 +490,8 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
     if (trace) {
       S3D_CUDA(cudaMemcpy(hp, pairs, sizeof(PairState) * np, cudaMemcpyDeviceToHost));
       for (uint32_t p = 0; p < np; ++p)
-        fprintf(stderr, "[s3d trace] it=%d pair=%u active=%d outer=%d inner=%d ncorr=%u t=(%.9g %.9g %.9g) r10=%.9g r20=%.9g r21=%.9g\n", it, p,
-                hp[p].active, hp[p].outer_iterations, hp[p].inner_iterations, hp[p].n_corr, hp[p].T[12], hp[p].T[13], hp[p].T[14], hp[p].T[1],
+        fprintf(stderr, "[s3d trace] round=%ld pair=%u phase=%d outer=%d inner=%d ncorr=%u t=(%.9g %.9g %.9g) r10=%.9g r20=%.9g r21=%.9g\n", round, p,
+                hp[p].phase, hp[p].outer_iterations, hp[p].inner_iterations, hp[p].n_corr, hp[p].T[12], hp[p].T[13], hp[p].T[14], hp[p].T[1],
                 hp[p].T[2], hp[p].T[6]);
     }
     if (h_flags[1] <= 0) break;

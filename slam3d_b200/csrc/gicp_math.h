@@ -3,19 +3,15 @@
 // What it computes (reference: PCL gicp.hpp as driven by slam3d doICP, PointCloudSensor.cpp:52-82):
 //   * closed 3x3 / 6x6 symmetric eigen-decompositions (cyclic Jacobi) — covariance regularisation and the
 //     Newton step of estimateRigidTransformationNewton;
-//   * the GICP objective f(x) = 1/m sum r^T M r, r = R(x) p + t - q, its exact gradient and Hessian in the
-//     (t, ZYX-Euler) parametrisation, evaluated from 74 sufficient statistics ("moments") of the current
-//     correspondence set instead of a pass over the points.  The statistics are accumulated once per outer
-//     iteration by the fused correspondence kernel (gicp.cu), so the whole inner Newton loop of PCL runs on
-//     one thread without touching point data again.
+//   * the GICP objective f(x) = 1/m sum d^T M d, d = T(x) p - q, its exact gradient and Hessian in the
+//     (t, ZYX-Euler) parametrisation, assembled from 74 sums of one pass over the correspondences, and PCL's inner
+//     Newton optimiser as a resumable state machine (one yield per objective evaluation).
 //
-// B200-first design note: f is a quadratic form in the 12 entries of W = [R | t]:
-//     m f = sum_ab w_a^T S_ab w_b - 2 sum_a v_a^T w_a + s0,   w_a = row a of W,  phi = (p, 1)
-//     S_ab = sum_i M_i[a][b] phi_i phi_i^T  (6 x 10 unique),  v_a = sum_i (M_i q_i)[a] phi_i  (3 x 4),  s0 = sum q^T M q.
-// PCL evaluates r with T(x) rounded to float32 (applyState builds a Matrix4f).  That rounding is systematic over all
-// points and decides when PCL's inner loop stops (gradient tolerance 1e-2, "no improvement"), so it is mirrored:
-// W is rounded to float before the quadratic form is evaluated.  Not mirrored (documented in DESIGN.md): the
-// per-point float rounding of T*p itself, which is zero-mean and contributes < 2e-5 to the gradient norm.
+// B200-first design note: of the 74 sums, 60 (sum M (x) phi phi^T, phi = (p,1)) do not depend on x and give the whole
+// Hessian except its second-derivative term; an evaluation pass only adds the 13 sums that contain the residual d.
+// d is formed per point exactly as PCL forms it (float32 transform T(x), float subtraction, then double), because
+// PCL's line search decisions are dominated by that float rounding once the step is below ~1e-5 m; mirroring it makes
+// the GPU follow the oracle's iterate sequence instead of merely converging to a nearby point.
 #pragma once
 
 #include <math.h>
@@ -129,73 +125,40 @@ S3D_HD void matrix_from_state(const double x[6], float T[16]) {
   T[12] = (float)x[0]; T[13] = (float)x[1]; T[14] = (float)x[2]; T[15] = 1.f;
 }
 
-// G[a][c] = d(m f)/dW[a][c] and F = m f from the moments, for W = float([R | t]) (PCL's Matrix4f transformation).
-S3D_HD double moments_value_grad(const double* mom, const double (&R)[3][3], const double t[3], double (&G)[3][4], bool want_grad) {
-  double W[3][4];
-  for (int a = 0; a < 3; ++a) {
-    W[a][0] = (double)(float)R[a][0]; W[a][1] = (double)(float)R[a][1]; W[a][2] = (double)(float)R[a][2]; W[a][3] = (double)(float)t[a];
-  }
-  double F = mom[72];
-  for (int a = 0; a < 3; ++a) {
-    double SW[4] = {0, 0, 0, 0};  // sum_b S_ab w_b
-    for (int b = 0; b < 3; ++b) {
-      const double* S = mom + sym3(a, b) * 10;
-      for (int c = 0; c < 4; ++c) { double s = 0; for (int e = 0; e < 4; ++e) s += S[sym4(c, e)] * W[b][e]; SW[c] += s; }
-    }
-    for (int c = 0; c < 4; ++c) {
-      const double v = mom[60 + a * 4 + c];
-      F += W[a][c] * (SW[c] - 2.0 * v);
-      if (want_grad) G[a][c] = 2.0 * (SW[c] - v);
-    }
-  }
-  return F;
-}
-
-// f(x) = F / m   (OptimizationFunctorWithIndices::operator())
-S3D_HD double moments_f(const double* mom, const double x[6]) {
-  Euler E;
-  euler_derivs(x, E, false);
-  double G[3][4];
-  return moments_value_grad(mom, E.R, x, G, false) / mom[73];
-}
-
-// gradient g[6] and Hessian H[6][6] of f   (OptimizationFunctorWithIndices::dfddf)
-S3D_HD void moments_dfddf(const double* mom, const double x[6], double (&g)[6], double (&H)[6][6]) {
+// f, gradient g[6] and exact Hessian H[6][6] of the GICP objective at x from the 74 sums of one evaluation pass
+// (OptimizationFunctorWithIndices::operator() and ::dfddf).  Layout of `sums`:
+//   [sym3(a,b)*10 + sym4(c,e)]  sum M[a][b] phi_c phi_e, phi = (p, 1)      x-independent for one correspondence set
+//   [60 + a*4 + c]              sum (M d)[a] phi_c                            d = float(T(x) p) - q  exactly as PCL forms it
+//   [72] sum d^T M d            [73] number of correspondences m
+S3D_HD void objective_from_sums(const double* sums, const double x[6], double& f, double (&g)[6], double (&H)[6][6]) {
   Euler E;
   euler_derivs(x, E, true);
-  double G[3][4];
-  moments_value_grad(mom, E.R, x, G, true);
-  const double im = 1.0 / mom[73];
+  const double m = sums[73];
+  const double s = 2.0 / m;
+  f = sums[72] / m;
   for (int a = 0; a < 3; ++a) {
-    g[a] = G[a][3] * im;
-    for (int b = 0; b < 3; ++b) H[a][b] = 2.0 * mom[sym3(a, b) * 10 + 9] * im;
+    g[a] = s * sums[60 + a * 4 + 3];
+    for (int c = 0; c < 3; ++c) H[a][c] = s * sums[sym3(a, c) * 10 + 9];
   }
   for (int k = 0; k < 3; ++k) {
     double gr = 0;
-    for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) gr += G[a][c] * E.dR[k][a][c];
-    g[3 + k] = gr * im;
-    for (int a = 0; a < 3; ++a) {
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) gr += E.dR[k][a][b] * (s * sums[60 + a * 4 + b]);
+    g[3 + k] = gr;
+    for (int a = 0; a < 3; ++a) {  // translation-rotation block
       double h = 0;
-      for (int b = 0; b < 3; ++b) { const double* S = mom + sym3(a, b) * 10; for (int c = 0; c < 3; ++c) h += S[sym4(3, c)] * E.dR[k][b][c]; }
-      H[a][3 + k] = H[3 + k][a] = 2.0 * h * im;
+      for (int c = 0; c < 3; ++c) for (int b = 0; b < 3; ++b) h += E.dR[k][c][b] * (s * sums[sym3(a, c) * 10 + sym4(b, 3)]);
+      H[a][3 + k] = H[3 + k][a] = h;
     }
-  }
-  for (int k = 0; k < 3; ++k)
-    for (int l = k; l < 3; ++l) {
+    for (int l = 0; l < 3; ++l) {  // rotation-rotation block: first-order part + second-derivative part
       double h = 0;
       for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b) {
-          const double* S = mom + sym3(a, b) * 10;
-          for (int c = 0; c < 3; ++c) {
-            double s = 0;
-            for (int e = 0; e < 3; ++e) s += S[sym4(c, e)] * E.dR[l][b][e];
-            h += E.dR[k][a][c] * s;
-          }
+          for (int c = 0; c < 3; ++c) for (int e = 0; e < 3; ++e) h += E.dR[k][a][b] * E.dR[l][c][e] * (s * sums[sym3(a, c) * 10 + sym4(b, e)]);
+          h += E.ddR[k][l][a][b] * (s * sums[60 + a * 4 + b]);
         }
-      double h2 = 0;
-      for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) h2 += G[a][c] * E.ddR[k][l][a][c];
-      H[3 + k][3 + l] = H[3 + l][3 + k] = (2.0 * h + h2) * im;
+      H[3 + k][3 + l] = h;
     }
+  }
 }
 
 // delta = H'^-1 g, H' = H with negative eigenvalues replaced by the largest one (PCL 1.14 Newton step).
@@ -230,36 +193,61 @@ S3D_HD void newton_direction(const double (&H)[6][6], const double (&g)[6], doub
   }
 }
 
-// estimateRigidTransformationNewton on the moments.  T (float, column-major) in/out.
-// Returns false when there are fewer than 4 correspondences (PCL throws; the outer loop breaks unconverged).
-S3D_HD bool newton_from_moments(const double* mom, float T[16], int max_inner, int* inner_done) {
-  if (mom[73] < 4.0) return false;  // min_number_correspondences_
-  double x[6];
-  state_from_matrix(T, x);
+// estimateRigidTransformationNewton as a resumable state machine: every objective evaluation PCL's loop asks for is one
+// data pass on the GPU (gicp.cu), so the optimiser yields whenever it needs f (and the sums for g, H) at a new state.
+struct NewtonState {
+  double x[6];        // accepted state
+  double xc[6];       // state whose evaluation is pending / was just delivered
+  double fcur, alpha;
   double g[6], H[6][6], delta[6];
-  double fcur = moments_f(mom, x);
-  moments_dfddf(mom, x, g, H);
-  int it = 0;
-  do {
-    ++it;
-    newton_direction(H, g, delta);
-    double alpha = 1.0;
-    bool improved = false;
-    for (int ls = 0; ls < 10; ++ls, alpha /= 2) {
-      double xc[6];
-      for (int r = 0; r < 6; ++r) xc[r] = x[r] - alpha * delta[r];
-      const double fc = moments_f(mom, xc);
-      if (fc < fcur) { for (int r = 0; r < 6; ++r) x[r] = xc[r]; fcur = fc; improved = true; break; }
-    }
-    if (!improved) break;
-    moments_dfddf(mom, x, g, H);
-    const double gtn = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
-    const double grn = sqrt(g[3] * g[3] + g[4] * g[4] + g[5] * g[5]);
-    if (gtn < 1e-2 && grn < 1e-2) break;  // translation_/rotation_gradient_tolerance_
-  } while (it < max_inner);
-  *inner_done += it;
-  matrix_from_state(x, T);
+  int it, ls, phase;  // phase: 0 = waiting for the evaluation at the start state, 1 = line search, 2 = finished
+};
+
+S3D_HD void newton_begin(NewtonState& st, const float T[16]) {
+  state_from_matrix(T, st.x);
+  for (int i = 0; i < 6; ++i) st.xc[i] = st.x[i];
+  st.it = 0; st.ls = 0; st.alpha = 1.0; st.phase = 0;
+}
+
+S3D_HD bool newton_new_step(NewtonState& st) {  // do { ++it; direction; alpha = 1 ... }
+  ++st.it;
+  newton_direction(st.H, st.g, st.delta);
+  st.alpha = 1.0; st.ls = 0;
+  for (int r = 0; r < 6; ++r) st.xc[r] = st.x[r] - st.alpha * st.delta[r];
+  st.phase = 1;
   return true;
+}
+
+// `sums` = evaluation at st.xc.  Returns true when another evaluation (at the new st.xc) is needed, false when the
+// optimiser is finished (result in st.x).  Mirrors PCL 1.14: back-tracking alpha = 1, 1/2, ... (10 trials) until f
+// decreases, stop on no improvement, on both gradient norms < 1e-2, or after max_inner iterations.
+S3D_HD bool newton_advance(NewtonState& st, const double* sums, int max_inner) {
+  if (st.phase == 0) {
+    objective_from_sums(sums, st.x, st.fcur, st.g, st.H);
+    return newton_new_step(st);
+  }
+  if (st.phase == 1) {
+    const double fc = sums[72] / sums[73];
+    if (fc < st.fcur) {
+      for (int r = 0; r < 6; ++r) st.x[r] = st.xc[r];
+      objective_from_sums(sums, st.x, st.fcur, st.g, st.H);
+      const double gtn = sqrt(st.g[0] * st.g[0] + st.g[1] * st.g[1] + st.g[2] * st.g[2]);
+      const double grn = sqrt(st.g[3] * st.g[3] + st.g[4] * st.g[4] + st.g[5] * st.g[5]);
+      if (gtn < 1e-2 && grn < 1e-2) { st.phase = 2; return false; }  // translation_/rotation_gradient_tolerance_
+      if (st.it < max_inner) return newton_new_step(st);
+      st.phase = 2;
+      return false;
+    }
+    ++st.ls;
+    st.alpha /= 2;
+    if (st.ls < 10) {
+      for (int r = 0; r < 6; ++r) st.xc[r] = st.x[r] - st.alpha * st.delta[r];
+      return true;
+    }
+    st.phase = 2;  // no improvement found
+    return false;
+  }
+  return false;
 }
 
 // Mahalanobis matrix of one correspondence: M = (R C1 R^T + C2)^-1 with C = I - (1-eps) n n^T.

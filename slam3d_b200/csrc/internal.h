@@ -67,6 +67,10 @@ struct PairState {
   double fit_sum;
   uint32_t fit_n;
   int32_t max_iter, max_inner, k;
+  NewtonState nst;         // resumable inner optimiser (gicp_math.h)
+  float  T_eval[16];       // float matrix of the state whose objective evaluation is pending (PCL applyState)
+  double sums[kNumMoments];// reduced sums of the current correspondence set (static part) + last evaluation (residual part)
+  int32_t phase;           // kPhaseNeedNN / kPhaseEval / kPhaseFinished
   int32_t active;          // 1 while the outer loop runs
   int32_t converged;
   int32_t failed;          // optimiser exception (<4 correspondences)
@@ -98,6 +102,9 @@ struct Workspace {
   DevBuf prev_nn;                             // uint32[total]   last correspondence (warm start bound)
   DevBuf sec_lb;                              // float[total]    lower bound of the distance to every OTHER fixed point at the last search position
   DevBuf moments;                             // double[iter_tiles * 74]
+  DevBuf eval_part;                           // double[iter_tiles * 13]
+  DevBuf corr;                                // uint32[total]   correspondence of the current outer iteration (kNoIndex: none)
+  DevBuf mahal;                               // double[total*6] Mahalanobis matrix of each correspondence
   DevBuf iter_tile_pair, iter_tile_first;     // uint32[iter_tiles]
   uint32_t iter_tiles = 0;
   DevBuf fit_partial;                         // double[iter_tiles*2]
@@ -119,6 +126,8 @@ struct Workspace {
 };
 
 enum ErrorBits { kErrHashArena = 1 };
+enum PairPhase { kPhaseNeedNN = 0, kPhaseEval = 1, kPhaseFinished = 2 };
+constexpr int kEvalSums = 13;  // sums 60..72 of gicp_math.h: the residual-dependent part of an evaluation
 enum Stage { kStageVoxel = 0, kStageGrid = 1, kStageKnn = 2, kStageIter = 3, kStageSolve = 4, kStageFitness = 5 };
 
 // RAII: brackets the kernels launched in its scope with two events when profiling is on

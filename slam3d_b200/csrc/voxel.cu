@@ -47,7 +47,7 @@ void Workspace::destroy() {
   for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
   event_pool.clear();
   DevBuf* bufs[] = {&slots, &pairs, &raw_stage, &work, &gpts, &keys0, &keys1, &vals0, &vals1, &hist, &tile_slot, &tile_first,
-                    &slot_tile_begin, &tile_heads, &hash, &normals, &moved, &prev_nn, &sec_lb, &moments, &iter_tile_pair, &iter_tile_first,
+                    &slot_tile_begin, &tile_heads, &hash, &normals, &moved, &prev_nn, &sec_lb, &moments, &eval_part, &corr, &mahal, &iter_tile_pair, &iter_tile_first,
                     &fit_partial, &flags};
   for (DevBuf* b : bufs) b->release();
   h_slots.release(); h_pairs.release(); h_small.release(); h_tiles.release();

@@ -1,19 +1,64 @@
 // Host build of slam3d_b200/csrc/gicp_math.h for the CPU test-suite (tests/test_hostmath.py).
-// Test-only: lets the optimiser math that runs on one GPU thread be checked against the oracle without a GPU.
+// Test-only: lets the optimiser math that runs on the GPU be checked against the oracle without a GPU.  The evaluation
+// pass below does on the host what gicp_iter_kernel / gicp_eval_kernel do on the device (same float operation order).
+#include <vector>
+
 #include "../slam3d_b200/csrc/gicp_math.h"
 
+namespace {
+// Eigen Matrix4f * Vector4f with w = 1 (same order as common.cuh transform_mv); built with -ffp-contract=off
+inline void transform_mv(const float* T, const float* p, float* o) {
+  o[0] = ((T[0] * p[0] + T[4] * p[1]) + T[8] * p[2]) + T[12];
+  o[1] = ((T[1] * p[0] + T[5] * p[1]) + T[9] * p[2]) + T[13];
+  o[2] = ((T[2] * p[0] + T[6] * p[1]) + T[10] * p[2]) + T[14];
+}
+// 74 sums of one evaluation pass at state x: static part + residual part (d from the float transform, like PCL)
+void evaluate(const float* moved, const float* fixed, const double* M6, int m, const double x[6], double* sums) {
+  float T[16];
+  s3d::matrix_from_state(x, T);
+  for (int i = 0; i < s3d::kNumMoments; ++i) sums[i] = 0.0;
+  for (int i = 0; i < m; ++i) {
+    const float* p = moved + 4 * i; const float* q = fixed + 4 * i; const double* M = M6 + 6 * i;
+    float pp[3];
+    transform_mv(T, p, pp);
+    const double d[3] = {(double)(pp[0] - q[0]), (double)(pp[1] - q[1]), (double)(pp[2] - q[2])};
+    const double Mf[3][3] = {{M[0], M[1], M[2]}, {M[1], M[3], M[4]}, {M[2], M[4], M[5]}};
+    const double phi[4] = {p[0], p[1], p[2], 1.0};
+    double Md[3];
+    for (int a = 0; a < 3; ++a) Md[a] = Mf[a][0] * d[0] + Mf[a][1] * d[1] + Mf[a][2] * d[2];
+    for (int a = 0; a < 3; ++a) for (int b = a; b < 3; ++b) for (int c = 0; c < 4; ++c) for (int e = c; e < 4; ++e)
+      sums[s3d::sym3(a, b) * 10 + s3d::sym4(c, e)] += Mf[a][b] * phi[c] * phi[e];
+    for (int a = 0; a < 3; ++a) for (int c = 0; c < 4; ++c) sums[60 + a * 4 + c] += Md[a] * phi[c];
+    sums[72] += d[0] * Md[0] + d[1] * Md[1] + d[2] * Md[2];
+    sums[73] += 1.0;
+  }
+}
+}  // namespace
+
 extern "C" {
-double hm_f(const double* mom, const double* x) { return s3d::moments_f(mom, x); }
-void hm_dfddf(const double* mom, const double* x, double* g, double* H) {
-  double gg[6], HH[6][6];
-  s3d::moments_dfddf(mom, x, gg, HH);
+void hm_objective(const float* moved, const float* fixed, const double* M6, int m, const double* x, double* f, double* g, double* H) {
+  double sums[s3d::kNumMoments], gg[6], HH[6][6];
+  evaluate(moved, fixed, M6, m, x, sums);
+  s3d::objective_from_sums(sums, x, *f, gg, HH);
   for (int i = 0; i < 6; ++i) { g[i] = gg[i]; for (int j = 0; j < 6; ++j) H[j * 6 + i] = HH[i][j]; }
 }
-int hm_newton(const double* mom, float* T, int max_inner, int* inner_done) {
-  int d = 0;
-  bool ok = s3d::newton_from_moments(mom, T, max_inner, &d);
-  *inner_done = d;
-  return ok ? 0 : 2;
+// estimateRigidTransformationNewton through the resumable state machine; T column-major float in/out
+int hm_newton(const float* moved, const float* fixed, const double* M6, int m, float* T, int max_inner, int* inner_done, int* evaluations) {
+  if (m < 4) return 2;
+  s3d::NewtonState st;
+  s3d::newton_begin(st, T);
+  double sums[s3d::kNumMoments];
+  int evals = 0;
+  bool more = true;
+  while (more) {
+    evaluate(moved, fixed, M6, m, st.xc, sums);
+    ++evals;
+    more = s3d::newton_advance(st, sums, max_inner);
+  }
+  s3d::matrix_from_state(st.x, T);
+  *inner_done = st.it;
+  if (evaluations) *evaluations = evals;
+  return 0;
 }
 void hm_direction(const double* H, const double* g, double* delta) {
   double HH[6][6], gg[6], dd[6];
@@ -33,6 +78,4 @@ void hm_mahalanobis(const double* RRt, const double* a, const double* b, double*
   s3d::mahalanobis6(r, a, b, m);
   for (int i = 0; i < 6; ++i) M6[i] = m[i];
 }
-int hm_sym3(int a, int b) { return s3d::sym3(a, b); }
-int hm_sym4(int a, int b) { return s3d::sym4(a, b); }
 }

@@ -89,3 +89,21 @@ def test_tiny_clouds(ctx, oracle_mod):
     gi, gd, _ = ctx.knn_covariances(same, 4)
     oi, od = oracle_mod.knn_bruteforce(same, same, 4)
     assert np.array_equal(gi, oi)
+
+
+def test_map_cloud_2m_covariances(ctx, oracle_mod):
+    """BASELINE config 3: kNN-20 + covariance on the voxel-filtered 2 097 152-point synthetic map cloud."""
+    from slam3d_b200 import synth
+    cloud = synth.map_cloud(n_scans=16)
+    for leaf in (0.1, 0.2):
+        f, _, _ = ctx.voxel_downsample(cloud, leaf, want_leaf_index=False)
+        gi, gd, gc = ctx.knn_covariances(f, 20)
+        rng = np.random.default_rng(int(leaf * 100))
+        pick = rng.choice(f.shape[0], 1500, replace=False)
+        oi, od = oracle_mod.knn_bruteforce(f, f[pick], 20)
+        assert np.array_equal(gi[pick], oi) and np.array_equal(gd[pick].view(np.uint32), od.view(np.uint32))
+        # size-independent properties on the full result: self first, distances ascending, unit-trace structure of C
+        assert np.array_equal(gi[:, 0], np.arange(f.shape[0], dtype=np.uint32)) or np.all(gd[:, 0] == 0)
+        assert np.all(np.diff(gd, axis=1) >= 0)
+        ev = np.linalg.eigvalsh(gc[::997])
+        assert np.allclose(ev, [1e-3, 1, 1], atol=1e-9)
