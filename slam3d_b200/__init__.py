@@ -13,7 +13,7 @@ from . import _abi
 from ._abi import Cloud, Counters, RegistrationParameters, Result  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libs3d_b200.so")
+LIB_PATH = os.environ.get("S3D_LIB_PATH", os.path.join(_HERE, "libs3d_b200.so"))  # override: kernel-variant experiments only
 _lib = None
 
 

@@ -19,7 +19,13 @@
 
 namespace s3d {
 
-constexpr int kKnnThreads = 128;  // queries per CTA (one thread per query)
+#ifndef S3D_KNN_THREADS
+#define S3D_KNN_THREADS 128
+#endif
+#ifndef S3D_KNN_MINBLOCKS
+#define S3D_KNN_MINBLOCKS 8
+#endif
+constexpr int kKnnThreads = S3D_KNN_THREADS;  // queries per CTA (one thread per query)
 
 #ifdef S3D_KNN_STATS
 __device__ unsigned long long g_knn_stats[8];  // queries, level scans, cells probed, cells pruned, candidates, pushes, sift-downs, start-level probes
@@ -29,20 +35,8 @@ __device__ unsigned long long g_knn_stats[8];  // queries, level scans, cells pr
 #endif
 
 // max-heap of 64-bit keys in shared memory, element j of thread t at h[j * kKnnThreads]
-__device__ __forceinline__ void heap_push(uint64_t* h, int& n, uint64_t x) {
-  int i = n++;
-  while (i > 0) {
-    const int p = (i - 1) >> 1;
-    const uint64_t hp = h[p * kKnnThreads];
-    if (hp >= x) break;
-    h[i * kKnnThreads] = hp;
-    i = p;
-  }
-  h[i * kKnnThreads] = x;
-}
-// replaces the root by x (x < root) and restores the heap
-__device__ __forceinline__ void heap_sift_down(uint64_t* h, int n, uint64_t x) {
-  int i = 0;
+// puts x at node i (whose subtrees are heaps) and restores the heap below it; i = 0 replaces the root
+__device__ __forceinline__ void heap_sift_down(uint64_t* h, int n, uint64_t x, int i = 0) {
   for (;;) {
     int c = 2 * i + 1;
     if (c >= n) break;
@@ -60,7 +54,7 @@ __device__ __forceinline__ void heap_sift_down(uint64_t* h, int n, uint64_t x) {
 // lexicographic (d2, idx) order of the parity contract — and the k best live in a per-thread max-heap in shared
 // memory (bank-conflict free: element j of thread t at [j][t]).  A cell is skipped when the lower bound of its distance
 // exceeds the current k-th best.  Heapsort at the end yields FLANN's ascending neighbour order for the moments.
-__global__ void __launch_bounds__(kKnnThreads) knn_cov_kernel(const SlotInfo* __restrict__ slots, const HashEntry* __restrict__ arena,
+__global__ void __launch_bounds__(kKnnThreads, S3D_KNN_MINBLOCKS) knn_cov_kernel(const SlotInfo* __restrict__ slots, const HashEntry* __restrict__ arena,
                                                               const float4* __restrict__ gpts, const float4* __restrict__ work,
                                                               double4* __restrict__ normals, int k, uint32_t* __restrict__ knn_index,
                                                               float* __restrict__ knn_dist2) {
@@ -128,9 +122,12 @@ __global__ void __launch_bounds__(kKnnThreads) knn_cov_kernel(const SlotInfo* __
         if (!(cd == cd)) continue;  // NaN never enters
         const uint64_t ck = ((uint64_t)__float_as_uint(cd) << 32) | (uint64_t)__float_as_uint(v.w);
         if (cnt < kk) {
-          if (ck <= bound) {
-            heap_push(h, cnt, ck); KSTAT(5, 1);
-            if (cnt == kk) { tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32)); }
+          if (ck <= bound) {  // fill phase: append, and heapify once when the k-th candidate arrives
+            h[cnt * kKnnThreads] = ck; ++cnt; KSTAT(5, 1);
+            if (cnt == kk) {
+              for (int i = kk / 2 - 1; i >= 0; --i) heap_sift_down(h, kk, h[i * kKnnThreads], i);
+              tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
+            }
           }
         } else if (ck < tau) {
           heap_sift_down(h, kk, ck); KSTAT(6, 1);
@@ -143,6 +140,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_cov_kernel(const SlotInfo* __
     if (full) bound = tau;
   }
   // ---- heapsort: ascending (d2, idx) = FLANN's sorted result order --------------------------------------------------------
+  if (cnt < kk) for (int i = cnt / 2 - 1; i >= 0; --i) heap_sift_down(h, cnt, h[i * kKnnThreads], i);  // top level ended before the list filled
   for (int m = cnt - 1; m > 0; --m) {
     const uint64_t last = h[m * kKnnThreads];
     h[m * kKnnThreads] = h[0];
