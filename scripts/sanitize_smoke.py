@@ -1,0 +1,17 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck): every kernel of the path once."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import slam3d_b200
+from slam3d_b200 import synth
+from slam3d_b200._abi import RegistrationParameters
+
+src, tgt, _ = synth.scan_pair(seed=3)
+src, tgt = src[::8], tgt[::8]
+ctx = slam3d_b200.Context()
+out, li, ov = ctx.voxel_downsample(src, 0.3)
+idx, d2, cov = ctx.knn_covariances(out, 20)
+nn_i, nn_d = ctx.nearest_neighbors(out, out[::3])
+res = ctx.gicp_align_batch([src, tgt, src[:50]], [tgt, src, tgt], None, RegistrationParameters.defaults(point_cloud_density=0.3))
+print("sanitize smoke:", out.shape, idx.shape, [(r.status, r.outer_iterations) for r in res])
+ctx.close()

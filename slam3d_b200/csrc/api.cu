@@ -70,6 +70,23 @@ struct WsLease {
   Workspace& operator*() { return *ws; }
 };
 
+// Runs `body` (which sets up and processes one batch on `ws`); if the NN grid overflowed its optimistic hash arena the
+// batch is repeated once with exactly the size the device reported.
+template <typename F>
+static void with_arena_retry(Workspace& ws, F&& body) {
+  for (int attempt = 0;; ++attempt) {
+    try {
+      body();
+      return;
+    } catch (const ArenaOverflow& o) {
+      cudaStreamSynchronize(ws.stream);
+      ws.collect_spans();
+      if (attempt >= 2) throw CudaError{"hash arena overflow persists after re-allocation"};
+      ws.hash_want = o.needed;
+    }
+  }
+}
+
 template <typename F>
 static int guarded(F&& f) {
   try {
@@ -92,6 +109,9 @@ static void copy_out(Workspace& ws, void* dst, const void* src_dev, size_t bytes
   if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) ws.d2h += bytes;
 }
 
+static void align_chunk_body(Workspace& ws, const std::vector<const float*>& clouds, const std::vector<uint64_t>& sizes, const double* guesses,
+                             const s3d_registration_parameters& cfg, int n, s3d_result* out);
+
 // One sub-batch of align() calls on one device.
 static void align_chunk(s3d_context* ctx, int slot, const s3d_cloud* sources, const s3d_cloud* targets, const double* guesses,
                         const s3d_registration_parameters& cfg, int n, s3d_result* out) {
@@ -103,6 +123,11 @@ static void align_chunk(s3d_context* ctx, int slot, const s3d_cloud* sources, co
     clouds[2 * i] = sources[i].xyzw; sizes[2 * i] = sources[i].n;
     clouds[2 * i + 1] = targets[i].xyzw; sizes[2 * i + 1] = targets[i].n;
   }
+  with_arena_retry(ws, [&] { align_chunk_body(ws, clouds, sizes, guesses, cfg, n, out); });
+}
+
+static void align_chunk_body(Workspace& ws, const std::vector<const float*>& clouds, const std::vector<uint64_t>& sizes, const double* guesses,
+                             const s3d_registration_parameters& cfg, int n, s3d_result* out) {
   setup_batch(ws, clouds, sizes, n);
   const float leaf = cfg.point_cloud_density > 0 ? (float)cfg.point_cloud_density : 0.f;  // :127, setLeafSize(float)
   run_voxel(ws, leaf);
@@ -268,6 +293,8 @@ int s3d_knn_covariances(s3d_context* ctx, s3d_cloud cloud, int k, uint32_t* knn_
   return guarded([&]() -> int {
     WsLease lease(ctx, 0);
     Workspace& ws = *lease;
+    int rc = S3D_OK;
+    with_arena_retry(ws, [&] {
     setup_batch(ws, {cloud.xyzw}, {cloud.n}, 0);
     run_voxel(ws, 0.f);
     run_grid(ws, 0.f);
@@ -277,14 +304,16 @@ int s3d_knn_covariances(s3d_context* ctx, s3d_cloud cloud, int k, uint32_t* knn_
     if (knn_dist2) dd.reserve(4 * n * k);
     run_knn_covariances(ws, k, knn_index ? di.as<uint32_t>() : nullptr, knn_dist2 ? dd.as<float>() : nullptr);
     if (covariances) { dc.reserve(72 * n); run_expand_cov(ws, dc.as<double>()); }
-    copy_out(ws, knn_index, di.p, 4 * n * k);
-    copy_out(ws, knn_dist2, dd.p, 4 * n * k);
-    copy_out(ws, covariances, dc.p, 72 * n);
     int32_t* hf = ws.h_small.as<int32_t>();
     S3D_CUDA(cudaMemcpyAsync(hf, ws.flags.p, 16, cudaMemcpyDeviceToHost, ws.stream));
     S3D_CUDA(cudaStreamSynchronize(ws.stream));
-    if (hf[0] & kErrHashArena) { set_error("hash arena too small"); return S3D_INTERNAL_ERROR; }
-    return S3D_OK;
+    check_arena(ws, hf);
+    copy_out(ws, knn_index, di.p, 4 * n * k);
+    copy_out(ws, knn_dist2, dd.p, 4 * n * k);
+    copy_out(ws, covariances, dc.p, 72 * n);
+    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    });
+    return rc;
   });
 }
 
@@ -294,6 +323,7 @@ int s3d_nearest_neighbors(s3d_context* ctx, s3d_cloud reference, s3d_cloud queri
   return guarded([&]() -> int {
     WsLease lease(ctx, 0);
     Workspace& ws = *lease;
+    with_arena_retry(ws, [&] {
     setup_batch(ws, {reference.xyzw, queries.xyzw}, {reference.n, queries.n}, 0);
     run_voxel(ws, 0.f);
     run_grid(ws, 0.f);
@@ -308,12 +338,14 @@ int s3d_nearest_neighbors(s3d_context* ctx, s3d_cloud reference, s3d_cloud queri
     DevBuf& di = ws.moved; DevBuf& dd = ws.prev_nn;
     di.reserve(4 * queries.n); dd.reserve(4 * queries.n);
     run_nn_stage(ws, 0, 1, Td, di.as<uint32_t>(), dd.as<float>());
-    copy_out(ws, nn_index, di.p, 4 * queries.n);
-    copy_out(ws, nn_dist2, dd.p, 4 * queries.n);
     int32_t* hf = ws.h_small.as<int32_t>();
     S3D_CUDA(cudaMemcpyAsync(hf, ws.flags.p, 16, cudaMemcpyDeviceToHost, ws.stream));
     S3D_CUDA(cudaStreamSynchronize(ws.stream));
-    if (hf[0] & kErrHashArena) { set_error("hash arena too small"); return S3D_INTERNAL_ERROR; }
+    check_arena(ws, hf);
+    copy_out(ws, nn_index, di.p, 4 * queries.n);
+    copy_out(ws, nn_dist2, dd.p, 4 * queries.n);
+    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    });
     return S3D_OK;
   });
 }

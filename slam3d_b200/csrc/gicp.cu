@@ -415,6 +415,10 @@ static double rotation_angle(const double T[16]) {
   return 2.0 * atan2(sqrt(x * x + y * y + z * z), fabs(w));
 }
 
+void check_arena(Workspace& ws, const int32_t* h_flags) {
+  if (h_flags[0] & kErrHashArena) throw ArenaOverflow{(size_t)h_flags[3] + (size_t)h_flags[3] / 8 + 64};
+}
+
 // Runs the GICP loop + fitness for every pair of the batch (grids and covariances must be ready) and fills `out`
 // with the decisions of doICP (:74-77) and align() (:134-135, :167-172).
 void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& params, const double* guesses, s3d_result* out) {
@@ -510,7 +514,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   S3D_CUDA(cudaStreamSynchronize(st));
   ws.d2h += sizeof(PairState) * np + sizeof(SlotInfo) * ws.n_slots + 16;
   ws.collect_spans();
-  if (h_flags[0] & kErrHashArena) throw CudaError{"hash arena too small"};
+  check_arena(ws, h_flags);
   for (uint32_t p = 0; p < np; ++p) {
     const s3d_registration_parameters& cfg = params[p];
     const PairState& ps = hp[p];

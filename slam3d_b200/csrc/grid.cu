@@ -98,15 +98,21 @@ __global__ void __launch_bounds__(kSortThreads) grid_gather_kernel(SlotInfo* __r
   if ((threadIdx.x & 31) == 0 && cells) atomicAdd(&si.n_cells, cells);
 }
 
-// one thread: carve the hash arena (2 entries per occupied cell)
+// one thread: carve the hash arena (2 entries per occupied cell).  flags[3] always receives the number of entries the
+// batch needs, so that an overflow (flags[0] & kErrHashArena) can be answered by one exact re-allocation and a re-run.
 __global__ void hash_layout_kernel(SlotInfo* __restrict__ slots, uint32_t n_slots, uint32_t arena_cap, int32_t* __restrict__ flags) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   uint64_t running = 0;
   for (uint32_t s = 0; s < n_slots; ++s) {
     const uint64_t cap = 2ull * slots[s].n_cells + 8;
-    if (running + cap > arena_cap) { atomicOr(&flags[0], kErrHashArena); slots[s].hash_off = 0; slots[s].hash_cap = 0; continue; }
-    slots[s].hash_off = (uint32_t)running; slots[s].hash_cap = (uint32_t)cap;
+    slots[s].hash_off = (uint32_t)min(running, (uint64_t)0xFFFFFFFFu); slots[s].hash_cap = (uint32_t)cap;
     running += cap;
+  }
+  flags[3] = (int32_t)min(running, (uint64_t)0x7FFFFFFF);
+  if (running > arena_cap) {
+    atomicOr(&flags[0], kErrHashArena);
+    for (uint32_t s = 0; s < n_slots; ++s) { slots[s].hash_off = 0; slots[s].hash_cap = 0; }  // every later kernel sees an empty grid
+    running = 0;
   }
   flags[2] = (int32_t)running;
 }
@@ -152,8 +158,10 @@ void run_grid(Workspace& ws, float leaf_hint) {
   StageTimer timer(ws, kStageGrid);
   SlotInfo* slots = ws.slots.as<SlotInfo>();
   TileMap tm{ws.tile_slot.as<uint32_t>(), ws.tile_first.as<uint32_t>(), ws.n_tiles};
-  // arena: ~1.2 cells per point is typical for lidar scans; 3 entries/point leaves 25% head-room at load factor 1/2
-  const size_t want = 3 * size_t(ws.total) + 64 * size_t(ws.n_slots);
+  // arena: ~1.2 occupied cells per point is typical for voxel-filtered lidar scans; 3 entries/point leaves 25% head-room
+  // at load factor 1/2.  Sparse clouds (every point alone in its cell on many levels) overflow it: the layout kernel
+  // then flags kErrHashArena and reports the exact need, and the caller re-runs the batch (with_arena_retry).
+  const size_t want = std::max(ws.hash_want, 3 * size_t(ws.total) + 64 * size_t(ws.n_slots));
   if (ws.hash_cap < want) { ws.hash.reserve(sizeof(HashEntry) * want); ws.hash_cap = want; }
   launch_bbox(ws, kCountPts);
   grid_params_kernel<<<(ws.n_slots + 63) / 64, 64, 0, st>>>(slots, ws.n_slots, leaf_hint);

@@ -16,6 +16,7 @@ namespace s3d {
 void set_error(const std::string& msg);  // thread-local message behind s3d_last_error()
 
 struct CudaError { std::string what; };
+struct ArenaOverflow { size_t needed; };  // the hash arena was too small for this batch; re-run with `needed` entries
 #define S3D_CUDA(expr)                                                                                         \
   do {                                                                                                         \
     cudaError_t _e = (expr);                                                                                   \
@@ -97,6 +98,7 @@ struct Workspace {
   DevBuf tile_slot, tile_first, slot_tile_begin, tile_heads;
   DevBuf hash;                                // HashEntry[hash_cap]
   size_t hash_cap = 0;
+  size_t hash_want = 0;                       // entries requested by the last arena overflow (0: default sizing)
   DevBuf normals;                             // double[total*4]  unit normal of the regularised covariance (+pad)
   DevBuf moved;                               // float4[total]   guess * A (Morton order of A)
   DevBuf prev_nn;                             // uint32[total]   last correspondence (warm start bound)
@@ -149,6 +151,7 @@ void run_grid(Workspace& ws, float leaf_hint);      // NN grid on the working cl
 void run_knn_covariances(Workspace& ws, int k, uint32_t* knn_index, float* knn_dist2);  // outputs optional (device, slot-concatenated)
 void run_expand_cov(Workspace& ws, double* cov_out);  // full 3x3 covariances per original index (stage API)
 void run_nn_stage(Workspace& ws, uint32_t ref_slot, uint32_t qry_slot, const float* T16_dev, uint32_t* nn_index, float* nn_dist2);
+void check_arena(Workspace& ws, const int32_t* h_flags);  // throws ArenaOverflow when the grid build flagged it (h_flags: synchronised copy)
 void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& params, const double* guesses, s3d_result* out);
 
 }  // namespace s3d

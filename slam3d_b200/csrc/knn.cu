@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(kKnnThreads, S3D_KNN_MINBLOCKS) knn_cov_kernel
   const uint32_t r = blockIdx.x * kKnnThreads + threadIdx.x;
   if (r >= n) return;
   const GridView g = make_grid_view(si, arena, gpts);
+  if (g.cap == 0) return;  // grid build overflowed its arena: the host re-runs the batch
   const float4* cloud = work + si.off;  // original (voxel-key) order
   const int kk = k < (int)n ? k : (int)n;  // FLANN clamps k to the cloud size
   uint64_t* h = heap_smem + threadIdx.x;
@@ -185,7 +186,7 @@ __global__ void expand_cov_kernel(const SlotInfo* __restrict__ slots, const floa
                                   double* __restrict__ cov_out) {
   const SlotInfo& si = slots[blockIdx.y];
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= si.n_pts) return;
+  if (r >= si.n_pts || si.hash_cap == 0) return;  // hash_cap == 0: the grid build overflowed, the batch is being re-run
   const uint32_t orig = __float_as_uint(gpts[si.off + r].w);
   const double4 nv = normals[si.off + r];
   const double nn[3] = {nv.x, nv.y, nv.z};

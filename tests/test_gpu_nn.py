@@ -107,3 +107,18 @@ def test_map_cloud_2m_covariances(ctx, oracle_mod):
         assert np.all(np.diff(gd, axis=1) >= 0)
         ev = np.linalg.eigvalsh(gc[::997])
         assert np.allclose(ev, [1e-3, 1, 1], atol=1e-9)
+
+
+def test_sparse_cloud_overflows_hash_arena_and_retries(ctx, oracle_mod):
+    """Every point alone in its cell on many levels: the optimistic hash arena overflows and the library re-runs the
+    batch with the size the device reported (no error, exact results)."""
+    rng = np.random.default_rng(9)
+    g = np.stack(np.meshgrid(np.arange(22), np.arange(22), np.arange(22), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    ref = (g + rng.uniform(-0.2, 0.2, g.shape)).astype(np.float32)
+    gi, gd, _ = ctx.knn_covariances(ref, 8)
+    pick = rng.choice(ref.shape[0], 800, replace=False)
+    oi, od = oracle_mod.knn_bruteforce(ref, ref[pick], 8)
+    assert np.array_equal(gi[pick], oi) and np.array_equal(gd[pick].view(np.uint32), od.view(np.uint32))
+    ni, nd = ctx.nearest_neighbors(ref, ref[pick] + np.float32(0.3))
+    bi, bd = oracle_mod.knn_bruteforce(ref, ref[pick] + np.float32(0.3), 1)
+    assert np.array_equal(ni, bi[:, 0]) and np.array_equal(nd.view(np.uint32), bd[:, 0].view(np.uint32))
