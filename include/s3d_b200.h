@@ -132,6 +132,24 @@ void* s3d_context_stream(s3d_context* ctx, int device_slot);
 typedef struct s3d_counters { uint64_t kernel_launches, h2d_bytes, d2h_bytes; } s3d_counters;
 int s3d_get_counters(s3d_context* ctx, s3d_counters* out);
 
+/* ---- per-measurement device cache ------------------------------------------------------
+ * The reference rebuilds the voxel filter, both kd-trees and all covariances inside every align()
+ * (PointCloudSensor.cpp:58,125-131 are locals), although each scan is matched several times (once as target and once as
+ * source in odometry, many times as a loop-closure candidate).  s3d_prepare_cloud runs the per-cloud stages ONCE
+ * (H2D, voxel filter at `density`, NN grid, kNN-k covariances) and keeps the result on the device;
+ * s3d_gicp_align_prepared(_batch) then runs only the GICP loop + fitness + gates.  Results are bit-identical to
+ * s3d_gicp_align on the raw clouds with point_cloud_density == density and correspondence_randomness == k
+ * (status 6 if the handle was prepared with other values).  Handles are immutable and may be shared by threads. */
+typedef struct s3d_prepared_cloud s3d_prepared_cloud;
+int s3d_prepare_cloud(s3d_context* ctx, int device_slot, s3d_cloud cloud, double density, int k, s3d_prepared_cloud** out);
+int s3d_release_cloud(s3d_context* ctx, s3d_prepared_cloud* cloud);
+uint64_t s3d_prepared_cloud_size(const s3d_prepared_cloud* cloud); /* points after filtering */
+int s3d_gicp_align_prepared(s3d_context* ctx, const s3d_prepared_cloud* source, const s3d_prepared_cloud* target,
+                            const double guess[16], const s3d_registration_parameters* params, s3d_result* out);
+int s3d_gicp_align_prepared_batch(s3d_context* ctx, const s3d_prepared_cloud* const* sources,
+                                  const s3d_prepared_cloud* const* targets, const double* guesses,
+                                  const s3d_registration_parameters* params, int n_pairs, s3d_result* out);
+
 /* Optional per-stage device timing (CUDA events on the launching stream, read back at the call's final
  * synchronisation).  Stage ids: 0 voxel filter, 1 NN grid build, 2 kNN+covariances, 3 GICP correspondence/
  * linearisation kernel, 4 GICP solve kernel, 5 fitness.  ms[i] / launches[i] accumulate since the last reset. */

@@ -43,6 +43,13 @@ def lib():
         L.s3d_gicp_align.argtypes = [C.c_void_p, Cloud, Cloud, C.c_void_p, C.POINTER(RegistrationParameters), C.POINTER(Result)]
         L.s3d_gicp_align_batch.argtypes = [C.c_void_p, C.POINTER(Cloud), C.POINTER(Cloud), C.c_void_p, C.POINTER(RegistrationParameters),
                                            C.c_int, C.POINTER(Result)]
+        L.s3d_prepare_cloud.argtypes = [C.c_void_p, C.c_int, Cloud, C.c_double, C.c_int, C.POINTER(C.c_void_p)]
+        L.s3d_release_cloud.argtypes = [C.c_void_p, C.c_void_p]
+        L.s3d_prepared_cloud_size.restype = C.c_uint64
+        L.s3d_prepared_cloud_size.argtypes = [C.c_void_p]
+        L.s3d_gicp_align_prepared.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RegistrationParameters), C.POINTER(Result)]
+        L.s3d_gicp_align_prepared_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,
+                                                    C.POINTER(RegistrationParameters), C.c_int, C.POINTER(Result)]
         _lib = L
     return _lib
 
@@ -182,6 +189,64 @@ class Context:
         st = lib().s3d_gicp_align_batch(self._h, sc, tc, g.ctypes.data, C.byref(p), n, res)
         self._check(st, "s3d_gicp_align_batch")
         return list(res)
+
+
+class PreparedCloud:
+    """Device-resident, preprocessed scan (s3d_prepare_cloud): voxel filter + NN grid + covariances done once."""
+
+    def __init__(self, ctx, handle, density, k):
+        self._ctx, self._h, self.density, self.k = ctx, handle, density, k
+
+    @property
+    def size(self):
+        return int(lib().s3d_prepared_cloud_size(self._h))
+
+    def release(self):
+        if self._h:
+            lib().s3d_release_cloud(self._ctx._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self._ctx._h:
+                self.release()
+        except Exception:
+            pass
+
+
+def _prepare_cloud(self, cloud, density, k=20, device_slot=0):
+    a, c = _cloud(cloud)
+    h = C.c_void_p()
+    st = lib().s3d_prepare_cloud(self._h, device_slot, c, float(density), int(k), C.byref(h))
+    self._check(st, "s3d_prepare_cloud")
+    return PreparedCloud(self, h, float(density), int(k))
+
+
+def _gicp_align_prepared(self, source, target, guess=None, params=None):
+    g = _colmajor(guess)
+    p = params if params is not None else RegistrationParameters.defaults()
+    res = Result()
+    st = lib().s3d_gicp_align_prepared(self._h, source._h, target._h, g.ctypes.data, C.byref(p), C.byref(res))
+    if st in (_abi.S3D_INTERNAL_ERROR, _abi.S3D_INVALID_ARGUMENT):
+        raise S3DError(f"s3d_gicp_align_prepared failed ({st}): {last_error()}")
+    return res
+
+
+def _gicp_align_prepared_batch(self, sources, targets, guesses=None, params=None):
+    n = len(sources)
+    sp = (C.c_void_p * n)(*[s._h for s in sources])
+    tp = (C.c_void_p * n)(*[t._h for t in targets])
+    g = np.ascontiguousarray(np.stack([_colmajor(None if guesses is None else guesses[i]) for i in range(n)]))
+    p = params if params is not None else RegistrationParameters.defaults()
+    res = (Result * n)()
+    st = lib().s3d_gicp_align_prepared_batch(self._h, sp, tp, g.ctypes.data, C.byref(p), n, res)
+    self._check(st, "s3d_gicp_align_prepared_batch")
+    return list(res)
+
+
+Context.prepare_cloud = _prepare_cloud
+Context.gicp_align_prepared = _gicp_align_prepared
+Context.gicp_align_prepared_batch = _gicp_align_prepared_batch
 
 
 def last_error():

@@ -23,11 +23,21 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 struct DeviceCtx {
   int device = 0;
   std::mutex mu;
+  std::vector<std::pair<void*, size_t>> free_blocks;  // recycled allocations of released prepared clouds
   std::vector<std::unique_ptr<Workspace>> pool;  // idle workspaces
   std::vector<Workspace*> all;
 };
 
 }  // namespace s3d
+
+struct s3d_prepared_cloud {
+  int device_slot = 0;
+  s3d::SlotInfo info;        // host copy; gpts / normals / table point into `block`
+  void* block = nullptr;     // one device allocation: [gpts | normals | hash table]
+  size_t block_bytes = 0;
+  double density = 0;
+  int k = 0;
+};
 
 struct s3d_context {
   std::vector<std::unique_ptr<s3d::DeviceCtx>> devs;
@@ -224,6 +234,9 @@ int s3d_destroy_context(s3d_context* ctx) {
   for (auto& dc : ctx->devs) {
     for (auto& ws : dc->pool) ws->destroy();
     dc->pool.clear();
+    cudaSetDevice(dc->device);
+    for (auto& b : dc->free_blocks) cudaFree(b.first);
+    dc->free_blocks.clear();
   }
   delete ctx;
   return S3D_OK;
@@ -348,6 +361,183 @@ int s3d_nearest_neighbors(s3d_context* ctx, s3d_cloud reference, s3d_cloud queri
     });
     return S3D_OK;
   });
+}
+
+// ---- per-measurement device cache ---------------------------------------------------------------------------------
+static void* block_alloc(DeviceCtx* dc, size_t bytes, size_t* got) {
+  {
+    std::lock_guard<std::mutex> g(dc->mu);
+    for (size_t i = 0; i < dc->free_blocks.size(); ++i)
+      if (dc->free_blocks[i].second >= bytes && dc->free_blocks[i].second <= 2 * bytes + 4096) {
+        void* p = dc->free_blocks[i].first; *got = dc->free_blocks[i].second;
+        dc->free_blocks.erase(dc->free_blocks.begin() + i);
+        return p;
+      }
+  }
+  void* p = nullptr;
+  S3D_CUDA(cudaMalloc(&p, bytes));
+  *got = bytes;
+  return p;
+}
+
+int s3d_prepare_cloud(s3d_context* ctx, int device_slot, s3d_cloud cloud, double density, int k, s3d_prepared_cloud** out) {
+  if (!ctx || !out || device_slot < 0 || device_slot >= (int)ctx->devs.size()) return S3D_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (k < 1 || k > 32) { set_error("correspondence_randomness must be in [1, 32] on the GPU path"); return S3D_INVALID_ARGUMENT; }
+  return guarded([&]() -> int {
+    WsLease lease(ctx, device_slot);
+    Workspace& ws = *lease;
+    std::unique_ptr<s3d_prepared_cloud> h(new s3d_prepared_cloud());
+    h->device_slot = device_slot; h->density = density; h->k = k;
+    const float leaf = density > 0 ? (float)density : 0.f;
+    SlotInfo* hs = nullptr;
+    with_arena_retry(ws, [&] {
+      setup_batch(ws, {cloud.xyzw}, {cloud.n}, 0);
+      run_voxel(ws, leaf);
+      if (cloud.n) { run_grid(ws, leaf); run_knn_covariances(ws, k, nullptr, nullptr); }
+      hs = ws.h_slots.as<SlotInfo>();
+      int32_t* hf = ws.h_small.as<int32_t>();
+      S3D_CUDA(cudaMemcpyAsync(hs, ws.slots.p, sizeof(SlotInfo), cudaMemcpyDeviceToHost, ws.stream));
+      S3D_CUDA(cudaMemcpyAsync(hf, ws.flags.p, 16, cudaMemcpyDeviceToHost, ws.stream));
+      S3D_CUDA(cudaStreamSynchronize(ws.stream));
+      ws.d2h += sizeof(SlotInfo) + 16;
+      ws.collect_spans();
+      check_arena(ws, hf);
+    });
+    h->info = hs[0];
+    const size_t n = h->info.n_pts;
+    auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+    const size_t b_pts = up(16 * n), b_nrm = up(32 * n), b_tab = up(sizeof(HashEntry) * (size_t)h->info.hash_cap);
+    if (n) {
+      h->block = block_alloc(ctx->devs[device_slot].get(), b_pts + b_nrm + b_tab, &h->block_bytes);
+      char* base = static_cast<char*>(h->block);
+      S3D_CUDA(cudaMemcpyAsync(base, ws.gpts.as<float4>() + hs[0].off, 16 * n, cudaMemcpyDeviceToDevice, ws.stream));
+      S3D_CUDA(cudaMemcpyAsync(base + b_pts, ws.normals.as<double4>() + hs[0].off, 32 * n, cudaMemcpyDeviceToDevice, ws.stream));
+      S3D_CUDA(cudaMemcpyAsync(base + b_pts + b_nrm, ws.hash.as<HashEntry>() + hs[0].hash_off, sizeof(HashEntry) * (size_t)h->info.hash_cap,
+                               cudaMemcpyDeviceToDevice, ws.stream));
+      S3D_CUDA(cudaStreamSynchronize(ws.stream));
+      h->info.gpts = reinterpret_cast<const float4*>(base);
+      h->info.normals = reinterpret_cast<const double4*>(base + b_pts);
+      h->info.table = reinterpret_cast<const HashEntry*>(base + b_pts + b_nrm);
+    } else {
+      h->info.gpts = nullptr; h->info.normals = nullptr; h->info.table = nullptr; h->info.hash_cap = 0;
+    }
+    h->info.hash_off = 0; h->info.off = 0; h->info.raw = nullptr;
+    *out = h.release();
+    return S3D_OK;
+  });
+}
+
+int s3d_release_cloud(s3d_context* ctx, s3d_prepared_cloud* cloud) {
+  if (!cloud) return S3D_OK;
+  if (!ctx || cloud->device_slot >= (int)ctx->devs.size()) return S3D_INVALID_ARGUMENT;
+  if (cloud->block) {
+    DeviceCtx* dc = ctx->devs[cloud->device_slot].get();
+    std::lock_guard<std::mutex> g(dc->mu);
+    dc->free_blocks.emplace_back(cloud->block, cloud->block_bytes);  // recycled by the next prepare; freed with the context
+  }
+  delete cloud;
+  return S3D_OK;
+}
+
+uint64_t s3d_prepared_cloud_size(const s3d_prepared_cloud* cloud) { return cloud ? cloud->info.n_pts : 0; }
+
+namespace s3d {
+// One sub-batch of align() calls on prepared clouds (all on device slot `slot`).
+static void align_prepared_chunk(s3d_context* ctx, int slot, const s3d_prepared_cloud* const* sources, const s3d_prepared_cloud* const* targets,
+                                 const double* guesses, const s3d_registration_parameters& cfg, int n, s3d_result* out) {
+  WsLease lease(ctx, slot);
+  Workspace& ws = *lease;
+  S3D_CUDA(cudaSetDevice(ws.device));
+  const uint32_t ns = 2 * n;
+  ws.n_slots = ns; ws.n_pairs = n; ws.n_tiles = 0;
+  ws.h_off.assign(ns, 0); ws.h_n.assign(ns, 0);
+  ws.pair_off.resize(n);
+  ws.slots.reserve(sizeof(SlotInfo) * ns);
+  ws.h_slots.reserve(sizeof(SlotInfo) * ns);
+  SlotInfo* hs = ws.h_slots.as<SlotInfo>();
+  uint64_t total = 0;
+  ws.max_na = 0;
+  for (int i = 0; i < n; ++i) {
+    hs[2 * i] = sources[i]->info; hs[2 * i + 1] = targets[i]->info;
+    ws.h_n[2 * i] = sources[i]->info.n_pts; ws.h_n[2 * i + 1] = targets[i]->info.n_pts;
+    ws.pair_off[i] = (uint32_t)total;
+    total += (targets[i]->info.n_pts + 3u) & ~3u;
+    ws.max_na = std::max(ws.max_na, targets[i]->info.n_pts);
+  }
+  if (total >= (1ull << 31)) throw CudaError{"batch too large: more than 2^31 points"};
+  ws.total = (uint32_t)total;
+  S3D_CUDA(cudaMemcpyAsync(ws.slots.p, hs, sizeof(SlotInfo) * ns, cudaMemcpyHostToDevice, ws.stream));
+  S3D_CUDA(cudaMemsetAsync(ws.flags.p, 0, 64, ws.stream));
+  if (cfg.registration_algorithm != S3D_ALG_GICP) {  // same order as align(): <100 gate first, then the algorithm switch
+    for (int i = 0; i < n; ++i) {
+      memset(&out[i], 0, sizeof out[i]);
+      for (int j = 0; j < 16; ++j) out[i].T[j] = (j % 5 == 0) ? 1.0 : 0.0;
+      out[i].n_source = ws.h_n[2 * i]; out[i].n_target = ws.h_n[2 * i + 1];
+      out[i].status = (out[i].n_source < 100 || out[i].n_target < 100) ? S3D_TOO_FEW_POINTS : S3D_UNKNOWN_ALGORITHM;
+    }
+    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    if (cfg.registration_algorithm == S3D_ALG_GICP_OMP || cfg.registration_algorithm == S3D_ALG_NDT_OMP)
+      set_error("OMP is not available, you need to rebuild SLAM3D with OMP or use another matching algorithm.");
+    else if (cfg.registration_algorithm == S3D_ALG_NDT) set_error("NDT is not implemented by the B200 path (SURVEY 8f rank 4).");
+    else set_error("Unknown registration algorithm specified.");
+    return;
+  }
+  std::vector<s3d_registration_parameters> params(n, cfg);
+  run_gicp(ws, params, guesses, out);
+}
+}  // namespace s3d
+
+int s3d_gicp_align_prepared_batch(s3d_context* ctx, const s3d_prepared_cloud* const* sources, const s3d_prepared_cloud* const* targets,
+                                  const double* guesses, const s3d_registration_parameters* params, int n_pairs, s3d_result* out) {
+  if (!ctx || !params || !out || n_pairs < 0 || (n_pairs > 0 && (!sources || !targets || !guesses))) return S3D_INVALID_ARGUMENT;
+  if (n_pairs == 0) return S3D_OK;
+  const int slot = sources[0] ? sources[0]->device_slot : 0;
+  for (int i = 0; i < n_pairs; ++i) {
+    if (!sources[i] || !targets[i]) return S3D_INVALID_ARGUMENT;
+    if (sources[i]->device_slot != slot || targets[i]->device_slot != slot) { set_error("prepared clouds of one call must live on one device"); return S3D_INVALID_ARGUMENT; }
+    for (const s3d_prepared_cloud* h : {sources[i], targets[i]})
+      if (h->density != params->point_cloud_density || (params->registration_algorithm == S3D_ALG_GICP && h->k != params->correspondence_randomness)) {
+        set_error("prepared cloud was built with another point_cloud_density / correspondence_randomness");
+        return S3D_INVALID_ARGUMENT;
+      }
+  }
+  const int W = std::max(1, ctx->streams_per_device);
+  std::vector<int> st(W, S3D_OK);
+  std::vector<std::string> errs(W);
+  std::atomic<int> next{0};
+  const int chunk = std::max(1, std::min(ctx->max_pairs_per_launch, (n_pairs + W - 1) / W));
+  auto worker = [&](int w) {
+    st[w] = guarded([&]() -> int {
+      for (;;) {
+        const int b = next.fetch_add(1) * chunk;
+        if (b >= n_pairs) break;
+        const int n = std::min(chunk, n_pairs - b);
+        align_prepared_chunk(ctx, slot, sources + b, targets + b, guesses + 16 * (size_t)b, *params, n, out + b);
+      }
+      return S3D_OK;
+    });
+    if (st[w] != S3D_OK) errs[w] = g_last_error;
+  };
+  if (W == 1 || n_pairs == 1) worker(0);
+  else {
+    std::vector<std::thread> th;
+    for (int w = 0; w < W; ++w) th.emplace_back(worker, w);
+    for (auto& t : th) t.join();
+  }
+  for (int w = 0; w < W; ++w) if (st[w] != S3D_OK) { set_error(errs[w]); return st[w]; }
+  return S3D_OK;
+}
+
+int s3d_gicp_align_prepared(s3d_context* ctx, const s3d_prepared_cloud* source, const s3d_prepared_cloud* target, const double guess[16],
+                            const s3d_registration_parameters* params, s3d_result* out) {
+  if (!ctx || !params || !out || !guess || !source || !target) return S3D_INVALID_ARGUMENT;
+  memset(out, 0, sizeof *out);
+  const int st = s3d_gicp_align_prepared_batch(ctx, &source, &target, guess, params, 1, out);
+  if (st != S3D_OK) { out->status = st; return st; }
+  std::string buf;
+  if (const char* msg = status_text(out->status, *out, *params, buf)) set_error(msg);
+  return out->status;
 }
 
 int s3d_gicp_align_batch(s3d_context* ctx, const s3d_cloud* sources, const s3d_cloud* targets, const double* guesses,

@@ -20,6 +20,8 @@ constexpr int kMaxLevels = 10;       // Morton bits per axis (30-bit keys)
 constexpr uint32_t kInvalidKey = 0xFFFFFFFFu;
 constexpr uint32_t kNoIndex = 0xFFFFFFFFu;
 
+struct HashEntry;
+
 // Per-slot description, device resident.
 struct SlotInfo {
   // --- raw input -----------------------------------------------------------------------------------
@@ -44,6 +46,10 @@ struct SlotInfo {
   uint32_t hash_off;              // first entry of this slot's table in the hash arena
   uint32_t hash_cap;              // entries
   uint32_t n_cells;               // occupied cells over all levels
+  // --- where the prepared cloud lives (batch workspace arrays + off, or the buffers of an s3d_prepared_cloud) ---------
+  const float4*    gpts;          // Morton-sorted points, .w = original index bits
+  const double4*   normals;       // unit normal of the regularised covariance per sorted point
+  const HashEntry* table;         // hash arena base; this slot's entries start at hash_off
 };
 
 // Host-built tile table: tile t of a launch belongs to slot tile_slot[t] and covers elements

@@ -81,7 +81,7 @@ __device__ void begin_outer(PairState& ps) {
 }
 
 // Registration::align set-up: gates of align() :134-135, output = guess * input (transformPointCloud), state reset.
-__global__ void __launch_bounds__(256) gicp_prepare_kernel(const SlotInfo* __restrict__ slots, PairState* __restrict__ pairs, const float4* __restrict__ gpts,
+__global__ void __launch_bounds__(256) gicp_prepare_kernel(const SlotInfo* __restrict__ slots, PairState* __restrict__ pairs,
                                                            float4* __restrict__ moved, uint32_t* __restrict__ prev_nn, float* __restrict__ sec_lb,
                                                            int32_t* __restrict__ flags) {
   const uint32_t p = blockIdx.y;
@@ -97,11 +97,11 @@ __global__ void __launch_bounds__(256) gicp_prepare_kernel(const SlotInfo* __res
   if (!enough) return;
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= sa.n_pts) return;
-  const float4 v = gpts[sa.off + r];
+  const float4 v = sa.gpts[r];
   const float3 m = transform_se3(ps.guess, v.x, v.y, v.z);
-  moved[sa.off + r] = make_float4(m.x, m.y, m.z, v.w);
-  prev_nn[sa.off + r] = kNoIndex;
-  sec_lb[sa.off + r] = 0.f;
+  moved[ps.pt_off + r] = make_float4(m.x, m.y, m.z, v.w);
+  prev_nn[ps.pt_off + r] = kNoIndex;
+  sec_lb[ps.pt_off + r] = 0.f;
 }
 
 // Temporal-coherence certificate (exactness preserving).  The last search for this point ran at position q_old and left
@@ -123,8 +123,7 @@ __device__ __forceinline__ bool certified_same_nn(const GridView& g, float3 q, f
 }
 
 __global__ void __launch_bounds__(kIterTile) gicp_iter_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
-                                                              const HashEntry* __restrict__ arena, const float4* __restrict__ gpts,
-                                                              const float4* __restrict__ moved, const double4* __restrict__ normals,
+                                                              const float4* __restrict__ moved,
                                                               uint32_t* __restrict__ prev_nn, float* __restrict__ sec_lb, uint32_t* __restrict__ corr,
                                                               double* __restrict__ mahal, double* __restrict__ moments) {
   __shared__ double feat[kIterTile][kFeat];
@@ -141,30 +140,30 @@ __global__ void __launch_bounds__(kIterTile) gicp_iter_kernel(const SlotInfo* __
 #pragma unroll
   for (int i = 0; i < kFeat; ++i) f[i] = 0.0;
   if (r < sa.n_pts) {
-    const GridView g = make_grid_view(sb, arena, gpts);
-    const float4 mv = moved[sa.off + r];
+    const GridView g = make_grid_view(sb);
+    const float4 mv = moved[ps.pt_off + r];
     const float3 q = transform_mv(ps.T, mv.x, mv.y, mv.z);
     const double thr = ps.max_corr2;
     const float cutoff = __double2float_ru(thr);
-    const uint32_t hint = prev_nn[sa.off + r];
+    const uint32_t hint = prev_nn[ps.pt_off + r];
     NNResult nn;
     float lb_new;
-    if (!certified_same_nn(g, q, transform_mv(ps.T_search, mv.x, mv.y, mv.z), hint, sec_lb[sa.off + r], nn, lb_new)) {
+    if (!certified_same_nn(g, q, transform_mv(ps.T_search, mv.x, mv.y, mv.z), hint, sec_lb[ps.pt_off + r], nn, lb_new)) {
       nn = nn_search(g, q.x, q.y, q.z, cutoff, hint);
-      prev_nn[sa.off + r] = nn.pos;
+      prev_nn[ps.pt_off + r] = nn.pos;
       lb_new = sqrtf(nn.lb2) * 0.99999f;
     }
-    sec_lb[sa.off + r] = lb_new;
+    sec_lb[ps.pt_off + r] = lb_new;
     uint32_t c = kNoIndex;
     if (nn.pos != kNoIndex && (double)nn.d2 < thr) {
       c = nn.pos;
-      const double4 n1 = normals[sa.off + r];
-      const double4 n2 = normals[sb.off + nn.pos];
+      const double4 n1 = sa.normals[r];
+      const double4 n2 = sb.normals[nn.pos];
       double a[3], b[3] = {n2.x, n2.y, n2.z};
       for (int i = 0; i < 3; ++i) a[i] = ps.R[i][0] * n1.x + ps.R[i][1] * n1.y + ps.R[i][2] * n1.z;
       double M[6];
       mahalanobis6(ps.RRt, a, b, M);
-      double* mo = mahal + 6 * (size_t)(sa.off + r);
+      double* mo = mahal + 6 * (size_t)(ps.pt_off + r);
 #pragma unroll
       for (int i = 0; i < 6; ++i) mo[i] = M[i];
       // PCL's first objective evaluation of this outer iteration: d = float(T(x0) * p) - q, float subtraction, then double
@@ -181,7 +180,7 @@ __global__ void __launch_bounds__(kIterTile) gicp_iter_kernel(const SlotInfo* __
       f[12] = d0 * Md0 + d1 * Md1 + d2 * Md2;
       f[13] = 1.0;
     }
-    corr[sa.off + r] = c;
+    corr[ps.pt_off + r] = c;
   }
 #pragma unroll
   for (int i = 0; i < kFeat; ++i) feat[threadIdx.x][i] = f[i];
@@ -204,7 +203,7 @@ __global__ void __launch_bounds__(kIterTile) gicp_iter_kernel(const SlotInfo* __
 
 // One objective evaluation at the trial state of every pair in kPhaseEval: the 13 residual sums per 256-point tile.
 __global__ void __launch_bounds__(kIterTile) gicp_eval_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
-                                                              const float4* __restrict__ gpts, const float4* __restrict__ moved,
+                                                              const float4* __restrict__ moved,
                                                               const uint32_t* __restrict__ corr, const double* __restrict__ mahal,
                                                               double* __restrict__ eval_part) {
   __shared__ double feat[kIterTile][8];  // px py pz | (Md)0..2 | d^T M d | 1
@@ -219,11 +218,11 @@ __global__ void __launch_bounds__(kIterTile) gicp_eval_kernel(const SlotInfo* __
   const uint32_t r = first + threadIdx.x;
   double f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (r < sa.n_pts) {
-    const uint32_t c = corr[sa.off + r];
+    const uint32_t c = corr[ps.pt_off + r];
     if (c != kNoIndex) {
-      const float4 mv = moved[sa.off + r];
-      const float4 qb = gpts[sb.off + c];
-      const double* M = mahal + 6 * (size_t)(sa.off + r);
+      const float4 mv = moved[ps.pt_off + r];
+      const float4 qb = sb.gpts[c];
+      const double* M = mahal + 6 * (size_t)(ps.pt_off + r);
       const float3 pp = transform_mv(ps.T_eval, mv.x, mv.y, mv.z);
       const double d0 = (double)__fsub_rn(pp.x, qb.x), d1 = (double)__fsub_rn(pp.y, qb.y), d2 = (double)__fsub_rn(pp.z, qb.z);
       const double Md0 = M[0] * d0 + M[1] * d1 + M[2] * d2;
@@ -313,13 +312,27 @@ __global__ void __launch_bounds__(256) gicp_ctrl_kernel(const SlotInfo* __restri
   __syncthreads();
   if ((int)threadIdx.x < n_sums) ps.sums[(after_eval ? 60 : 0) + threadIdx.x] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x];
   __syncthreads();
-  if (threadIdx.x != 0) return;
-  if (!after_eval) {
-    ps.n_corr = (uint32_t)ps.sums[73];
-    for (int i = 0; i < 16; ++i) { ps.prev[i] = ps.T[i]; ps.T_search[i] = ps.T[i]; }  // previous_transformation_ = transformation_
-    if (ps.sums[73] < 4.0) { finish_outer(ps, true, flags); return; }  // min_number_correspondences_: PCL throws
+  // objective at the evaluated state: one thread builds the Euler derivative tensors, 42 threads contract one entry each
+  __shared__ Euler E;
+  __shared__ double gH[42];
+  __shared__ int go;
+  if (threadIdx.x == 0) {
+    go = 1;
+    if (!after_eval) {
+      ps.n_corr = (uint32_t)ps.sums[73];
+      for (int i = 0; i < 16; ++i) { ps.prev[i] = ps.T[i]; ps.T_search[i] = ps.T[i]; }  // previous_transformation_ = transformation_
+      if (ps.sums[73] < 4.0) { finish_outer(ps, true, flags); go = 0; }  // min_number_correspondences_: PCL throws
+    }
+    if (go) euler_derivs(ps.nst.xc, E, true);
   }
-  if (newton_advance(ps.nst, ps.sums, ps.max_inner)) {
+  __syncthreads();
+  if (!go) return;
+  if (threadIdx.x < 42) gH[threadIdx.x] = objective_entry(ps.sums, E, threadIdx.x);
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double g[6], H[6][6];
+  for (int i = 0; i < 6; ++i) { g[i] = gH[i]; for (int j = 0; j < 6; ++j) H[i][j] = gH[6 + 6 * i + j]; }
+  if (newton_advance_pre(ps.nst, ps.sums[72] / ps.sums[73], g, H, ps.max_inner)) {
     matrix_from_state(ps.nst.xc, ps.T_eval);
     ps.phase = kPhaseEval;
   } else {
@@ -329,7 +342,6 @@ __global__ void __launch_bounds__(256) gicp_ctrl_kernel(const SlotInfo* __restri
 
 // getFitnessScore(max_range): transformPointCloud(input, final), 1-NN, d2 <= max_range (sic), mean of d2   (A.6)
 __global__ void __launch_bounds__(kIterTile) gicp_fitness_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
-                                                                 const HashEntry* __restrict__ arena, const float4* __restrict__ gpts,
                                                                  const float4* __restrict__ moved, const uint32_t* __restrict__ prev_nn,
                                                                  const float* __restrict__ sec_lb, double* __restrict__ fit_partial) {
   __shared__ double ssum[kIterTile];
@@ -344,14 +356,14 @@ __global__ void __launch_bounds__(kIterTile) gicp_fitness_kernel(const SlotInfo*
   const uint32_t r = first + threadIdx.x;
   double s = 0.0; uint32_t c = 0;
   if (r < sa.n_pts) {
-    const GridView g = make_grid_view(sb, arena, gpts);
-    const float4 v = gpts[sa.off + r];
+    const GridView g = make_grid_view(sb);
+    const float4 v = sa.gpts[r];
     const float3 q = transform_se3(ps.final_T, v.x, v.y, v.z);
-    const float4 mv = moved[sa.off + r];
-    const uint32_t hint = prev_nn[sa.off + r];
+    const float4 mv = moved[ps.pt_off + r];
+    const uint32_t hint = prev_nn[ps.pt_off + r];
     NNResult nn;
     float lb_new;
-    if (!certified_same_nn(g, q, transform_mv(ps.T_search, mv.x, mv.y, mv.z), hint, sec_lb[sa.off + r], nn, lb_new))
+    if (!certified_same_nn(g, q, transform_mv(ps.T_search, mv.x, mv.y, mv.z), hint, sec_lb[ps.pt_off + r], nn, lb_new))
       nn = nn_search(g, q.x, q.y, q.z, __double2float_ru(ps.fit_range), hint);
     if (nn.pos != kNoIndex && (double)nn.d2 <= ps.fit_range) { s = (double)nn.d2; c = 1; }
   }
@@ -431,8 +443,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   }
   const uint32_t np = ws.n_pairs;
   cudaStream_t st = ws.stream;
-  uint32_t max_na = 0;
-  for (uint32_t p = 0; p < np; ++p) max_na = std::max(max_na, ws.h_n[2 * p + 1]);
+  const uint32_t max_na = ws.max_na;
   const uint32_t tiles_per_pair = std::max<uint32_t>(1, (max_na + kIterTile - 1) / kIterTile);
   ws.pairs.reserve(sizeof(PairState) * np);
   ws.h_pairs.reserve(sizeof(PairState) * np);
@@ -457,6 +468,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
     ps.max_corr2 = cfg.max_correspondence_distance * cfg.max_correspondence_distance;
     ps.rot_eps = cfg.rotation_epsilon; ps.trans_eps = cfg.transformation_epsilon;
     ps.fit_range = cfg.max_correspondence_distance;
+    ps.pt_off = ws.pair_off[p];
     ps.max_iter = cfg.maximum_iterations; ps.max_inner = cfg.maximum_optimizer_iterations; ps.k = cfg.correspondence_randomness;
     max_iter = std::max(max_iter, cfg.maximum_iterations);
   }
@@ -466,7 +478,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   int32_t* flags = ws.flags.as<int32_t>();
   int32_t* h_flags = ws.h_small.as<int32_t>();
   dim3 grid(tiles_per_pair, np);
-  gicp_prepare_kernel<<<grid, 256, 0, st>>>(slots, pairs, ws.gpts.as<float4>(), ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), flags);
+  gicp_prepare_kernel<<<grid, 256, 0, st>>>(slots, pairs, ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), flags);
   ++ws.launches;
   // Rounds: [search + first evaluation] -> ctrl -> [trial evaluation] -> ctrl.  A pair needs one round per outer iteration
   // plus one per extra objective evaluation; PCL's loop is a do-while, so maximum_iterations <= 0 still runs one iteration.
@@ -475,15 +487,14 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   for (long round = 0; round < max_rounds; ++round) {
     {
       StageTimer timer(ws, kStageIter);
-      gicp_iter_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.hash.as<HashEntry>(), ws.gpts.as<float4>(), ws.moved.as<float4>(),
-                                                   ws.normals.as<double4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), ws.corr.as<uint32_t>(),
+      gicp_iter_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), ws.corr.as<uint32_t>(),
                                                    ws.mahal.as<double>(), ws.moments.as<double>());
       ++ws.launches;
     }
     {
       StageTimer timer(ws, kStageSolve);
       gicp_ctrl_kernel<<<np, 256, 0, st>>>(slots, pairs, ws.moments.as<double>(), ws.eval_part.as<double>(), tiles_per_pair, 0, flags);
-      gicp_eval_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.gpts.as<float4>(), ws.moved.as<float4>(), ws.corr.as<uint32_t>(),
+      gicp_eval_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.moved.as<float4>(), ws.corr.as<uint32_t>(),
                                                    ws.mahal.as<double>(), ws.eval_part.as<double>());
       gicp_ctrl_kernel<<<np, 256, 0, st>>>(slots, pairs, ws.moments.as<double>(), ws.eval_part.as<double>(), tiles_per_pair, 1, flags);
       ws.launches += 3;
@@ -502,7 +513,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   }
   {
     StageTimer timer(ws, kStageFitness);
-    gicp_fitness_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.hash.as<HashEntry>(), ws.gpts.as<float4>(), ws.moved.as<float4>(),
+    gicp_fitness_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.moved.as<float4>(),
                                                     ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), ws.fit_partial.as<double>());
     gicp_fitness_reduce_kernel<<<(np + 63) / 64, 64, 0, st>>>(slots, pairs, ws.fit_partial.as<double>(), tiles_per_pair, np);
     ws.launches += 2;

@@ -130,35 +130,42 @@ S3D_HD void matrix_from_state(const double x[6], float T[16]) {
 //   [sym3(a,b)*10 + sym4(c,e)]  sum M[a][b] phi_c phi_e, phi = (p, 1)      x-independent for one correspondence set
 //   [60 + a*4 + c]              sum (M d)[a] phi_c                            d = float(T(x) p) - q  exactly as PCL forms it
 //   [72] sum d^T M d            [73] number of correspondences m
+// One entry of the gradient (idx 0..5) or of the Hessian (idx 6 + 6 i + j), so that the GPU can spread the 42 entries over
+// threads while the host (tests) walks them in a loop — the arithmetic per entry is the same.
+S3D_HD double objective_entry(const double* sums, const Euler& E, int idx) {
+  const double s = 2.0 / sums[73];
+  if (idx < 3) return s * sums[60 + idx * 4 + 3];
+  if (idx < 6) {
+    const int k = idx - 3;
+    double gr = 0;
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) gr += E.dR[k][a][b] * (s * sums[60 + a * 4 + b]);
+    return gr;
+  }
+  int i = (idx - 6) / 6, j = (idx - 6) % 6;
+  if (i < 3 && j < 3) return s * sums[sym3(i, j) * 10 + 9];
+  if (i >= 3 && j < 3) { const int t = i; i = j; j = t; }
+  if (i < 3) {  // translation-rotation block
+    const int a = i, k = j - 3;
+    double h = 0;
+    for (int c = 0; c < 3; ++c) for (int b = 0; b < 3; ++b) h += E.dR[k][c][b] * (s * sums[sym3(a, c) * 10 + sym4(b, 3)]);
+    return h;
+  }
+  const int k = i - 3, l = j - 3;  // rotation-rotation block: first-order part + second-derivative part
+  double h = 0;
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
+      for (int c = 0; c < 3; ++c) for (int e = 0; e < 3; ++e) h += E.dR[k][a][b] * E.dR[l][c][e] * (s * sums[sym3(a, c) * 10 + sym4(b, e)]);
+      h += E.ddR[k][l][a][b] * (s * sums[60 + a * 4 + b]);
+    }
+  return h;
+}
+
 S3D_HD void objective_from_sums(const double* sums, const double x[6], double& f, double (&g)[6], double (&H)[6][6]) {
   Euler E;
   euler_derivs(x, E, true);
-  const double m = sums[73];
-  const double s = 2.0 / m;
-  f = sums[72] / m;
-  for (int a = 0; a < 3; ++a) {
-    g[a] = s * sums[60 + a * 4 + 3];
-    for (int c = 0; c < 3; ++c) H[a][c] = s * sums[sym3(a, c) * 10 + 9];
-  }
-  for (int k = 0; k < 3; ++k) {
-    double gr = 0;
-    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) gr += E.dR[k][a][b] * (s * sums[60 + a * 4 + b]);
-    g[3 + k] = gr;
-    for (int a = 0; a < 3; ++a) {  // translation-rotation block
-      double h = 0;
-      for (int c = 0; c < 3; ++c) for (int b = 0; b < 3; ++b) h += E.dR[k][c][b] * (s * sums[sym3(a, c) * 10 + sym4(b, 3)]);
-      H[a][3 + k] = H[3 + k][a] = h;
-    }
-    for (int l = 0; l < 3; ++l) {  // rotation-rotation block: first-order part + second-derivative part
-      double h = 0;
-      for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b) {
-          for (int c = 0; c < 3; ++c) for (int e = 0; e < 3; ++e) h += E.dR[k][a][b] * E.dR[l][c][e] * (s * sums[sym3(a, c) * 10 + sym4(b, e)]);
-          h += E.ddR[k][l][a][b] * (s * sums[60 + a * 4 + b]);
-        }
-      H[3 + k][3 + l] = h;
-    }
-  }
+  f = sums[72] / sums[73];
+  for (int i = 0; i < 6; ++i) g[i] = objective_entry(sums, E, i);
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) H[i][j] = objective_entry(sums, E, 6 + 6 * i + j);
 }
 
 // delta = H'^-1 g, H' = H with negative eigenvalues replaced by the largest one (PCL 1.14 Newton step).
@@ -218,26 +225,23 @@ S3D_HD bool newton_new_step(NewtonState& st) {  // do { ++it; direction; alpha =
   return true;
 }
 
-// `sums` = evaluation at st.xc.  Returns true when another evaluation (at the new st.xc) is needed, false when the
-// optimiser is finished (result in st.x).  Mirrors PCL 1.14: back-tracking alpha = 1, 1/2, ... (10 trials) until f
-// decreases, stop on no improvement, on both gradient norms < 1e-2, or after max_inner iterations.
-S3D_HD bool newton_advance(NewtonState& st, const double* sums, int max_inner) {
-  if (st.phase == 0) {
-    objective_from_sums(sums, st.x, st.fcur, st.g, st.H);
-    return newton_new_step(st);
+// f, g, H = objective at st.xc (the evaluation that was pending).  Returns true when another evaluation (at the new st.xc)
+// is needed, false when the optimiser is finished (result in st.x).  Mirrors PCL 1.14: back-tracking alpha = 1, 1/2, ...
+// (10 trials) until f decreases, stop on no improvement, on both gradient norms < 1e-2, or after max_inner iterations.
+S3D_HD bool newton_advance_pre(NewtonState& st, double f, const double (&g)[6], const double (&H)[6][6], int max_inner) {
+  if (st.phase == 0 || (st.phase == 1 && f < st.fcur)) {
+    const bool first = st.phase == 0;
+    for (int r = 0; r < 6; ++r) { st.x[r] = st.xc[r]; st.g[r] = g[r]; for (int c = 0; c < 6; ++c) st.H[r][c] = H[r][c]; }
+    st.fcur = f;
+    if (first) return newton_new_step(st);
+    const double gtn = sqrt(st.g[0] * st.g[0] + st.g[1] * st.g[1] + st.g[2] * st.g[2]);
+    const double grn = sqrt(st.g[3] * st.g[3] + st.g[4] * st.g[4] + st.g[5] * st.g[5]);
+    if (gtn < 1e-2 && grn < 1e-2) { st.phase = 2; return false; }  // translation_/rotation_gradient_tolerance_
+    if (st.it < max_inner) return newton_new_step(st);
+    st.phase = 2;
+    return false;
   }
   if (st.phase == 1) {
-    const double fc = sums[72] / sums[73];
-    if (fc < st.fcur) {
-      for (int r = 0; r < 6; ++r) st.x[r] = st.xc[r];
-      objective_from_sums(sums, st.x, st.fcur, st.g, st.H);
-      const double gtn = sqrt(st.g[0] * st.g[0] + st.g[1] * st.g[1] + st.g[2] * st.g[2]);
-      const double grn = sqrt(st.g[3] * st.g[3] + st.g[4] * st.g[4] + st.g[5] * st.g[5]);
-      if (gtn < 1e-2 && grn < 1e-2) { st.phase = 2; return false; }  // translation_/rotation_gradient_tolerance_
-      if (st.it < max_inner) return newton_new_step(st);
-      st.phase = 2;
-      return false;
-    }
     ++st.ls;
     st.alpha /= 2;
     if (st.ls < 10) {
@@ -248,6 +252,13 @@ S3D_HD bool newton_advance(NewtonState& st, const double* sums, int max_inner) {
     return false;
   }
   return false;
+}
+
+// `sums` = evaluation at st.xc (host-side convenience: computes the objective, then advances)
+S3D_HD bool newton_advance(NewtonState& st, const double* sums, int max_inner) {
+  double f, g[6], H[6][6];
+  objective_from_sums(sums, st.xc, f, g, H);
+  return newton_advance_pre(st, f, g, H, max_inner);
 }
 
 // Mahalanobis matrix of one correspondence: M = (R C1 R^T + C2)^-1 with C = I - (1-eps) n n^T.

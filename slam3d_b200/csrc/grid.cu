@@ -158,11 +158,6 @@ void run_grid(Workspace& ws, float leaf_hint) {
   StageTimer timer(ws, kStageGrid);
   SlotInfo* slots = ws.slots.as<SlotInfo>();
   TileMap tm{ws.tile_slot.as<uint32_t>(), ws.tile_first.as<uint32_t>(), ws.n_tiles};
-  // arena: ~1.2 occupied cells per point is typical for voxel-filtered lidar scans; 3 entries/point leaves 25% head-room
-  // at load factor 1/2.  Sparse clouds (every point alone in its cell on many levels) overflow it: the layout kernel
-  // then flags kErrHashArena and reports the exact need, and the caller re-runs the batch (with_arena_retry).
-  const size_t want = std::max(ws.hash_want, 3 * size_t(ws.total) + 64 * size_t(ws.n_slots));
-  if (ws.hash_cap < want) { ws.hash.reserve(sizeof(HashEntry) * want); ws.hash_cap = want; }
   launch_bbox(ws, kCountPts);
   grid_params_kernel<<<(ws.n_slots + 63) / 64, 64, 0, st>>>(slots, ws.n_slots, leaf_hint);
   uint32_t* keys[2] = {ws.keys0.as<uint32_t>(), ws.keys1.as<uint32_t>()};

@@ -77,8 +77,8 @@ struct PairState {
   int32_t failed;          // optimiser exception (<4 correspondences)
   int32_t outer_iterations, inner_iterations;
   uint32_t n_corr;
-  uint32_t tiles_done;     // last-block-done counter of the iteration kernel
-  uint32_t fit_tiles_done;
+  uint32_t pt_off;         // first index of this pair in the per-pair arrays (moved, prev_nn, sec_lb, corr, mahal)
+  uint32_t reserved;
 };
 
 constexpr int kIterTile = 256;   // source points per CTA in the fused correspondence kernel
@@ -90,6 +90,8 @@ struct Workspace {
   // sizes of the current batch
   uint32_t n_slots = 0, n_pairs = 0, total = 0, n_tiles = 0;
   std::vector<uint32_t> h_off, h_n;           // per slot
+  std::vector<uint32_t> pair_off;             // per pair: offset into the per-pair arrays
+  uint32_t max_na = 0;                        // largest moving cloud of the batch (upper bound of the iteration grid)
   DevBuf slots, pairs;                        // SlotInfo[n_slots], PairState[n_pairs]
   DevBuf raw_stage;                           // float4[total]   H2D landing zone for host inputs
   DevBuf work, gpts;                          // float4[total]

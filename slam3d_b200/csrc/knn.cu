@@ -54,8 +54,7 @@ __device__ __forceinline__ void heap_sift_down(uint64_t* h, int n, uint64_t x, i
 // lexicographic (d2, idx) order of the parity contract — and the k best live in a per-thread max-heap in shared
 // memory (bank-conflict free: element j of thread t at [j][t]).  A cell is skipped when the lower bound of its distance
 // exceeds the current k-th best.  Heapsort at the end yields FLANN's ascending neighbour order for the moments.
-__global__ void __launch_bounds__(kKnnThreads, S3D_KNN_MINBLOCKS) knn_cov_kernel(const SlotInfo* __restrict__ slots, const HashEntry* __restrict__ arena,
-                                                              const float4* __restrict__ gpts, const float4* __restrict__ work,
+__global__ void __launch_bounds__(kKnnThreads, S3D_KNN_MINBLOCKS) knn_cov_kernel(const SlotInfo* __restrict__ slots, const float4* __restrict__ work,
                                                               double4* __restrict__ normals, int k, uint32_t* __restrict__ knn_index,
                                                               float* __restrict__ knn_dist2) {
   extern __shared__ uint64_t heap_smem[];  // k * kKnnThreads keys
@@ -63,7 +62,7 @@ __global__ void __launch_bounds__(kKnnThreads, S3D_KNN_MINBLOCKS) knn_cov_kernel
   const uint32_t n = si.n_pts;
   const uint32_t r = blockIdx.x * kKnnThreads + threadIdx.x;
   if (r >= n) return;
-  const GridView g = make_grid_view(si, arena, gpts);
+  const GridView g = make_grid_view(si);
   if (g.cap == 0) return;  // grid build overflowed its arena: the host re-runs the batch
   const float4* cloud = work + si.off;  // original (voxel-key) order
   const int kk = k < (int)n ? k : (int)n;  // FLANN clamps k to the cloud size
@@ -182,13 +181,12 @@ __global__ void __launch_bounds__(kKnnThreads, S3D_KNN_MINBLOCKS) knn_cov_kernel
 }
 
 // stage-API helper: full regularised covariance per ORIGINAL index, column-major 3x3
-__global__ void expand_cov_kernel(const SlotInfo* __restrict__ slots, const float4* __restrict__ gpts, const double4* __restrict__ normals,
-                                  double* __restrict__ cov_out) {
+__global__ void expand_cov_kernel(const SlotInfo* __restrict__ slots, double* __restrict__ cov_out) {
   const SlotInfo& si = slots[blockIdx.y];
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= si.n_pts || si.hash_cap == 0) return;  // hash_cap == 0: the grid build overflowed, the batch is being re-run
-  const uint32_t orig = __float_as_uint(gpts[si.off + r].w);
-  const double4 nv = normals[si.off + r];
+  const uint32_t orig = __float_as_uint(si.gpts[r].w);
+  const double4 nv = si.normals[r];
   const double nn[3] = {nv.x, nv.y, nv.z};
   double* o = cov_out + ((size_t)si.off + orig) * 9;
   for (int c = 0; c < 3; ++c) for (int rr = 0; rr < 3; ++rr) o[c * 3 + rr] = (rr == c ? 1.0 : 0.0) - (1.0 - kGicpEpsilon) * nn[rr] * nn[c];
@@ -198,11 +196,10 @@ void run_knn_covariances(Workspace& ws, int k, uint32_t* knn_index, float* knn_d
   if (ws.n_tiles == 0) return;
   uint32_t max_n = 0;
   for (uint32_t s = 0; s < ws.n_slots; ++s) max_n = std::max(max_n, ws.h_n[s]);
-  ws.normals.reserve(sizeof(double4) * std::max<size_t>(ws.total, 4));
   StageTimer timer(ws, kStageKnn);
   dim3 grid((max_n + kKnnThreads - 1) / kKnnThreads, ws.n_slots);
-  knn_cov_kernel<<<grid, kKnnThreads, sizeof(uint64_t) * k * kKnnThreads, ws.stream>>>(ws.slots.as<SlotInfo>(), ws.hash.as<HashEntry>(), ws.gpts.as<float4>(),
-                                                         ws.work.as<float4>(), ws.normals.as<double4>(), k, knn_index, knn_dist2);
+  knn_cov_kernel<<<grid, kKnnThreads, sizeof(uint64_t) * k * kKnnThreads, ws.stream>>>(ws.slots.as<SlotInfo>(), ws.work.as<float4>(),
+                                                                                        ws.normals.as<double4>(), k, knn_index, knn_dist2);
   ++ws.launches;
   S3D_CUDA(cudaGetLastError());
 }
@@ -220,19 +217,18 @@ void run_expand_cov(Workspace& ws, double* cov_out) {
   for (uint32_t s = 0; s < ws.n_slots; ++s) max_n = std::max(max_n, ws.h_n[s]);
   if (max_n == 0) return;
   dim3 grid((max_n + 255) / 256, ws.n_slots);
-  expand_cov_kernel<<<grid, 256, 0, ws.stream>>>(ws.slots.as<SlotInfo>(), ws.gpts.as<float4>(), ws.normals.as<double4>(), cov_out);
+  expand_cov_kernel<<<grid, 256, 0, ws.stream>>>(ws.slots.as<SlotInfo>(), cov_out);
   ++ws.launches;
 }
 
 // ---- stage API: exact 1-NN of T*query in a reference slot (thread per query) --------------------------------------
-__global__ void __launch_bounds__(256) nn_stage_kernel(const SlotInfo* __restrict__ slots, const HashEntry* __restrict__ arena,
-                                                       const float4* __restrict__ gpts, uint32_t ref_slot, uint32_t qry_slot,
+__global__ void __launch_bounds__(256) nn_stage_kernel(const SlotInfo* __restrict__ slots, uint32_t ref_slot, uint32_t qry_slot,
                                                        const float* __restrict__ T, uint32_t* __restrict__ nn_index, float* __restrict__ nn_dist2) {
   const SlotInfo& rs = slots[ref_slot];
   const SlotInfo& qs = slots[qry_slot];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= qs.n_raw) return;
-  const GridView g = make_grid_view(rs, arena, gpts);
+  const GridView g = make_grid_view(rs);
   const float4 v = qs.raw[i];
   float3 q = make_float3(v.x, v.y, v.z);
   if (T) q = transform_mv(T, v.x, v.y, v.z);
@@ -244,8 +240,7 @@ __global__ void __launch_bounds__(256) nn_stage_kernel(const SlotInfo* __restric
 void run_nn_stage(Workspace& ws, uint32_t ref_slot, uint32_t qry_slot, const float* T16_dev, uint32_t* nn_index, float* nn_dist2) {
   const uint32_t nq = ws.h_n[qry_slot];
   if (nq == 0) return;
-  nn_stage_kernel<<<(nq + 255) / 256, 256, 0, ws.stream>>>(ws.slots.as<SlotInfo>(), ws.hash.as<HashEntry>(), ws.gpts.as<float4>(), ref_slot,
-                                                           qry_slot, T16_dev, nn_index, nn_dist2);
+  nn_stage_kernel<<<(nq + 255) / 256, 256, 0, ws.stream>>>(ws.slots.as<SlotInfo>(), ref_slot, qry_slot, T16_dev, nn_index, nn_dist2);
   ++ws.launches;
   S3D_CUDA(cudaGetLastError());
 }

@@ -20,9 +20,9 @@ struct GridView {
   float ox, oy, oz, inv_h0, h0, margin;
 };
 
-__device__ __forceinline__ GridView make_grid_view(const SlotInfo& si, const HashEntry* arena, const float4* gpts) {
+__device__ __forceinline__ GridView make_grid_view(const SlotInfo& si) {
   GridView g;
-  g.table = arena + si.hash_off; g.pts = gpts + si.off; g.cap = si.hash_cap; g.n = si.n_pts; g.nlev = si.nlev;
+  g.table = si.table + si.hash_off; g.pts = si.gpts; g.cap = si.hash_cap; g.n = si.n_pts; g.nlev = si.nlev;
   g.ox = si.g_min[0]; g.oy = si.g_min[1]; g.oz = si.g_min[2]; g.inv_h0 = si.inv_h0; g.h0 = si.h0; g.margin = si.margin;
   return g;
 }

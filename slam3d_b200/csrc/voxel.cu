@@ -74,7 +74,17 @@ void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const s
   ws.total = static_cast<uint32_t>(total); ws.n_tiles = n_tiles;
   const size_t tot = std::max<size_t>(total, 4);
   ws.slots.reserve(sizeof(SlotInfo) * ns);
-  ws.work.reserve(16 * tot); ws.gpts.reserve(16 * tot);
+  ws.work.reserve(16 * tot); ws.gpts.reserve(16 * tot); ws.normals.reserve(32 * tot);
+  // hash arena: ~1.2 occupied cells per point is typical for voxel-filtered lidar scans; 3 entries/point leaves 25% head-room
+  // at load factor 1/2.  Sparse clouds (every point alone in its cell on many levels) overflow it: the layout kernel
+  // then flags kErrHashArena and reports the exact need, and the caller re-runs the batch (with_arena_retry in api.cu).
+  {
+    const size_t want = std::max(ws.hash_want, 3 * size_t(total) + 64 * size_t(ns));
+    if (ws.hash_cap < want) { ws.hash.reserve(sizeof(HashEntry) * want); ws.hash_cap = want; }
+  }
+  ws.pair_off.resize(n_pairs);
+  ws.max_na = 0;
+  for (uint32_t p = 0; p < n_pairs; ++p) { ws.pair_off[p] = ws.h_off[2 * p + 1]; ws.max_na = std::max(ws.max_na, ws.h_n[2 * p + 1]); }
   ws.keys0.reserve(4 * tot); ws.keys1.reserve(4 * tot); ws.vals0.reserve(4 * tot); ws.vals1.reserve(4 * tot);
   ws.hist.reserve(sizeof(uint32_t) * 256 * std::max<uint32_t>(n_tiles, 1));
   ws.tile_slot.reserve(4 * std::max<uint32_t>(n_tiles, 1)); ws.tile_first.reserve(4 * std::max<uint32_t>(n_tiles, 1));
@@ -104,6 +114,7 @@ void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const s
     SlotInfo& si = hs[s];
     memset(&si, 0, sizeof si);
     si.off = ws.h_off[s]; si.n_raw = ws.h_n[s];
+    si.gpts = ws.gpts.as<float4>() + si.off; si.normals = ws.normals.as<double4>() + si.off; si.table = ws.hash.as<HashEntry>();
     for (int a = 0; a < 3; ++a) {  // ordered-uint encodings of +inf / -inf, filled in by the bbox kernel
       reinterpret_cast<uint32_t&>(si.bb_min[a]) = 0xFFFFFFFFu; reinterpret_cast<uint32_t&>(si.bb_max[a]) = 0u;
       reinterpret_cast<uint32_t&>(si.g_min[a]) = 0xFFFFFFFFu; reinterpret_cast<uint32_t&>(si.g_max[a]) = 0u;
