@@ -142,6 +142,9 @@ int s3d_get_counters(s3d_context* ctx, s3d_counters* out);
  * (status 6 if the handle was prepared with other values).  Handles are immutable and may be shared by threads. */
 typedef struct s3d_prepared_cloud s3d_prepared_cloud;
 int s3d_prepare_cloud(s3d_context* ctx, int device_slot, s3d_cloud cloud, double density, int k, s3d_prepared_cloud** out);
+/* n clouds in one pass (same result as n calls of s3d_prepare_cloud; out receives n handles, all-or-nothing). */
+int s3d_prepare_clouds(s3d_context* ctx, int device_slot, const s3d_cloud* clouds, int n, double density, int k,
+                       s3d_prepared_cloud** out);
 int s3d_release_cloud(s3d_context* ctx, s3d_prepared_cloud* cloud);
 uint64_t s3d_prepared_cloud_size(const s3d_prepared_cloud* cloud); /* points after filtering */
 int s3d_gicp_align_prepared(s3d_context* ctx, const s3d_prepared_cloud* source, const s3d_prepared_cloud* target,

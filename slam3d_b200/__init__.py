@@ -44,6 +44,7 @@ def lib():
         L.s3d_gicp_align_batch.argtypes = [C.c_void_p, C.POINTER(Cloud), C.POINTER(Cloud), C.c_void_p, C.POINTER(RegistrationParameters),
                                            C.c_int, C.POINTER(Result)]
         L.s3d_prepare_cloud.argtypes = [C.c_void_p, C.c_int, Cloud, C.c_double, C.c_int, C.POINTER(C.c_void_p)]
+        L.s3d_prepare_clouds.argtypes = [C.c_void_p, C.c_int, C.POINTER(Cloud), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_void_p)]
         L.s3d_release_cloud.argtypes = [C.c_void_p, C.c_void_p]
         L.s3d_prepared_cloud_size.restype = C.c_uint64
         L.s3d_prepared_cloud_size.argtypes = [C.c_void_p]
@@ -222,6 +223,18 @@ def _prepare_cloud(self, cloud, density, k=20, device_slot=0):
     return PreparedCloud(self, h, float(density), int(k))
 
 
+def _prepare_clouds(self, clouds, density, k=20, device_slot=0):
+    n = len(clouds)
+    keep = []
+    cc = (Cloud * n)()
+    for i in range(n):
+        a, c = _cloud(clouds[i]); keep.append(a); cc[i] = c
+    hh = (C.c_void_p * n)()
+    st = lib().s3d_prepare_clouds(self._h, device_slot, cc, n, float(density), int(k), hh)
+    self._check(st, "s3d_prepare_clouds")
+    return [PreparedCloud(self, C.c_void_p(hh[i]), float(density), int(k)) for i in range(n)]
+
+
 def _gicp_align_prepared(self, source, target, guess=None, params=None):
     g = _colmajor(guess)
     p = params if params is not None else RegistrationParameters.defaults()
@@ -245,6 +258,7 @@ def _gicp_align_prepared_batch(self, sources, targets, guesses=None, params=None
 
 
 Context.prepare_cloud = _prepare_cloud
+Context.prepare_clouds = _prepare_clouds
 Context.gicp_align_prepared = _gicp_align_prepared
 Context.gicp_align_prepared_batch = _gicp_align_prepared_batch
 

@@ -380,42 +380,46 @@ static void* block_alloc(DeviceCtx* dc, size_t bytes, size_t* got) {
   return p;
 }
 
-int s3d_prepare_cloud(s3d_context* ctx, int device_slot, s3d_cloud cloud, double density, int k, s3d_prepared_cloud** out) {
-  if (!ctx || !out || device_slot < 0 || device_slot >= (int)ctx->devs.size()) return S3D_INVALID_ARGUMENT;
-  *out = nullptr;
-  if (k < 1 || k > 32) { set_error("correspondence_randomness must be in [1, 32] on the GPU path"); return S3D_INVALID_ARGUMENT; }
-  return guarded([&]() -> int {
-    WsLease lease(ctx, device_slot);
-    Workspace& ws = *lease;
-    std::unique_ptr<s3d_prepared_cloud> h(new s3d_prepared_cloud());
+namespace s3d {
+// Per-cloud stages for `n` clouds in one workspace pass, then one device block per cloud.
+static void prepare_chunk(s3d_context* ctx, int device_slot, const s3d_cloud* clouds, int n, double density, int k, s3d_prepared_cloud** out) {
+  WsLease lease(ctx, device_slot);
+  Workspace& ws = *lease;
+  const float leaf = density > 0 ? (float)density : 0.f;
+  std::vector<const float*> ptrs(n);
+  std::vector<uint64_t> sizes(n);
+  uint64_t total = 0;
+  for (int i = 0; i < n; ++i) { ptrs[i] = clouds[i].xyzw; sizes[i] = clouds[i].n; total += clouds[i].n; }
+  SlotInfo* hs = nullptr;
+  with_arena_retry(ws, [&] {
+    setup_batch(ws, ptrs, sizes, 0);
+    run_voxel(ws, leaf);
+    if (total) { run_grid(ws, leaf); run_knn_covariances(ws, k, nullptr, nullptr); }
+    hs = ws.h_slots.as<SlotInfo>();
+    int32_t* hf = ws.h_small.as<int32_t>();
+    S3D_CUDA(cudaMemcpyAsync(hs, ws.slots.p, sizeof(SlotInfo) * n, cudaMemcpyDeviceToHost, ws.stream));
+    S3D_CUDA(cudaMemcpyAsync(hf, ws.flags.p, 16, cudaMemcpyDeviceToHost, ws.stream));
+    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.d2h += sizeof(SlotInfo) * n + 16;
+    ws.collect_spans();
+    check_arena(ws, hf);
+  });
+  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+  std::vector<std::unique_ptr<s3d_prepared_cloud>> hh(n);
+  for (int i = 0; i < n; ++i) {
+    std::unique_ptr<s3d_prepared_cloud>& h = hh[i];
+    h.reset(new s3d_prepared_cloud());
     h->device_slot = device_slot; h->density = density; h->k = k;
-    const float leaf = density > 0 ? (float)density : 0.f;
-    SlotInfo* hs = nullptr;
-    with_arena_retry(ws, [&] {
-      setup_batch(ws, {cloud.xyzw}, {cloud.n}, 0);
-      run_voxel(ws, leaf);
-      if (cloud.n) { run_grid(ws, leaf); run_knn_covariances(ws, k, nullptr, nullptr); }
-      hs = ws.h_slots.as<SlotInfo>();
-      int32_t* hf = ws.h_small.as<int32_t>();
-      S3D_CUDA(cudaMemcpyAsync(hs, ws.slots.p, sizeof(SlotInfo), cudaMemcpyDeviceToHost, ws.stream));
-      S3D_CUDA(cudaMemcpyAsync(hf, ws.flags.p, 16, cudaMemcpyDeviceToHost, ws.stream));
-      S3D_CUDA(cudaStreamSynchronize(ws.stream));
-      ws.d2h += sizeof(SlotInfo) + 16;
-      ws.collect_spans();
-      check_arena(ws, hf);
-    });
-    h->info = hs[0];
-    const size_t n = h->info.n_pts;
-    auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
-    const size_t b_pts = up(16 * n), b_nrm = up(32 * n), b_tab = up(sizeof(HashEntry) * (size_t)h->info.hash_cap);
-    if (n) {
+    h->info = hs[i];
+    const size_t np = h->info.n_pts;
+    const size_t b_pts = up(16 * np), b_nrm = up(32 * np), b_tab = up(sizeof(HashEntry) * (size_t)h->info.hash_cap);
+    if (np) {
       h->block = block_alloc(ctx->devs[device_slot].get(), b_pts + b_nrm + b_tab, &h->block_bytes);
       char* base = static_cast<char*>(h->block);
-      S3D_CUDA(cudaMemcpyAsync(base, ws.gpts.as<float4>() + hs[0].off, 16 * n, cudaMemcpyDeviceToDevice, ws.stream));
-      S3D_CUDA(cudaMemcpyAsync(base + b_pts, ws.normals.as<double4>() + hs[0].off, 32 * n, cudaMemcpyDeviceToDevice, ws.stream));
-      S3D_CUDA(cudaMemcpyAsync(base + b_pts + b_nrm, ws.hash.as<HashEntry>() + hs[0].hash_off, sizeof(HashEntry) * (size_t)h->info.hash_cap,
+      S3D_CUDA(cudaMemcpyAsync(base, ws.gpts.as<float4>() + hs[i].off, 16 * np, cudaMemcpyDeviceToDevice, ws.stream));
+      S3D_CUDA(cudaMemcpyAsync(base + b_pts, ws.normals.as<double4>() + hs[i].off, 32 * np, cudaMemcpyDeviceToDevice, ws.stream));
+      S3D_CUDA(cudaMemcpyAsync(base + b_pts + b_nrm, ws.hash.as<HashEntry>() + hs[i].hash_off, sizeof(HashEntry) * (size_t)h->info.hash_cap,
                                cudaMemcpyDeviceToDevice, ws.stream));
-      S3D_CUDA(cudaStreamSynchronize(ws.stream));
       h->info.gpts = reinterpret_cast<const float4*>(base);
       h->info.normals = reinterpret_cast<const double4*>(base + b_pts);
       h->info.table = reinterpret_cast<const HashEntry*>(base + b_pts + b_nrm);
@@ -423,9 +427,51 @@ int s3d_prepare_cloud(s3d_context* ctx, int device_slot, s3d_cloud cloud, double
       h->info.gpts = nullptr; h->info.normals = nullptr; h->info.table = nullptr; h->info.hash_cap = 0;
     }
     h->info.hash_off = 0; h->info.off = 0; h->info.raw = nullptr;
-    *out = h.release();
-    return S3D_OK;
-  });
+  }
+  S3D_CUDA(cudaStreamSynchronize(ws.stream));
+  for (int i = 0; i < n; ++i) out[i] = hh[i].release();
+}
+}  // namespace s3d
+
+int s3d_prepare_clouds(s3d_context* ctx, int device_slot, const s3d_cloud* clouds, int n, double density, int k, s3d_prepared_cloud** out) {
+  if (!ctx || !out || n < 0 || (n > 0 && !clouds) || device_slot < 0 || device_slot >= (int)ctx->devs.size()) return S3D_INVALID_ARGUMENT;
+  for (int i = 0; i < n; ++i) out[i] = nullptr;
+  if (k < 1 || k > 32) { set_error("correspondence_randomness must be in [1, 32] on the GPU path"); return S3D_INVALID_ARGUMENT; }
+  if (n == 0) return S3D_OK;
+  const int W = std::max(1, ctx->streams_per_device);
+  const int chunk = std::max(1, std::min(2 * ctx->max_pairs_per_launch, (n + W - 1) / W));
+  std::vector<int> st(W, S3D_OK);
+  std::vector<std::string> errs(W);
+  std::atomic<int> next{0};
+  auto worker = [&](int w) {
+    st[w] = guarded([&]() -> int {
+      for (;;) {
+        const int b = next.fetch_add(1) * chunk;
+        if (b >= n) break;
+        prepare_chunk(ctx, device_slot, clouds + b, std::min(chunk, n - b), density, k, out + b);
+      }
+      return S3D_OK;
+    });
+    if (st[w] != S3D_OK) errs[w] = g_last_error;
+  };
+  if (W == 1 || n <= 2) worker(0);
+  else {
+    std::vector<std::thread> th;
+    for (int w = 0; w < W; ++w) th.emplace_back(worker, w);
+    for (auto& t : th) t.join();
+  }
+  for (int w = 0; w < W; ++w)
+    if (st[w] != S3D_OK) {
+      for (int i = 0; i < n; ++i) { s3d_release_cloud(ctx, out[i]); out[i] = nullptr; }
+      set_error(errs[w]);
+      return st[w];
+    }
+  return S3D_OK;
+}
+
+int s3d_prepare_cloud(s3d_context* ctx, int device_slot, s3d_cloud cloud, double density, int k, s3d_prepared_cloud** out) {
+  if (!out) return S3D_INVALID_ARGUMENT;
+  return s3d_prepare_clouds(ctx, device_slot, &cloud, 1, density, k, out);
 }
 
 int s3d_release_cloud(s3d_context* ctx, s3d_prepared_cloud* cloud) {

@@ -20,6 +20,7 @@
 // Roofline: per outer iteration 16 B (moving point) + 32 B (its normal) + gathered 16 B + 32 B (fixed point + normal) per
 // correspondence, + 48 B (M) written; per evaluation 16 + 16 + 48 B.  The working set is L2 resident; the search is latency
 // bound on the hash probes.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 
@@ -484,6 +485,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   // plus one per extra objective evaluation; PCL's loop is a do-while, so maximum_iterations <= 0 still runs one iteration.
   const bool trace = getenv("S3D_TRACE") != nullptr;
   const long max_rounds = (long)std::max(max_iter, 1) * 64 + 64;
+  auto t_round = std::chrono::steady_clock::now();
   for (long round = 0; round < max_rounds; ++round) {
     {
       StageTimer timer(ws, kStageIter);
@@ -504,6 +506,13 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
     ws.d2h += 16;
     if (trace) {
       S3D_CUDA(cudaMemcpy(hp, pairs, sizeof(PairState) * np, cudaMemcpyDeviceToHost));
+      int n_nn = 0, n_ev = 0, n_fin = 0;
+      for (uint32_t p = 0; p < np; ++p) { n_nn += hp[p].phase == kPhaseNeedNN; n_ev += hp[p].phase == kPhaseEval; n_fin += hp[p].phase == kPhaseFinished; }
+      const auto now = std::chrono::steady_clock::now();
+      fprintf(stderr, "[s3d trace] round=%ld dt=%.1f us  after round: need_nn=%d eval=%d finished=%d\n", round,
+              std::chrono::duration<double, std::micro>(now - t_round).count(), n_nn, n_ev, n_fin);
+      t_round = std::chrono::steady_clock::now();
+      if (np <= 4)
       for (uint32_t p = 0; p < np; ++p)
         fprintf(stderr, "[s3d trace] round=%ld pair=%u phase=%d outer=%d inner=%d ncorr=%u t=(%.9g %.9g %.9g) r10=%.9g r20=%.9g r21=%.9g\n", round, p,
                 hp[p].phase, hp[p].outer_iterations, hp[p].inner_iterations, hp[p].n_corr, hp[p].T[12], hp[p].T[13], hp[p].T[14], hp[p].T[1],

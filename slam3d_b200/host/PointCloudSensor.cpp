@@ -2,6 +2,7 @@
 // Reference behaviour cited per function (slam3d/sensor/pcl/PointCloudSensor.cpp).
 #include "PointCloudSensor.hpp"
 
+#include <list>
 #include <stdexcept>
 
 namespace slam3d_b200 {
@@ -19,6 +20,49 @@ s3d_context* defaultContext() {
   return ctx;
 }
 
+namespace {
+struct Prepared {
+  s3d_prepared_cloud* h = nullptr;
+  ~Prepared() { if (h) s3d_release_cloud(defaultContext(), h); }
+};
+struct CacheEntry { const PointCloud* key; std::weak_ptr<PointCloud> alive; double density; int k; std::shared_ptr<Prepared> prepared; };
+std::mutex g_cache_mutex;
+std::list<CacheEntry> g_cache;  // front = most recently used
+size_t g_cache_capacity = 32;
+size_t g_cache_hits = 0;
+}  // namespace
+
+void setPreparedCacheCapacity(size_t capacity) {
+  std::lock_guard<std::mutex> g(g_cache_mutex);
+  g_cache_capacity = capacity;
+  while (g_cache.size() > g_cache_capacity) g_cache.pop_back();
+}
+size_t preparedCacheHits() { std::lock_guard<std::mutex> g(g_cache_mutex); return g_cache_hits; }
+
+static s3d_cloud asCloud(const PointCloud::Ptr& c);
+
+// the prepared form of `cloud` for (density, k): from the cache, or built now and remembered
+static std::shared_ptr<Prepared> prepared(const PointCloud::Ptr& cloud, double density, int k) {
+  {
+    std::lock_guard<std::mutex> g(g_cache_mutex);
+    for (auto it = g_cache.begin(); it != g_cache.end();) {
+      if (it->alive.expired()) { it = g_cache.erase(it); continue; }  // the measurement is gone; its address may be reused
+      if (it->key == cloud.get() && it->density == density && it->k == k) {
+        ++g_cache_hits;
+        g_cache.splice(g_cache.begin(), g_cache, it);
+        return g_cache.front().prepared;
+      }
+      ++it;
+    }
+  }
+  std::shared_ptr<Prepared> p(new Prepared());
+  if (s3d_prepare_cloud(defaultContext(), 0, asCloud(cloud), density, k, &p->h) != S3D_OK) throw std::runtime_error(s3d_last_error());
+  std::lock_guard<std::mutex> g(g_cache_mutex);
+  g_cache.push_front({cloud.get(), cloud, density, k, p});
+  while (g_cache.size() > g_cache_capacity) g_cache.pop_back();
+  return p;
+}
+
 static s3d_cloud asCloud(const PointCloud::Ptr& c) {
   s3d_cloud o;
   o.xyzw = c && c->size() ? &c->points[0].x : nullptr;
@@ -31,7 +75,16 @@ Transform align(PointCloudMeasurement::Ptr source, PointCloudMeasurement::Ptr ta
                 const RegistrationParameters& config, s3d_result* result_info) {
   const s3d_registration_parameters c = config.toC();
   s3d_result res;
-  const int st = s3d_gicp_align(defaultContext(), asCloud(source->getPointCloud()), asCloud(target->getPointCloud()), guess.data(), &c, &res);
+  int st;
+  bool use_cache;
+  { std::lock_guard<std::mutex> g(g_cache_mutex); use_cache = g_cache_capacity > 0; }
+  if (use_cache && config.registration_algorithm == GICP && config.correspondence_randomness >= 1 && config.correspondence_randomness <= 32) {
+    std::shared_ptr<Prepared> ps = prepared(source->getPointCloud(), config.point_cloud_density, config.correspondence_randomness);
+    std::shared_ptr<Prepared> pt = prepared(target->getPointCloud(), config.point_cloud_density, config.correspondence_randomness);
+    st = s3d_gicp_align_prepared(defaultContext(), ps->h, pt->h, guess.data(), &c, &res);
+  } else {
+    st = s3d_gicp_align(defaultContext(), asCloud(source->getPointCloud()), asCloud(target->getPointCloud()), guess.data(), &c, &res);
+  }
   if (result_info) *result_info = res;
   switch (st) {
     case S3D_OK: break;

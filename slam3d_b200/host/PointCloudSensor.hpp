@@ -22,6 +22,13 @@ namespace slam3d_b200 {
 // Process-wide C-ABI context (created on first use; re-entrant, see s3d_b200.h).
 s3d_context* defaultContext();
 
+// Per-measurement device cache.  The reference rebuilds filter, trees and covariances in every align();
+// here a scan that is matched again (target then source in odometry, repeated loop-closure candidate) is preprocessed once.
+// Keyed by the cloud object (slam3d measurements are immutable once stored, MeasurementStorage.cpp:13-21), the density and k;
+// least-recently-used entries are dropped beyond `capacity`.  capacity 0 disables the cache (every align() runs the raw path).
+void setPreparedCacheCapacity(size_t capacity);
+size_t preparedCacheHits();
+
 // align(source, target, guess, config) — PointCloudSensor.cpp:119-174.  Throws NoMatch / std::runtime_error exactly
 // where the reference does.  `result_info` (optional) receives the C-ABI result (fitness, iterations...).
 Transform align(PointCloudMeasurement::Ptr source, PointCloudMeasurement::Ptr target, const Transform& guess,

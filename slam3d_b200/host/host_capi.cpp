@@ -32,6 +32,8 @@ struct OtherMeasurement : Measurement {
 extern "C" {
 
 const char* s3dhost_last_message() { return g_msg.c_str(); }
+void s3dhost_set_cache_capacity(uint64_t n) { setPreparedCacheCapacity((size_t)n); }
+uint64_t s3dhost_cache_hits() { return (uint64_t)preparedCacheHits(); }
 
 void* s3dhost_sensor_create(const char* name) { return new PointCloudSensor(name, nullptr); }
 void s3dhost_sensor_destroy(void* s) { delete static_cast<PointCloudSensor*>(s); }

@@ -129,3 +129,16 @@ def map_cloud(seed=20260117, n_scans=16, path_len=12.0):
         p = scan(scene, pose, rng).astype(np.float64)
         out.append((p @ pose[:3, :3].T + pose[:3, 3]).astype(np.float32))
     return np.concatenate(out, 0)
+
+
+def trajectory(seed=20260117, n_scans=9):
+    """n_scans consecutive scans of one scene along an odometry path; returns (scans, poses) with poses[i] = scan i in the world."""
+    rng = np.random.default_rng(seed)
+    scene = Scene(seed)
+    pose = np.eye(4)
+    scans, poses = [], []
+    for i in range(n_scans):
+        scans.append(scan(scene, pose, rng))
+        poses.append(pose.copy())
+        pose = pose @ odometry_motion(rng)
+    return scans, poses

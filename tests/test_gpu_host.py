@@ -29,6 +29,8 @@ def host():
                                               C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.s3dhost_downsample.restype = C.c_int64
     lib.s3dhost_downsample.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_void_p]
+    lib.s3dhost_set_cache_capacity.argtypes = [C.c_uint64]
+    lib.s3dhost_cache_hits.restype = C.c_uint64
     lib.s3dhost_run_odometry.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
     return lib
 
@@ -129,9 +131,17 @@ def test_minihost_odometry_and_two_threads(host, oracle_mod, kitti):
         o = np.eye(4); o[0, 3] = 0.65 * i
         odoms[i] = o.T  # column-major
     out = np.zeros((3, 16)); nw = C.c_int(0)
+    host.s3dhost_set_cache_capacity(0)                  # raw path: every align() preprocesses both clouds
+    n0 = host.s3dhost_run_odometry(sensor, ptrs, sizes, 4, odoms.ctypes.data, 1, out.ctypes.data, C.byref(nw))
+    assert n0 == 3 and nw.value == 0
+    uncached = out.copy()
+    host.s3dhost_set_cache_capacity(32)                 # device cache: scans 2 and 3 are preprocessed once, used twice
+    hits0 = host.s3dhost_cache_hits()
     n1 = host.s3dhost_run_odometry(sensor, ptrs, sizes, 4, odoms.ctypes.data, 1, out.ctypes.data, C.byref(nw))
     assert n1 == 3 and nw.value == 0
+    assert host.s3dhost_cache_hits() - hits0 == 2
     single = out.copy()
+    assert np.array_equal(single, uncached)             # the cache never changes a result
     n2 = host.s3dhost_run_odometry(sensor, ptrs, sizes, 4, odoms.ctypes.data, 2, out.ctypes.data, C.byref(nw))
     assert n2 == 3                      # two concurrent threads: identical edges in both (checked inside) ...
     assert np.array_equal(out, single)  # ... and identical to the single-threaded run

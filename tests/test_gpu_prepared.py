@@ -26,7 +26,7 @@ def same(a, b):
 
 def test_odometry_chain_bit_identical_to_raw(ctx, kitti):
     p = RegistrationParameters.defaults(point_cloud_density=0.2)
-    prepared = [ctx.prepare_cloud(k, 0.2, 20) for k in kitti]          # every scan preprocessed once ...
+    prepared = ctx.prepare_clouds(kitti, 0.2, 20)                      # every scan preprocessed once (one batched pass) ...
     assert [h.size for h in prepared] == [31834, 31481, 30882, 30435]  # SURVEY Appendix B voxel counts
     chain = ctx.gicp_align_prepared_batch(prepared[:-1], prepared[1:], None, p)   # ... and used as target and as source
     for i in range(3):
