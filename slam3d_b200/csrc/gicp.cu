@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(kIterTile) gicp_iter_kernel(const SlotInfo* __
   }
 }
 
-// One objective evaluation at the trial state of every pair in kPhaseEval: the 13 residual sums per 256-point tile.
+// Objective evaluations at the pending back-tracking trials of every pair in kPhaseEval: 13 residual sums per trial and
+// 256-point tile, residual formed exactly as PCL forms it.
 __global__ void __launch_bounds__(kIterTile) gicp_eval_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
                                                               const float4* __restrict__ moved,
                                                               const uint32_t* __restrict__ corr, const double* __restrict__ mahal,
@@ -217,14 +218,25 @@ __global__ void __launch_bounds__(kIterTile) gicp_eval_kernel(const SlotInfo* __
   const uint32_t first = blockIdx.x * kIterTile;
   if (first >= sa.n_pts) return;
   const uint32_t r = first + threadIdx.x;
-  double f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool valid = false;
+  float4 mv = make_float4(0.f, 0.f, 0.f, 0.f), qb = mv;
+  double M[6] = {0, 0, 0, 0, 0, 0};
   if (r < sa.n_pts) {
     const uint32_t c = corr[ps.pt_off + r];
     if (c != kNoIndex) {
-      const float4 mv = moved[ps.pt_off + r];
-      const float4 qb = sb.gpts[c];
-      const double* M = mahal + 6 * (size_t)(ps.pt_off + r);
-      const float3 pp = transform_mv(ps.T_eval, mv.x, mv.y, mv.z);
+      valid = true;
+      mv = moved[ps.pt_off + r];
+      qb = sb.gpts[c];
+      const double* Mp = mahal + 6 * (size_t)(ps.pt_off + r);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) M[i] = Mp[i];
+    }
+  }
+  const size_t tile = (size_t)p * gridDim.x + blockIdx.x;
+  for (int j = ps.trial_first; j < ps.trial_first + ps.trial_count; ++j) {
+    double f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (valid) {
+      const float3 pp = transform_mv(ps.T_trial[j], mv.x, mv.y, mv.z);
       const double d0 = (double)__fsub_rn(pp.x, qb.x), d1 = (double)__fsub_rn(pp.y, qb.y), d2 = (double)__fsub_rn(pp.z, qb.z);
       const double Md0 = M[0] * d0 + M[1] * d1 + M[2] * d2;
       const double Md1 = M[1] * d0 + M[3] * d1 + M[4] * d2;
@@ -232,25 +244,24 @@ __global__ void __launch_bounds__(kIterTile) gicp_eval_kernel(const SlotInfo* __
       f[0] = mv.x; f[1] = mv.y; f[2] = mv.z; f[3] = Md0; f[4] = Md1; f[5] = Md2;
       f[6] = d0 * Md0 + d1 * Md1 + d2 * Md2; f[7] = 1.0;
     }
-  }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) feat[threadIdx.x][i] = f[i];
-  __syncthreads();
-  // sum s (0..11: (Md)_a * phi_c with a = s / 4, c = s % 4; 12: d^T M d) over 16 sub-ranges of 16 points, ascending order
-  if (threadIdx.x < 16 * kEvalSums) {
-    const int sidx = threadIdx.x % kEvalSums, sub = threadIdx.x / kEvalSums;
-    const int ia = sidx < 12 ? 3 + sidx / 4 : 6;
-    const int ib = sidx < 12 ? (sidx % 4 < 3 ? sidx % 4 : 7) : 7;
-    double acc = 0.0;
-    for (int i = sub * 16; i < sub * 16 + 16; ++i) acc += feat[i][ia] * feat[i][ib];
-    part[sub][sidx] = acc;
-  }
-  __syncthreads();
-  if (threadIdx.x < kEvalSums) {
-    double acc = 0.0;
-    for (int sub = 0; sub < 16; ++sub) acc += part[sub][threadIdx.x];
-    const size_t tile = (size_t)p * gridDim.x + blockIdx.x;
-    eval_part[tile * kEvalSums + threadIdx.x] = acc;
+    for (int i = 0; i < 8; ++i) feat[threadIdx.x][i] = f[i];
+    __syncthreads();
+    // sum s (0..11: (Md)_a * phi_c with a = s / 4, c = s % 4; 12: d^T M d) over 16 sub-ranges of 16 points, ascending order
+    if (threadIdx.x < 16 * kEvalSums) {
+      const int sidx = threadIdx.x % kEvalSums, sub = threadIdx.x / kEvalSums;
+      const int ia = sidx < 12 ? 3 + sidx / 4 : 6;
+      const int ib = sidx < 12 ? (sidx % 4 < 3 ? sidx % 4 : 7) : 7;
+      double acc = 0.0;
+      for (int i = sub * 16; i < sub * 16 + 16; ++i) acc += feat[i][ia] * feat[i][ib];
+      part[sub][sidx] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < kEvalSums) {
+      double acc = 0.0;
+      for (int sub = 0; sub < 16; ++sub) acc += part[sub][threadIdx.x];
+      eval_part[(tile * kLineSearchTrials + j) * kEvalSums + threadIdx.x] = acc;
+    }
   }
 }
 
@@ -287,22 +298,29 @@ __device__ void finish_outer(PairState& ps, bool optimiser_failed, int32_t* flag
   }
 }
 
-// one CTA per pair: ordered reduction of the tile partials of the pass that just ran, then one thread advances the optimiser
+// one CTA per pair: ordered reduction of the tile partials of the pass that just ran, then the optimiser advances
 __global__ void __launch_bounds__(256) gicp_ctrl_kernel(const SlotInfo* __restrict__ slots, PairState* __restrict__ pairs,
                                                         const double* __restrict__ moments, const double* __restrict__ eval_part,
                                                         uint32_t tiles_per_pair, int after_eval, int32_t* __restrict__ flags) {
-  __shared__ double part[3][kNumMoments];
+  __shared__ double part[3][kLineSearchTrials * kEvalSums];
+  __shared__ double red[kLineSearchTrials * kEvalSums];
+  __shared__ Euler E;
+  __shared__ double gH[42];
+  __shared__ int mode;      // 0: nothing to assemble, 1: assemble the objective at ps.nst.xc from ps.sums
+  __shared__ int newstep;   // a new Newton step started: its trial matrices are needed
   const uint32_t p = blockIdx.x;
   PairState& ps = pairs[p];
-  // the first ctrl launch of a round serves pairs that just searched, the second one pairs that were just evaluated
+  // the first ctrl launch of a round serves pairs that just searched, the later ones pairs that were just evaluated
   if (ps.phase != (after_eval ? kPhaseEval : kPhaseNeedNN)) return;
   const uint32_t n_tiles = (slots[2 * p + 1].n_pts + kIterTile - 1) / kIterTile;
-  const int n_sums = after_eval ? kEvalSums : kNumMoments;
-  const int stride = n_sums;
-  const double* src0 = after_eval ? eval_part + (size_t)p * tiles_per_pair * kEvalSums : moments + (size_t)p * tiles_per_pair * kNumMoments;
-  if ((int)threadIdx.x < 3 * n_sums) {
+  const int n_sums = after_eval ? ps.trial_count * kEvalSums : kNumMoments;
+  const int stride = after_eval ? kLineSearchTrials * kEvalSums : kNumMoments;
+  const double* src0 = after_eval ? eval_part + (size_t)p * tiles_per_pair * stride + ps.trial_first * kEvalSums
+                                  : moments + (size_t)p * tiles_per_pair * stride;
+  const int subs = n_sums * 3 <= 256 ? 3 : (n_sums * 2 <= 256 ? 2 : 1);
+  if ((int)threadIdx.x < subs * n_sums) {
     const int m = threadIdx.x % n_sums, sub = threadIdx.x / n_sums;
-    const uint32_t per = (n_tiles + 2) / 3;
+    const uint32_t per = (n_tiles + subs - 1) / subs;
     const uint32_t lo = sub * per, hi = min(n_tiles, lo + per);
     const double* src = src0 + m;
     double s = 0.0;
@@ -311,33 +329,58 @@ __global__ void __launch_bounds__(256) gicp_ctrl_kernel(const SlotInfo* __restri
     part[sub][m] = s;
   }
   __syncthreads();
-  if ((int)threadIdx.x < n_sums) ps.sums[(after_eval ? 60 : 0) + threadIdx.x] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x];
-  __syncthreads();
-  // objective at the evaluated state: one thread builds the Euler derivative tensors, 42 threads contract one entry each
-  __shared__ Euler E;
-  __shared__ double gH[42];
-  __shared__ int go;
-  if (threadIdx.x == 0) {
-    go = 1;
-    if (!after_eval) {
-      ps.n_corr = (uint32_t)ps.sums[73];
-      for (int i = 0; i < 16; ++i) { ps.prev[i] = ps.T[i]; ps.T_search[i] = ps.T[i]; }  // previous_transformation_ = transformation_
-      if (ps.sums[73] < 4.0) { finish_outer(ps, true, flags); go = 0; }  // min_number_correspondences_: PCL throws
-    }
-    if (go) euler_derivs(ps.nst.xc, E, true);
+  if ((int)threadIdx.x < n_sums) {
+    double s = part[0][threadIdx.x];
+    for (int sub = 1; sub < subs; ++sub) s += part[sub][threadIdx.x];
+    red[threadIdx.x] = s;
   }
   __syncthreads();
-  if (!go) return;
+  if (threadIdx.x == 0) {
+    mode = 1; newstep = 0;
+    if (!after_eval) {
+      for (int i = 0; i < kNumMoments; ++i) ps.sums[i] = red[i];
+      ps.n_corr = (uint32_t)ps.sums[73];
+      for (int i = 0; i < 16; ++i) { ps.prev[i] = ps.T[i]; ps.T_search[i] = ps.T[i]; }  // previous_transformation_ = transformation_
+      if (ps.sums[73] < 4.0) { finish_outer(ps, true, flags); mode = 0; }  // min_number_correspondences_: PCL throws
+    } else {
+      double f_trial[kLineSearchTrials];
+      for (int j = 0; j < ps.trial_count; ++j) f_trial[ps.trial_first + j] = red[j * kEvalSums + 12] / ps.sums[73];
+      const int j = newton_pick_trial(ps.nst, f_trial, ps.trial_first, ps.trial_count);
+      if (j >= 0) {
+        newton_select_trial(ps.nst, j);
+        for (int i = 0; i < kEvalSums; ++i) ps.sums[60 + i] = red[(j - ps.trial_first) * kEvalSums + i];
+      } else if (ps.trial_first == 0 && kLineSearchTrials > 1) {
+        ps.trial_first = 1; ps.trial_count = kLineSearchTrials - 1;  // trial 0 did not improve: evaluate all remaining trials in one pass
+        mode = 0;
+      } else {
+        ps.nst.phase = 2;  // no improvement found
+        finish_outer(ps, false, flags);
+        mode = 0;
+      }
+    }
+    if (mode) euler_derivs(ps.nst.xc, E, true);
+  }
+  __syncthreads();
+  if (!mode) return;
+  // objective at the evaluated state: 42 threads contract one gradient / Hessian entry each
   if (threadIdx.x < 42) gH[threadIdx.x] = objective_entry(ps.sums, E, threadIdx.x);
   __syncthreads();
-  if (threadIdx.x != 0) return;
-  double g[6], H[6][6];
-  for (int i = 0; i < 6; ++i) { g[i] = gH[i]; for (int j = 0; j < 6; ++j) H[i][j] = gH[6 + 6 * i + j]; }
-  if (newton_advance_pre(ps.nst, ps.sums[72] / ps.sums[73], g, H, ps.max_inner)) {
-    matrix_from_state(ps.nst.xc, ps.T_eval);
-    ps.phase = kPhaseEval;
-  } else {
-    finish_outer(ps, false, flags);
+  if (threadIdx.x == 0) {
+    double g[6], H[6][6];
+    for (int i = 0; i < 6; ++i) { g[i] = gH[i]; for (int j = 0; j < 6; ++j) H[i][j] = gH[6 + 6 * i + j]; }
+    if (newton_advance_pre(ps.nst, ps.sums[72] / ps.sums[73], g, H, ps.max_inner)) {
+      ps.trial_first = 0; ps.trial_count = 1;
+      ps.phase = kPhaseEval;
+      newstep = 1;
+    } else {
+      finish_outer(ps, false, flags);
+    }
+  }
+  __syncthreads();
+  if (newstep && threadIdx.x < kLineSearchTrials) {  // float matrices of all back-tracking trials of the new step
+    double xc[6];
+    newton_trial_state(ps.nst, threadIdx.x, xc);
+    matrix_from_state(xc, ps.T_trial[threadIdx.x]);
   }
 }
 
@@ -452,7 +495,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   ws.prev_nn.reserve(4 * std::max<size_t>(ws.total, 4));
   ws.sec_lb.reserve(4 * std::max<size_t>(ws.total, 4));
   ws.moments.reserve(sizeof(double) * kNumMoments * size_t(tiles_per_pair) * np);
-  ws.eval_part.reserve(sizeof(double) * kEvalSums * size_t(tiles_per_pair) * np);
+  ws.eval_part.reserve(sizeof(double) * kEvalSums * kLineSearchTrials * size_t(tiles_per_pair) * np);
   ws.corr.reserve(4 * std::max<size_t>(ws.total, 4));
   ws.mahal.reserve(48 * std::max<size_t>(ws.total, 4));
   ws.fit_partial.reserve(sizeof(double) * 2 * size_t(tiles_per_pair) * np);
@@ -496,10 +539,13 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
     {
       StageTimer timer(ws, kStageSolve);
       gicp_ctrl_kernel<<<np, 256, 0, st>>>(slots, pairs, ws.moments.as<double>(), ws.eval_part.as<double>(), tiles_per_pair, 0, flags);
-      gicp_eval_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.moved.as<float4>(), ws.corr.as<uint32_t>(),
-                                                   ws.mahal.as<double>(), ws.eval_part.as<double>());
-      gicp_ctrl_kernel<<<np, 256, 0, st>>>(slots, pairs, ws.moments.as<double>(), ws.eval_part.as<double>(), tiles_per_pair, 1, flags);
-      ws.launches += 3;
+      ++ws.launches;
+      for (int e = 0; e < 2; ++e) {  // two evaluate/advance passes per round: most outer iterations finish without another host poll
+        gicp_eval_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.moved.as<float4>(), ws.corr.as<uint32_t>(),
+                                                     ws.mahal.as<double>(), ws.eval_part.as<double>());
+        gicp_ctrl_kernel<<<np, 256, 0, st>>>(slots, pairs, ws.moments.as<double>(), ws.eval_part.as<double>(), tiles_per_pair, 1, flags);
+        ws.launches += 2;
+      }
     }
     S3D_CUDA(cudaMemcpyAsync(h_flags, flags, 16, cudaMemcpyDeviceToHost, st));
     S3D_CUDA(cudaStreamSynchronize(st));

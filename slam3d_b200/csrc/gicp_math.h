@@ -254,6 +254,33 @@ S3D_HD bool newton_advance_pre(NewtonState& st, double f, const double (&g)[6], 
   return false;
 }
 
+// ---- speculative back-tracking -------------------------------------------------------------------------------------
+// PCL tries alpha = 1, 1/2, ..., 2^-9 one objective evaluation at a time.  On the GPU an evaluation is a data pass and
+// a host poll, and the tail of the trials only runs in the float-rounding dominated regime near convergence, so trial 0
+// is evaluated alone and, if it fails, trials 1..9 together in ONE pass; the first improving trial is then selected,
+// which is exactly what the sequential loop would have accepted.
+constexpr int kLineSearchTrials = 10;
+
+S3D_HD void newton_trial_state(const NewtonState& st, int j, double xc[6]) {
+  double alpha = 1.0;
+  for (int i = 0; i < j; ++i) alpha /= 2;  // same halving sequence as the sequential loop (exact in binary)
+  for (int r = 0; r < 6; ++r) xc[r] = st.x[r] - alpha * st.delta[r];
+}
+
+// f_trial[j] = f at trial j for j in [first, first + count).  Returns the accepted trial or -1.
+S3D_HD int newton_pick_trial(const NewtonState& st, const double* f_trial, int first, int count) {
+  for (int j = first; j < first + count; ++j) if (f_trial[j] < st.fcur) return j;
+  return -1;
+}
+
+// Makes trial j the pending state, as if the sequential loop had just evaluated it.
+S3D_HD void newton_select_trial(NewtonState& st, int j) {
+  st.alpha = 1.0;
+  for (int i = 0; i < j; ++i) st.alpha /= 2;
+  st.ls = j;
+  for (int r = 0; r < 6; ++r) st.xc[r] = st.x[r] - st.alpha * st.delta[r];
+}
+
 // `sums` = evaluation at st.xc (host-side convenience: computes the objective, then advances)
 S3D_HD bool newton_advance(NewtonState& st, const double* sums, int max_inner) {
   double f, g[6], H[6][6];

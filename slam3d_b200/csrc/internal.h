@@ -69,7 +69,9 @@ struct PairState {
   uint32_t fit_n;
   int32_t max_iter, max_inner, k;
   NewtonState nst;         // resumable inner optimiser (gicp_math.h)
-  float  T_eval[16];       // float matrix of the state whose objective evaluation is pending (PCL applyState)
+  float  T_eval[16];       // float matrix of the outer iteration's start state x0 (PCL applyState), evaluated by the search pass
+  float  T_trial[kLineSearchTrials][16];  // float matrices of the back-tracking trials x - 2^-j delta of the current Newton step
+  int32_t trial_first, trial_count;       // trials the next evaluation pass has to cover (0,1 first; 1,9 if trial 0 failed)
   double sums[kNumMoments];// reduced sums of the current correspondence set (static part) + last evaluation (residual part)
   int32_t phase;           // kPhaseNeedNN / kPhaseEval / kPhaseFinished
   int32_t active;          // 1 while the outer loop runs
@@ -131,7 +133,7 @@ struct Workspace {
 
 enum ErrorBits { kErrHashArena = 1 };
 enum PairPhase { kPhaseNeedNN = 0, kPhaseEval = 1, kPhaseFinished = 2 };
-constexpr int kEvalSums = 13;  // sums 60..72 of gicp_math.h: the residual-dependent part of an evaluation
+constexpr int kEvalSums = 13;  // sums 60..72 of gicp_math.h: the residual-dependent part of an evaluation (per trial)
 enum Stage { kStageVoxel = 0, kStageGrid = 1, kStageKnn = 2, kStageIter = 3, kStageSolve = 4, kStageFitness = 5 };
 
 // RAII: brackets the kernels launched in its scope with two events when profiling is on

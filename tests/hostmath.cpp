@@ -42,18 +42,34 @@ void hm_objective(const float* moved, const float* fixed, const double* M6, int 
   s3d::objective_from_sums(sums, x, *f, gg, HH);
   for (int i = 0; i < 6; ++i) { g[i] = gg[i]; for (int j = 0; j < 6; ++j) H[j * 6 + i] = HH[i][j]; }
 }
-// estimateRigidTransformationNewton through the resumable state machine; T column-major float in/out
+// estimateRigidTransformationNewton through the resumable state machine with the speculative back-tracking of
+// gicp_ctrl_kernel (trial 0 alone, then trials 1..9 in one go); T column-major float in/out
 int hm_newton(const float* moved, const float* fixed, const double* M6, int m, float* T, int max_inner, int* inner_done, int* evaluations) {
   if (m < 4) return 2;
   s3d::NewtonState st;
   s3d::newton_begin(st, T);
-  double sums[s3d::kNumMoments];
-  int evals = 0;
-  bool more = true;
+  double sums[s3d::kNumMoments], trial_sums[s3d::kLineSearchTrials][s3d::kNumMoments];
+  int evals = 1;
+  evaluate(moved, fixed, M6, m, st.xc, sums);
+  bool more = s3d::newton_advance(st, sums, max_inner);  // objective at x0, first step
   while (more) {
-    evaluate(moved, fixed, M6, m, st.xc, sums);
-    ++evals;
-    more = s3d::newton_advance(st, sums, max_inner);
+    int first = 0, count = 1, j = -1;
+    for (;;) {
+      double f_trial[s3d::kLineSearchTrials];
+      for (int t = first; t < first + count; ++t) {
+        double xc[6];
+        s3d::newton_trial_state(st, t, xc);
+        evaluate(moved, fixed, M6, m, xc, trial_sums[t]);
+        f_trial[t] = trial_sums[t][72] / trial_sums[t][73];
+      }
+      ++evals;
+      j = s3d::newton_pick_trial(st, f_trial, first, count);
+      if (j >= 0 || first != 0) break;
+      first = 1; count = s3d::kLineSearchTrials - 1;
+    }
+    if (j < 0) { st.phase = 2; break; }  // no improvement
+    s3d::newton_select_trial(st, j);
+    more = s3d::newton_advance(st, trial_sums[j], max_inner);
   }
   s3d::matrix_from_state(st.x, T);
   *inner_done = st.it;
