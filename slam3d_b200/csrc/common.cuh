@@ -111,6 +111,17 @@ __device__ __forceinline__ uint32_t hash_slot(uint32_t key, uint32_t level, uint
   return __umulhi(h, cap);  // uniform in [0, cap)
 }
 
+// cell with Morton key `key` at `level` (the caller has checked that it lies inside the grid); false when empty
+__device__ __forceinline__ bool cell_range_key(const HashEntry* __restrict__ table, uint32_t cap, uint32_t key, int level, uint32_t& begin, uint32_t& end) {
+  uint32_t s = hash_slot(key, (uint32_t)level, cap);
+  for (;;) {
+    const uint4 e = __ldg(reinterpret_cast<const uint4*>(table + s));
+    if (e.y == 0xFFFFFFFFu) return false;
+    if (e.x == key && e.y == (uint32_t)level) { begin = e.z; end = e.w; return true; }
+    if (++s == cap) s = 0;
+  }
+}
+
 // cell (cx,cy,cz) at `level`; returns false when the cell is empty or outside the grid
 __device__ __forceinline__ bool cell_range(const HashEntry* __restrict__ table, uint32_t cap, int nlev, int level,
                                            int cx, int cy, int cz, uint32_t& begin, uint32_t& end) {

@@ -73,6 +73,18 @@ __device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int
                                            float qx, float qy, float qz, NNResult& best) {
   const int dim = 1 << (g.nlev - L);
   const float hl = g.h0 * (float)(1 << L) * 0.9999f;
+  // Morton bits of the three cell coordinates per axis, spread once per block instead of once per cell
+  const uint32_t sx0 = spread3((uint32_t)(cx - 1)), sx1 = spread3((uint32_t)cx), sx2 = spread3((uint32_t)(cx + 1));
+  const uint32_t sy0 = spread3((uint32_t)(cy - 1)) << 1, sy1 = spread3((uint32_t)cy) << 1, sy2 = spread3((uint32_t)(cy + 1)) << 1;
+  const uint32_t sz0 = spread3((uint32_t)(cz - 1)) << 2, sz1 = spread3((uint32_t)cz) << 2, sz2 = spread3((uint32_t)(cz + 1)) << 2;
+  // squared axis gaps to the lower neighbour / upper neighbour cell (0 for the own cell), shrunk by the float slack
+  float glx = 0.f, gux = 0.f, gly = 0.f, guy = 0.f, glz = 0.f, guz = 0.f;
+  if (prune) {
+    const float a0 = fmaxf(ax * hl - g.margin, 0.f), a1 = fmaxf((1.f - ax) * hl - g.margin, 0.f);
+    const float b0 = fmaxf(ay * hl - g.margin, 0.f), b1 = fmaxf((1.f - ay) * hl - g.margin, 0.f);
+    const float c0 = fmaxf(az * hl - g.margin, 0.f), c1 = fmaxf((1.f - az) * hl - g.margin, 0.f);
+    glx = a0 * a0; gux = a1 * a1; gly = b0 * b0; guy = b1 * b1; glz = c0 * c0; guz = c1 * c1;
+  }
 #pragma unroll 1
   for (int i = 0; i < 27; ++i) {
     const int c = cell_order(i);
@@ -80,13 +92,12 @@ __device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int
     const int ix = cx + dx - 1, iy = cy + dy - 1, iz = cz + dz - 1;
     if ((unsigned)ix >= (unsigned)dim || (unsigned)iy >= (unsigned)dim || (unsigned)iz >= (unsigned)dim) continue;
     if (prune) {
-      const float fx = dx == 0 ? ax : (dx == 1 ? 0.f : 1.f - ax), fy = dy == 0 ? ay : (dy == 1 ? 0.f : 1.f - ay), fz = dz == 0 ? az : (dz == 1 ? 0.f : 1.f - az);
-      const float rx = fmaxf(fx * hl - g.margin, 0.f), ry = fmaxf(fy * hl - g.margin, 0.f), rz = fmaxf(fz * hl - g.margin, 0.f);
-      const float cell_lb = (rx * rx + ry * ry + rz * rz) * 0.99999f;
+      const float cell_lb = ((dx == 0 ? glx : (dx == 1 ? 0.f : gux)) + (dy == 0 ? gly : (dy == 1 ? 0.f : guy)) + (dz == 0 ? glz : (dz == 1 ? 0.f : guz))) * 0.99999f;
       if (cell_lb > best.d2) { best.lb2 = fminf(best.lb2, cell_lb); continue; }
     }
+    const uint32_t key = (dx == 0 ? sx0 : (dx == 1 ? sx1 : sx2)) | (dy == 0 ? sy0 : (dy == 1 ? sy1 : sy2)) | (dz == 0 ? sz0 : (dz == 1 ? sz1 : sz2));
     uint32_t begin, end;
-    if (!cell_range(g.table, g.cap, g.nlev, L, ix, iy, iz, begin, end)) continue;
+    if (!cell_range_key(g.table, g.cap, key, L, begin, end)) continue;
     for (uint32_t p = begin; p < end; ++p) {
       const float4 v = __ldg(g.pts + p);
       const float d2 = dist2_pcl(qx, qy, qz, v.x, v.y, v.z);
