@@ -99,6 +99,8 @@ struct Workspace {
   DevBuf work, gpts;                          // float4[total]
   DevBuf keys0, keys1, vals0, vals1;          // uint32[total]
   DevBuf hist;                                // uint32[n_tiles*256]
+  DevBuf sort_totals;                         // uint32[4 passes * n_slots * 256]
+  DevBuf long_runs;                           // uint4[total/64]  voxels with more than 64 points: (slot, first sorted position, output rank)
   DevBuf tile_slot, tile_first, slot_tile_begin, tile_heads;
   DevBuf hash;                                // HashEntry[hash_cap]
   size_t hash_cap = 0;

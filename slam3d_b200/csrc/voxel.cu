@@ -46,7 +46,7 @@ void Workspace::destroy() {
   collect_spans();
   for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
   event_pool.clear();
-  DevBuf* bufs[] = {&slots, &pairs, &raw_stage, &work, &gpts, &keys0, &keys1, &vals0, &vals1, &hist, &tile_slot, &tile_first,
+  DevBuf* bufs[] = {&slots, &pairs, &raw_stage, &work, &gpts, &keys0, &keys1, &vals0, &vals1, &hist, &sort_totals, &long_runs, &tile_slot, &tile_first,
                     &slot_tile_begin, &tile_heads, &hash, &normals, &moved, &prev_nn, &sec_lb, &moments, &eval_part, &corr, &mahal, &iter_tile_pair, &iter_tile_first,
                     &fit_partial, &flags};
   for (DevBuf* b : bufs) b->release();
@@ -87,6 +87,8 @@ void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const s
   for (uint32_t p = 0; p < n_pairs; ++p) { ws.pair_off[p] = ws.h_off[2 * p + 1]; ws.max_na = std::max(ws.max_na, ws.h_n[2 * p + 1]); }
   ws.keys0.reserve(4 * tot); ws.keys1.reserve(4 * tot); ws.vals0.reserve(4 * tot); ws.vals1.reserve(4 * tot);
   ws.hist.reserve(sizeof(uint32_t) * 256 * std::max<uint32_t>(n_tiles, 1));
+  ws.sort_totals.reserve(sizeof(uint32_t) * 256 * 4 * std::max<uint32_t>(ns, 1));
+  ws.long_runs.reserve(sizeof(uint4) * (tot / 64 + ns + 1));
   ws.tile_slot.reserve(4 * std::max<uint32_t>(n_tiles, 1)); ws.tile_first.reserve(4 * std::max<uint32_t>(n_tiles, 1));
   ws.tile_heads.reserve(4 * std::max<uint32_t>(n_tiles, 1));
   ws.slot_tile_begin.reserve(4 * (ns + 1));
@@ -171,12 +173,24 @@ __global__ void __launch_bounds__(kSortThreads) bbox_kernel(SlotInfo* __restrict
     }
     cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
   }
-  if ((threadIdx.x & 31) == 0 && cnt) {
-    uint32_t* dmin = reinterpret_cast<uint32_t*>(which == kCountRaw ? si.bb_min : si.g_min);
-    uint32_t* dmax = reinterpret_cast<uint32_t*>(which == kCountRaw ? si.bb_max : si.g_max);
+  // one set of atomics per CTA (8192 warps hammering 7 addresses cost 40 us on a 2M-point cloud)
+  __shared__ float smn[8][3], smx[8][3];
+  __shared__ uint32_t scnt[8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { for (int a = 0; a < 3; ++a) { smn[w][a] = mn[a]; smx[w][a] = mx[a]; } scnt[w] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) {
+      for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], smn[i][a]); mx[a] = fmaxf(mx[a], smx[i][a]); }
+      cnt += scnt[i];
+    }
+    if (cnt) {
+      uint32_t* dmin = reinterpret_cast<uint32_t*>(which == kCountRaw ? si.bb_min : si.g_min);
+      uint32_t* dmax = reinterpret_cast<uint32_t*>(which == kCountRaw ? si.bb_max : si.g_max);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { atomicMin(&dmin[a], float_to_ordered(mn[a])); atomicMax(&dmax[a], float_to_ordered(mx[a])); }
-    if (which == kCountRaw) atomicAdd(&si.n_finite, cnt);
+      for (int a = 0; a < 3; ++a) { atomicMin(&dmin[a], float_to_ordered(mn[a])); atomicMax(&dmax[a], float_to_ordered(mx[a])); }
+      if (which == kCountRaw) atomicAdd(&si.n_finite, cnt);
+    }
   }
 }
 
@@ -279,10 +293,34 @@ __global__ void voxel_scan_kernel(SlotInfo* __restrict__ slots, uint32_t n_slots
   if (lane == 0) si.n_pts = running;
 }
 
-// A.1 steps 8-9: float centroid per run, in ascending input order, written in ascending key order.
+// A.1 steps 8-9: float centroid per run (voxel), summed in ascending input order — (((p0 + p1) + p2) + ...) exactly as
+// PCL's CentroidPoint — and written in ascending key order.  Two kernels:
+//   voxel_centroid_kernel       one thread per run; right for scan-sized clouds (2-3 points per voxel).  Runs longer than
+//                               kLongRun are only queued: with dependent index->point loads a thread needs ~0.4 us per point,
+//                               and map-sized clouds have voxels with thousands of points (1.16 ms on 2M points, 0.2 m leaf);
+//   voxel_long_centroid_kernel  one warp per queued run: 32 lanes fetch 32 points at once, then the warp consumes them in
+//                               order through shuffles, so the additions stay strictly sequential but never wait for loads.
+constexpr uint32_t kLongRun = 64;
+
+// sorted[e] = raw[vals[e]]: the points in voxel-key order, so that the centroid kernels stream them instead of chasing
+// index -> point through two dependent loads per addition
+__global__ void __launch_bounds__(kSortThreads) voxel_gather_kernel(const SlotInfo* __restrict__ slots, TileMap tm, const uint32_t* __restrict__ vals,
+                                                                     float4* __restrict__ sorted) {
+  const uint32_t t = blockIdx.x;
+  const uint32_t slot = tm.tile_slot[t], first = tm.tile_first[t];
+  const SlotInfo& si = slots[slot];
+  if (si.overflow) return;
+#pragma unroll
+  for (int j = 0; j < kSortTile / kSortThreads; ++j) {
+    const uint32_t e = first + j * kSortThreads + threadIdx.x;
+    if (e < si.n_finite) sorted[si.off + e] = si.raw[vals[si.off + e]];
+  }
+}
+
 __global__ void __launch_bounds__(kSortThreads) voxel_centroid_kernel(const SlotInfo* __restrict__ slots, TileMap tm,
-                                                                       const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                                       const uint32_t* __restrict__ tile_heads, float4* __restrict__ work) {
+                                                                       const uint32_t* __restrict__ keys, const float4* __restrict__ sorted,
+                                                                       const uint32_t* __restrict__ tile_heads, float4* __restrict__ work,
+                                                                       uint4* __restrict__ long_runs, uint32_t* __restrict__ n_long) {
   __shared__ uint32_t wsum[8];
   const uint32_t t = blockIdx.x;
   const uint32_t slot = tm.tile_slot[t], first = tm.tile_first[t];
@@ -291,8 +329,7 @@ __global__ void __launch_bounds__(kSortThreads) voxel_centroid_kernel(const Slot
   const uint32_t n = si.n_finite;
   if (first >= n) return;
   const uint32_t* k = keys + si.off;
-  const uint32_t* v = vals + si.off;
-  const float4* raw = si.raw;
+  const float4* pts = sorted + si.off;
   constexpr int kPer = kSortTile / kSortThreads;
   const uint32_t e0 = first + threadIdx.x * kPer;  // kPer consecutive sorted positions per thread
   uint32_t head_mask = 0, cnt = 0;
@@ -321,15 +358,62 @@ __global__ void __launch_bounds__(kSortThreads) voxel_centroid_kernel(const Slot
     if (!(head_mask & (1u << j))) continue;
     const uint32_t e = e0 + j;
     const uint32_t kk = k[e];
+    if (e + kLongRun < n && k[e + kLongRun] == kk) {  // sorted keys: the run has more than kLongRun points
+      long_runs[atomicAdd(n_long, 1u)] = make_uint4(slot, e, rank, 0u);
+      ++rank;
+      continue;
+    }
     float sx = 0.f, sy = 0.f, sz = 0.f;
     uint32_t l = e;
     do {
-      const float4 p = raw[v[l]];
+      const float4 p = pts[l];
       sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z);
       ++l;
     } while (l < n && k[l] == kk);
     const float c = (float)(l - e);
     out[rank++] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), 1.0f);
+  }
+}
+
+__global__ void __launch_bounds__(256) voxel_long_centroid_kernel(const SlotInfo* __restrict__ slots, const uint32_t* __restrict__ keys,
+                                                                  const float4* __restrict__ sorted, float4* __restrict__ work,
+                                                                  const uint4* __restrict__ long_runs, const uint32_t* __restrict__ n_long) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+  constexpr int kDepth = 4;  // batches of 32 points in flight per warp
+  for (uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < *n_long; q += warps) {
+    const uint4 job = long_runs[q];
+    const SlotInfo& si = slots[job.x];
+    const uint32_t n = si.n_finite;
+    const uint32_t* k = keys + si.off;
+    const float4* pts = sorted + si.off;
+    const uint32_t kk = k[job.y];
+    // length of the run: keys are sorted, so gallop + binary search for the first position with another key
+    uint32_t lo = job.y + kLongRun, step = kLongRun, hi;
+    for (;;) { hi = lo + step; if (hi >= n) { hi = n; break; } if (k[hi] != kk) break; lo = hi; step <<= 1; }
+    while (lo + 1 < hi) { const uint32_t mid = (lo + hi) >> 1; if (k[mid] == kk) lo = mid; else hi = mid; }
+    const uint32_t end = hi;  // k[lo] == kk, k[hi] != kk (or hi == n)
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    float4 buf[kDepth];
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d) { const uint32_t e = job.y + d * 32 + lane; buf[d] = e < end ? pts[e] : make_float4(0.f, 0.f, 0.f, 0.f); }
+    for (uint32_t b = job.y; b < end; b += 32 * kDepth) {
+#pragma unroll
+      for (int d = 0; d < kDepth; ++d) {
+        const float4 p = buf[d];
+        const uint32_t nb = b + (d + kDepth) * 32 + lane;           // refill this slot with the batch kDepth ahead
+        buf[d] = nb < end ? pts[nb] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int take = (int)min(32u, end > b + d * 32 ? end - (b + d * 32) : 0u);
+        for (int j = 0; j < take; ++j) {
+          sx = __fadd_rn(sx, __shfl_sync(FULL, p.x, j));
+          sy = __fadd_rn(sy, __shfl_sync(FULL, p.y, j));
+          sz = __fadd_rn(sz, __shfl_sync(FULL, p.z, j));
+        }
+      }
+    }
+    const float c = (float)(end - job.y);
+    if (lane == 0) work[si.off + job.z] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), 1.0f);
   }
 }
 
@@ -370,11 +454,16 @@ void run_voxel(Workspace& ws, float leaf, uint32_t* leaf_keys) {
     voxel_keys_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, keys[0]);
     ++ws.launches;
     if (leaf_keys) S3D_CUDA(cudaMemcpyAsync(leaf_keys, keys[0], 4 * size_t(ws.total), cudaMemcpyDeviceToDevice, st));
-    radix_sort_segmented(st, slots, ws.n_slots, tm, ws.slot_tile_begin.as<uint32_t>(), keys, vals, ws.hist.as<uint32_t>(), 4, kCountRaw, &ws.launches);
+    radix_sort_segmented(st, slots, ws.n_slots, tm, ws.slot_tile_begin.as<uint32_t>(), keys, vals, ws.hist.as<uint32_t>(), ws.sort_totals.as<uint32_t>(), 4, kCountRaw, &ws.launches);
     voxel_heads_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, keys[0], ws.tile_heads.as<uint32_t>());
     voxel_scan_kernel<<<ws.n_slots, 32, 0, st>>>(slots, ws.n_slots, ws.slot_tile_begin.as<uint32_t>(), ws.tile_heads.as<uint32_t>());
-    voxel_centroid_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, keys[0], vals[0], ws.tile_heads.as<uint32_t>(), ws.work.as<float4>());
-    ws.launches += 3;
+    uint32_t* n_long = ws.flags.as<uint32_t>() + 8;  // flags[8]: number of queued long runs (flags are zeroed by setup_batch)
+    float4* sorted = ws.gpts.as<float4>();  // free until the NN grid is built
+    voxel_gather_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, vals[0], sorted);
+    voxel_centroid_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, keys[0], sorted, ws.tile_heads.as<uint32_t>(), ws.work.as<float4>(),
+                                                               ws.long_runs.as<uint4>(), n_long);
+    voxel_long_centroid_kernel<<<148 * 2, 256, 0, st>>>(slots, keys[0], sorted, ws.work.as<float4>(), ws.long_runs.as<uint4>(), n_long);
+    ws.launches += 5;
   }
   voxel_passthrough_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.work.as<float4>());
   ++ws.launches;
