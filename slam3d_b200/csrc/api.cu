@@ -142,7 +142,7 @@ static void align_chunk_body(Workspace& ws, const std::vector<const float*>& clo
   const float leaf = cfg.point_cloud_density > 0 ? (float)cfg.point_cloud_density : 0.f;  // :127, setLeafSize(float)
   run_voxel(ws, leaf);
   const bool gicp = cfg.registration_algorithm == S3D_ALG_GICP;
-  const bool k_ok = cfg.correspondence_randomness >= 1 && cfg.correspondence_randomness <= 32;
+  const bool k_ok = cfg.correspondence_randomness >= 1 && cfg.correspondence_randomness <= kMaxK;
   if (!gicp || !k_ok) {
     // the reference evaluates the <100 gate before the algorithm switch (:134-135 then :139-165)
     SlotInfo* hs = ws.h_slots.as<SlotInfo>();
@@ -156,7 +156,7 @@ static void align_chunk_body(Workspace& ws, const std::vector<const float*>& clo
       if (out[i].n_source < 100 || out[i].n_target < 100) out[i].status = S3D_TOO_FEW_POINTS;
       else out[i].status = gicp ? S3D_INVALID_ARGUMENT : S3D_UNKNOWN_ALGORITHM;
     }
-    if (gicp) set_error("correspondence_randomness must be in [1, 32] on the GPU path");
+    if (gicp) set_error("correspondence_randomness must be in [1, 200] on the GPU path");
     else if (cfg.registration_algorithm == S3D_ALG_GICP_OMP || cfg.registration_algorithm == S3D_ALG_NDT_OMP)
       set_error("OMP is not available, you need to rebuild SLAM3D with OMP or use another matching algorithm.");
     else if (cfg.registration_algorithm == S3D_ALG_NDT) set_error("NDT is not implemented by the B200 path (SURVEY 8f rank 4).");
@@ -302,7 +302,7 @@ int s3d_voxel_downsample(s3d_context* ctx, s3d_cloud in, float leaf, float* out_
 
 int s3d_knn_covariances(s3d_context* ctx, s3d_cloud cloud, int k, uint32_t* knn_index, float* knn_dist2, double* covariances) {
   if (!ctx) return S3D_INVALID_ARGUMENT;
-  if (k < 1 || k > 32 || (uint64_t)k > cloud.n) { set_error("k must be in [1, 32] and not larger than the cloud"); return S3D_INVALID_ARGUMENT; }
+  if (k < 1 || k > kMaxK || (uint64_t)k > cloud.n) { set_error("k must be in [1, 200] and not larger than the cloud"); return S3D_INVALID_ARGUMENT; }
   return guarded([&]() -> int {
     WsLease lease(ctx, 0);
     Workspace& ws = *lease;
@@ -436,7 +436,7 @@ static void prepare_chunk(s3d_context* ctx, int device_slot, const s3d_cloud* cl
 int s3d_prepare_clouds(s3d_context* ctx, int device_slot, const s3d_cloud* clouds, int n, double density, int k, s3d_prepared_cloud** out) {
   if (!ctx || !out || n < 0 || (n > 0 && !clouds) || device_slot < 0 || device_slot >= (int)ctx->devs.size()) return S3D_INVALID_ARGUMENT;
   for (int i = 0; i < n; ++i) out[i] = nullptr;
-  if (k < 1 || k > 32) { set_error("correspondence_randomness must be in [1, 32] on the GPU path"); return S3D_INVALID_ARGUMENT; }
+  if (k < 1 || k > kMaxK) { set_error("correspondence_randomness must be in [1, 200] on the GPU path"); return S3D_INVALID_ARGUMENT; }
   if (n == 0) return S3D_OK;
   const int W = std::max(1, ctx->streams_per_device);
   const int chunk = std::max(1, std::min(2 * ctx->max_pairs_per_launch, (n + W - 1) / W));

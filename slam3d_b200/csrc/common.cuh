@@ -19,6 +19,7 @@ constexpr int kSortThreads = 256;
 constexpr int kMaxLevels = 10;       // Morton bits per axis (30-bit keys)
 constexpr uint32_t kInvalidKey = 0xFFFFFFFFu;
 constexpr uint32_t kNoIndex = 0xFFFFFFFFu;
+constexpr int kMaxK = 200;           // correspondence_randomness limit: the per-thread heap of the kNN kernel lives in shared memory (k KB per CTA)
 
 struct HashEntry;
 

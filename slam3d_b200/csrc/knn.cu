@@ -209,6 +209,8 @@ void run_knn_covariances(Workspace& ws, int k, uint32_t* knn_index, float* knn_d
   for (uint32_t s = 0; s < ws.n_slots; ++s) max_n = std::max(max_n, ws.h_n[s]);
   StageTimer timer(ws, kStageKnn);
   dim3 grid((max_n + kKnnThreads - 1) / kKnnThreads, ws.n_slots);
+  const size_t heap_bytes = sizeof(uint64_t) * k * kKnnThreads;
+  if (heap_bytes > 48 * 1024) S3D_CUDA(cudaFuncSetAttribute(knn_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heap_bytes));
   knn_cov_kernel<<<grid, kKnnThreads, sizeof(uint64_t) * k * kKnnThreads, ws.stream>>>(ws.slots.as<SlotInfo>(), ws.work.as<float4>(),
                                                                                         ws.normals.as<double4>(), k, knn_index, knn_dist2);
   ++ws.launches;

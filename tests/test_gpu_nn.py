@@ -29,7 +29,7 @@ def test_knn_indices_bit_exact(ctx, oracle_mod, filtered):
         assert bad.mean() < 2e-3, bad.sum()  # exactly degenerate neighbourhoods may pick another in-plane direction
 
 
-@pytest.mark.parametrize("k", [1, 5, 20, 32])
+@pytest.mark.parametrize("k", [1, 5, 20, 32, 50, 128])
 def test_knn_other_k(ctx, oracle_mod, filtered, k):
     f = filtered[0][::5]
     gi, gd, _ = ctx.knn_covariances(f, k)
