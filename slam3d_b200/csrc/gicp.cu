@@ -298,6 +298,31 @@ __device__ void finish_outer(PairState& ps, bool optimiser_failed, int32_t* flag
   }
 }
 
+// euler_derivs(x, E, true) spread over the CTA: threads 0..2 build the factor matrices of one axis each (the three sincos),
+// threads 0..9 one product (A B) C each, with the same operand order as the serial function, so E is bit-identical.
+__device__ void euler_derivs_cta(const double* x, Euler& E, double (*fac)[3][3][3]) {  // fac[axis][order] in shared memory
+  const int t = threadIdx.x;
+  if (t < 3) euler_factor(x[3 + t], t, fac[t][0], fac[t][1], fac[t][2]);  // axis 0 = X(phi), 1 = Y(theta), 2 = Z(psi)
+  __syncthreads();
+  if (t < 10) {
+    // derivative orders (z, y, x) of: R | dR0 dR1 dR2 | ddR00 ddR11 ddR22 | ddR01 ddR02 ddR12
+    const int oz = (t == 3) ? 1 : (t == 6) ? 2 : (t == 8 || t == 9) ? 1 : 0;
+    const int oy = (t == 2) ? 1 : (t == 5) ? 2 : (t == 7 || t == 9) ? 1 : 0;
+    const int ox = (t == 1) ? 1 : (t == 4) ? 2 : (t == 7 || t == 8) ? 1 : 0;
+    double T[3][3], O[3][3];
+    mat3_mul(fac[2][oz], fac[1][oy], T);
+    mat3_mul(T, fac[0][ox], O);
+    double (*dst)[3] = t == 0 ? E.R : t == 1 ? E.dR[0] : t == 2 ? E.dR[1] : t == 3 ? E.dR[2] : t == 4 ? E.ddR[0][0] : t == 5 ? E.ddR[1][1]
+                     : t == 6 ? E.ddR[2][2] : t == 7 ? E.ddR[0][1] : t == 8 ? E.ddR[0][2] : E.ddR[1][2];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) dst[i][j] = O[i][j];
+    if (t >= 7) {  // mixed second derivatives are symmetric in (k, l)
+      double (*sym)[3] = t == 7 ? E.ddR[1][0] : t == 8 ? E.ddR[2][0] : E.ddR[2][1];
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) sym[i][j] = O[i][j];
+    }
+  }
+  __syncthreads();
+}
+
 // one CTA per pair: ordered reduction of the tile partials of the pass that just ran, then the optimiser advances
 __global__ void __launch_bounds__(256) gicp_ctrl_kernel(const SlotInfo* __restrict__ slots, PairState* __restrict__ pairs,
                                                         const double* __restrict__ moments, const double* __restrict__ eval_part,
@@ -305,6 +330,7 @@ __global__ void __launch_bounds__(256) gicp_ctrl_kernel(const SlotInfo* __restri
   __shared__ double part[3][kLineSearchTrials * kEvalSums];
   __shared__ double red[kLineSearchTrials * kEvalSums];
   __shared__ Euler E;
+  __shared__ double fac[3][3][3][3];
   __shared__ double gH[42];
   __shared__ int mode;      // 0: nothing to assemble, 1: assemble the objective at ps.nst.xc from ps.sums
   __shared__ int newstep;   // a new Newton step started: its trial matrices are needed
@@ -358,10 +384,10 @@ __global__ void __launch_bounds__(256) gicp_ctrl_kernel(const SlotInfo* __restri
         mode = 0;
       }
     }
-    if (mode) euler_derivs(ps.nst.xc, E, true);
   }
   __syncthreads();
   if (!mode) return;
+  euler_derivs_cta(ps.nst.xc, E, fac);
   // objective at the evaluated state: 42 threads contract one gradient / Hessian entry each
   if (threadIdx.x < 42) gH[threadIdx.x] = objective_entry(ps.sums, E, threadIdx.x);
   __syncthreads();
