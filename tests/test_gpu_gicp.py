@@ -148,3 +148,23 @@ def test_batched_loop_closure_candidates(ctx, oracle_mod):
             check(rf[i], of)
     for i in range(4, n):  # repeated pairs must reproduce the first occurrence bit for bit
         assert np.array_equal(rc[i].pose(), rc[i % 4].pose()) and np.array_equal(rf[i].pose(), rf[i % 4].pose())
+
+
+def test_in_process_multi_device_context(kitti):
+    """s3d_create_context(devices=[0, 1, ...]): one context, pairs sharded over the devices by host threads, same results."""
+    import torch
+    import slam3d_b200
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs 2 GPUs")
+    p = RegistrationParameters.defaults(point_cloud_density=0.2)
+    srcs = [kitti[i % 3] for i in range(7)]
+    tgts = [kitti[i % 3 + 1] for i in range(7)]
+    one = slam3d_b200.Context([0])
+    ref = one.gicp_align_batch(srcs, tgts, None, p)
+    one.close()
+    many = slam3d_b200.Context(list(range(min(n_dev, 4))))
+    got = many.gicp_align_batch(srcs, tgts, None, p)
+    many.close()
+    for a, b in zip(got, ref):
+        assert a.status == b.status and np.array_equal(a.pose(), b.pose()) and a.fitness == b.fitness
