@@ -153,6 +153,20 @@ int s3d_gicp_align_prepared_batch(s3d_context* ctx, const s3d_prepared_cloud* co
                                   const s3d_prepared_cloud* const* targets, const double* guesses,
                                   const s3d_registration_parameters* params, int n_pairs, s3d_result* out);
 
+/* ---- patch and map building -------------------------------------------------------------
+ * PointCloudSensor::transform (PointCloudSensor.cpp:228-233): pcl::transformPointCloud with a double 4x4.
+ * out_xyzw holds in.n points (host or device). */
+int s3d_transform_cloud(s3d_context* ctx, s3d_cloud in, const double T[16], float* out_xyzw);
+/* PointCloudSensor::removeOutliers (:211-226): pcl::RadiusOutlierRemoval — a point stays iff at least min_neighbors other
+ * points lie within `radius`; returns the input unchanged unless in.n > 0, radius > 0 and min_neighbors > 0.
+ * Output keeps the input order. */
+int s3d_remove_outliers(s3d_context* ctx, s3d_cloud in, double radius, unsigned min_neighbors, float* out_xyzw, uint64_t* n_out);
+/* PointCloudSensor::buildMap (:301-318) on explicit lists: accumulate transform(cloud_i, pose_i) in list order
+ * (getAccumulatedCloud :235-256, pose_i = vertex.correctedPose * measurement.sensorPose), removeOutliers, downsample.
+ * poses = n x 16 doubles; out_xyzw holds sum(clouds[i].n) points. */
+int s3d_build_map(s3d_context* ctx, const s3d_cloud* clouds, const double* poses, int n, double outlier_radius,
+                  unsigned outlier_neighbors, double resolution, float* out_xyzw, uint64_t* n_out);
+
 /* Optional per-stage device timing (CUDA events on the launching stream, read back at the call's final
  * synchronisation).  Stage ids: 0 voxel filter, 1 NN grid build, 2 kNN+covariances, 3 GICP correspondence/
  * linearisation kernel, 4 GICP solve kernel, 5 fitness.  ms[i] / launches[i] accumulate since the last reset. */

@@ -133,6 +133,39 @@ def gicp_align_batch(sources, targets, guesses=None, params=None, n_threads=0):
     return list(res)
 
 
+def transform_cloud(cloud, T):
+    a, c = _cloud(cloud)
+    t = np.ascontiguousarray(np.asarray(T, np.float64).T)
+    out = np.empty_like(a)
+    lib().s3d_oracle_transform_cloud(c, t.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def remove_outliers(cloud, radius, min_neighbors):
+    a, c = _cloud(cloud)
+    out = np.empty((max(a.shape[0], 1), 4), np.float32)
+    keep = np.zeros(max(a.shape[0], 1), np.uint8)
+    n = C.c_uint64(0)
+    lib().s3d_oracle_remove_outliers(c, C.c_double(radius), C.c_uint(min_neighbors), out.ctypes.data_as(C.c_void_p), C.byref(n),
+                                     keep.ctypes.data_as(C.c_void_p))
+    return out[: n.value].copy(), keep[: a.shape[0]].astype(bool)
+
+
+def build_map(clouds, poses, outlier_radius, outlier_neighbors, resolution):
+    n = len(clouds)
+    keep = []
+    cc = (Cloud * n)()
+    total = 0
+    for i in range(n):
+        a, c = _cloud(clouds[i]); keep.append(a); cc[i] = c; total += a.shape[0]
+    P = np.ascontiguousarray(np.stack([np.asarray(p, np.float64).T for p in poses])) if n else np.zeros((0, 4, 4))
+    out = np.empty((max(total, 1), 4), np.float32)
+    m = C.c_uint64(0)
+    lib().s3d_oracle_build_map(cc, P.ctypes.data_as(C.c_void_p), n, C.c_double(outlier_radius), C.c_uint(outlier_neighbors),
+                               C.c_double(resolution), out.ctypes.data_as(C.c_void_p), C.byref(m))
+    return out[: m.value].copy()
+
+
 def max_threads():
     return lib().s3d_oracle_max_threads()
 

@@ -759,6 +759,39 @@ static int align_impl(const P4* src, size_t nsrc, const P4* tgt, size_t ntgt, co
   return res.status = S3D_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Map building: PointCloudSensor::transform :228-233, getAccumulatedCloud :235-256,
+// removeOutliers :211-226 (pcl::RadiusOutlierRemoval), buildMap :301-318.
+// ------------------------------------------------------------------------------------------------
+
+// pcl::transformPointCloud(cloud, out, Matrix4d): double se3 form x*c0 + (y*c1 + (z*c2 + c3)), result cast to float.
+static inline P4 transform_se3_d(const double T[16], const P4& p) {
+  const double x = p.x, y = p.y, z = p.z;
+  P4 o;
+  o.x = static_cast<float>(x * T[0] + (y * T[4] + (z * T[8] + T[12])));
+  o.y = static_cast<float>(x * T[1] + (y * T[5] + (z * T[9] + T[13])));
+  o.z = static_cast<float>(x * T[2] + (y * T[6] + (z * T[10] + T[14])));
+  o.w = 1.f;
+  return o;
+}
+
+// pcl::RadiusOutlierRemoval on a dense cloud: nearestKSearch(min_pts + 1) (the query itself included) and the point is
+// kept iff the last of them is within the radius:  !(radius^2 < d2_k)  with d2 float, radius^2 double.
+static void radius_outlier_removal(const std::vector<P4>& in, double radius, unsigned min_pts, std::vector<P4>& out, uint8_t* keep) {
+  out.clear();
+  KdTree tree;
+  tree.build(in.data(), in.size());
+  const int k = static_cast<int>(min_pts) + 1;
+  const double r2 = radius * radius;
+  std::vector<KdTree::Cand> nb(k);
+  for (size_t i = 0; i < in.size(); ++i) {
+    const int found = tree.knn(in[i], k, nb.data());
+    const bool ok = found == k && !(r2 < static_cast<double>(nb[k - 1].d2));
+    if (keep) keep[i] = ok ? 1 : 0;
+    if (ok) out.push_back(in[i]);
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -931,3 +964,45 @@ int s3d_oracle_test_eigen6(const double A[36], double V[36], double w[6]) {
 }
 
 }  // extern "C"
+
+extern "C" {
+
+int s3d_oracle_transform_cloud(s3d_cloud cloud, const double T[16], float* out_xyzw) {
+  const P4* p = reinterpret_cast<const P4*>(cloud.xyzw);
+  P4* o = reinterpret_cast<P4*>(out_xyzw);
+  for (size_t i = 0; i < cloud.n; ++i) o[i] = transform_se3_d(T, p[i]);
+  return S3D_OK;
+}
+
+// PointCloudSensor::removeOutliers :211-226 — returns the input unchanged unless size > 0, radius > 0 and min_neighbors > 0
+int s3d_oracle_remove_outliers(s3d_cloud cloud, double radius, unsigned min_neighbors, float* out_xyzw, uint64_t* n_out, uint8_t* keep) {
+  const P4* p = reinterpret_cast<const P4*>(cloud.xyzw);
+  std::vector<P4> in(p, p + cloud.n), out;
+  if (cloud.n > 0 && radius > 0 && min_neighbors > 0) radius_outlier_removal(in, radius, min_neighbors, out, keep);
+  else { out = in; if (keep) std::fill(keep, keep + cloud.n, 1); }
+  if (!out.empty()) std::memcpy(out_xyzw, out.data(), out.size() * sizeof(P4));
+  *n_out = out.size();
+  return S3D_OK;
+}
+
+// PointCloudSensor::buildMap :301-318 with explicit (cloud, pose) lists: accumulate in list order, removeOutliers, downsample.
+// poses: n x 16 doubles (column-major) = vertex.correctedPose * measurement.sensorPose  (:248)
+int s3d_oracle_build_map(const s3d_cloud* clouds, const double* poses, int n, double outlier_radius, unsigned outlier_neighbors,
+                         double resolution, float* out_xyzw, uint64_t* n_out) {
+  std::vector<P4> accu;
+  for (int i = 0; i < n; ++i) {
+    const P4* p = reinterpret_cast<const P4*>(clouds[i].xyzw);
+    for (size_t j = 0; j < clouds[i].n; ++j) accu.push_back(transform_se3_d(poses + 16 * i, p[j]));
+  }
+  std::vector<P4> filtered;
+  if (!accu.empty() && outlier_radius > 0 && outlier_neighbors > 0) radius_outlier_removal(accu, outlier_radius, outlier_neighbors, filtered, nullptr);
+  else filtered = accu;
+  std::vector<P4> map;
+  if (!filtered.empty()) voxel_filter(filtered.data(), filtered.size(), static_cast<float>(resolution), map, nullptr, nullptr);  // downsample(): empty in, empty out
+  if (!map.empty()) std::memcpy(out_xyzw, map.data(), map.size() * sizeof(P4));
+  *n_out = map.size();
+  return S3D_OK;
+}
+
+}  // extern "C"
+

@@ -29,3 +29,21 @@ for leaf in (0.05, 0.1, 0.2):
         ctx.knn_covariances(fd, 20)
     st = ctx.stage_times(reset=True)
     print(f"          kNN-20+cov on M={M}: grid {st['grid']['ms']/3*1e3:.0f} us, knn_cov {st['knn_cov']['ms']/3*1e3:.0f} us -> {M/(st['knn_cov']['ms']/3)/1e3:.1f} M queries/s")
+
+# ---- map building (buildMap): 16 scans -> accumulate + RadiusOutlierRemoval(0.2, 3) + VoxelGrid(0.1) ----
+rng = np.random.default_rng(20260117)
+scene = synth.Scene(20260117)
+scans, poses = [], []
+for i in range(16):
+    P = synth.make_pose([12.0 * i / 15 - 6.0, 0.0, 0.0], [0.0, 0.0, 0.02 * i])
+    scans.append(synth.scan(scene, P, rng)); poses.append(P)
+dev_scans = [torch.from_numpy(slam3d_b200.as_xyzw(s)).cuda() for s in scans]
+for _ in range(2):
+    m = ctx.build_map(dev_scans, poses, 0.2, 3, 0.1)
+t0 = time.perf_counter()
+for _ in range(5):
+    m = ctx.build_map(dev_scans, poses, 0.2, 3, 0.1)
+dt = (time.perf_counter() - t0) / 5
+import oracle
+t0 = time.perf_counter(); mo = oracle.build_map(scans, poses, 0.2, 3, 0.1); to = time.perf_counter() - t0
+print(f"buildMap 16 scans (2 097 152 points) -> {m.shape[0]} map points: {dt*1e3:.2f} ms per map on the GPU (device-resident scans, result to host); oracle {to*1e3:.0f} ms; identical: {np.array_equal(m, mo)}")

@@ -43,6 +43,10 @@ def lib():
         L.s3d_gicp_align.argtypes = [C.c_void_p, Cloud, Cloud, C.c_void_p, C.POINTER(RegistrationParameters), C.POINTER(Result)]
         L.s3d_gicp_align_batch.argtypes = [C.c_void_p, C.POINTER(Cloud), C.POINTER(Cloud), C.c_void_p, C.POINTER(RegistrationParameters),
                                            C.c_int, C.POINTER(Result)]
+        L.s3d_transform_cloud.argtypes = [C.c_void_p, Cloud, C.c_void_p, C.c_void_p]
+        L.s3d_remove_outliers.argtypes = [C.c_void_p, Cloud, C.c_double, C.c_uint, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.s3d_build_map.argtypes = [C.c_void_p, C.POINTER(Cloud), C.c_void_p, C.c_int, C.c_double, C.c_uint, C.c_double, C.c_void_p,
+                                    C.POINTER(C.c_uint64)]
         L.s3d_prepare_cloud.argtypes = [C.c_void_p, C.c_int, Cloud, C.c_double, C.c_int, C.POINTER(C.c_void_p)]
         L.s3d_prepare_clouds.argtypes = [C.c_void_p, C.c_int, C.POINTER(Cloud), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_void_p)]
         L.s3d_release_cloud.argtypes = [C.c_void_p, C.c_void_p]
@@ -257,6 +261,41 @@ def _gicp_align_prepared_batch(self, sources, targets, guesses=None, params=None
     return list(res)
 
 
+def _transform_cloud(self, cloud, T):
+    a, c = _cloud(cloud)
+    t = _colmajor(T)
+    out = np.empty((a.shape[0], 4), np.float32)
+    self._check(lib().s3d_transform_cloud(self._h, c, t.ctypes.data, out.ctypes.data), "s3d_transform_cloud")
+    return out
+
+
+def _remove_outliers(self, cloud, radius, min_neighbors):
+    a, c = _cloud(cloud)
+    out = np.empty((max(a.shape[0], 1), 4), np.float32)
+    n = C.c_uint64(0)
+    self._check(lib().s3d_remove_outliers(self._h, c, float(radius), int(min_neighbors), out.ctypes.data, C.byref(n)), "s3d_remove_outliers")
+    return out[: n.value].copy()
+
+
+def _build_map(self, clouds, poses, outlier_radius=0.2, outlier_neighbors=3, resolution=0.1):
+    """PointCloudSensor::buildMap on explicit (cloud, pose) lists; defaults = the sensor's defaults (PointCloudSensor.cpp:179-183)."""
+    n = len(clouds)
+    keep = []
+    cc = (Cloud * max(n, 1))()
+    total = 0
+    for i in range(n):
+        a, c = _cloud(clouds[i]); keep.append(a); cc[i] = c; total += a.shape[0]
+    P = np.ascontiguousarray(np.stack([_colmajor(p) for p in poses])) if n else np.zeros((1, 4, 4))
+    out = np.empty((max(total, 1), 4), np.float32)
+    m = C.c_uint64(0)
+    self._check(lib().s3d_build_map(self._h, cc, P.ctypes.data, n, float(outlier_radius), int(outlier_neighbors), float(resolution),
+                                    out.ctypes.data, C.byref(m)), "s3d_build_map")
+    return out[: m.value].copy()
+
+
+Context.transform_cloud = _transform_cloud
+Context.remove_outliers = _remove_outliers
+Context.build_map = _build_map
 Context.prepare_cloud = _prepare_cloud
 Context.prepare_clouds = _prepare_clouds
 Context.gicp_align_prepared = _gicp_align_prepared

@@ -586,6 +586,82 @@ int s3d_gicp_align_prepared(s3d_context* ctx, const s3d_prepared_cloud* source, 
   return out->status;
 }
 
+// ---- patch and map building ------------------------------------------------------------------------------------------
+int s3d_transform_cloud(s3d_context* ctx, s3d_cloud in, const double T[16], float* out_xyzw) {
+  if (!ctx || !T || (in.n && !out_xyzw)) return S3D_INVALID_ARGUMENT;
+  if (in.n == 0) return S3D_OK;
+  return guarded([&]() -> int {
+    WsLease lease(ctx, 0);
+    Workspace& ws = *lease;
+    const uint32_t n = run_accumulate(ws, {in.xyzw}, {in.n}, T);
+    copy_out(ws, out_xyzw, ws.accu.p, 16 * (size_t)n);
+    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    return S3D_OK;
+  });
+}
+
+int s3d_remove_outliers(s3d_context* ctx, s3d_cloud in, double radius, unsigned min_neighbors, float* out_xyzw, uint64_t* n_out) {
+  if (!ctx || !n_out || (in.n && !out_xyzw)) return S3D_INVALID_ARGUMENT;
+  *n_out = 0;
+  if (in.n == 0) return S3D_OK;
+  return guarded([&]() -> int {
+    WsLease lease(ctx, 0);
+    Workspace& ws = *lease;
+    const double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    if (!(radius > 0 && min_neighbors > 0)) {  // :214 — the reference hands the input back
+      S3D_CUDA(cudaMemcpyAsync(out_xyzw, in.xyzw, 16 * in.n, cudaMemcpyDefault, ws.stream));
+      S3D_CUDA(cudaStreamSynchronize(ws.stream));
+      *n_out = in.n;
+      return S3D_OK;
+    }
+    // stage the input on the device (identity transform would rewrite w; a plain copy keeps the points verbatim)
+    ws.accu.reserve(16 * in.n); ws.accu2.reserve(16 * in.n);
+    S3D_CUDA(cudaMemcpyAsync(ws.accu.p, in.xyzw, 16 * in.n, cudaMemcpyDefault, ws.stream));
+    (void)I;
+    uint32_t kept = 0;
+    with_arena_retry(ws, [&] { kept = run_radius_filter(ws, ws.accu.as<float4>(), (uint32_t)in.n, radius, min_neighbors, ws.accu2.as<float4>()); });
+    copy_out(ws, out_xyzw, ws.accu2.p, 16 * (size_t)kept);
+    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    *n_out = kept;
+    return S3D_OK;
+  });
+}
+
+int s3d_build_map(s3d_context* ctx, const s3d_cloud* clouds, const double* poses, int n, double outlier_radius, unsigned outlier_neighbors,
+                  double resolution, float* out_xyzw, uint64_t* n_out) {
+  if (!ctx || !n_out || n < 0 || (n > 0 && (!clouds || !poses))) return S3D_INVALID_ARGUMENT;
+  *n_out = 0;
+  if (n == 0) return S3D_OK;
+  return guarded([&]() -> int {
+    WsLease lease(ctx, 0);
+    Workspace& ws = *lease;
+    std::vector<const float*> ptrs(n);
+    std::vector<uint64_t> sizes(n);
+    for (int i = 0; i < n; ++i) { ptrs[i] = clouds[i].xyzw; sizes[i] = clouds[i].n; }
+    uint32_t m = run_accumulate(ws, ptrs, sizes, poses);                          // getAccumulatedCloud
+    if (m == 0) return S3D_OK;
+    const float4* cur = ws.accu.as<float4>();
+    if (outlier_radius > 0 && outlier_neighbors > 0) {                             // removeOutliers
+      ws.accu2.reserve(16 * (size_t)m);
+      uint32_t kept = 0;
+      with_arena_retry(ws, [&] { kept = run_radius_filter(ws, cur, m, outlier_radius, outlier_neighbors, ws.accu2.as<float4>()); });
+      cur = ws.accu2.as<float4>(); m = kept;
+    }
+    if (m == 0) return S3D_OK;
+    if (!(resolution > 0)) { set_error("map resolution must be positive"); return S3D_INVALID_ARGUMENT; }
+    setup_batch(ws, {reinterpret_cast<const float*>(cur)}, {m}, 0);               // downsample
+    run_voxel(ws, (float)resolution);
+    SlotInfo* hs = ws.h_slots.as<SlotInfo>();
+    S3D_CUDA(cudaMemcpyAsync(hs, ws.slots.p, sizeof(SlotInfo), cudaMemcpyDeviceToHost, ws.stream));
+    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.d2h += sizeof(SlotInfo);
+    *n_out = hs[0].n_pts;
+    copy_out(ws, out_xyzw, ws.work.p, 16 * (size_t)hs[0].n_pts);
+    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    return S3D_OK;
+  });
+}
+
 int s3d_gicp_align_batch(s3d_context* ctx, const s3d_cloud* sources, const s3d_cloud* targets, const double* guesses,
                          const s3d_registration_parameters* params, int n_pairs, s3d_result* out) {
   if (!ctx || !params || !out || n_pairs < 0 || (n_pairs > 0 && (!sources || !targets || !guesses))) return S3D_INVALID_ARGUMENT;

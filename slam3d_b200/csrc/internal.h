@@ -116,7 +116,8 @@ struct Workspace {
   DevBuf iter_tile_pair, iter_tile_first;     // uint32[iter_tiles]
   uint32_t iter_tiles = 0;
   DevBuf fit_partial;                         // double[iter_tiles*2]
-  DevBuf flags;                               // int32[4]: [0] error bits, [1] active pairs, [2] hash entries used
+  DevBuf accu, accu2, map_aux;                // map building: accumulated cloud, filtered cloud, poses / keep flags
+  DevBuf flags;                               // int32[16]: [0] error bits, [1] active pairs, [2] hash entries used, [3] entries needed, [8] long voxel runs, [9] kept points
   PinnedBuf h_slots, h_pairs, h_small, h_tiles;  // pinned host mirrors
   uint64_t launches = 0, h2d = 0, d2h = 0;
   // optional stage timing (s3d_set_profiling)
@@ -157,6 +158,8 @@ void run_grid(Workspace& ws, float leaf_hint);      // NN grid on the working cl
 void run_knn_covariances(Workspace& ws, int k, uint32_t* knn_index, float* knn_dist2);  // outputs optional (device, slot-concatenated)
 void run_expand_cov(Workspace& ws, double* cov_out);  // full 3x3 covariances per original index (stage API)
 void run_nn_stage(Workspace& ws, uint32_t ref_slot, uint32_t qry_slot, const float* T16_dev, uint32_t* nn_index, float* nn_dist2);
+uint32_t run_accumulate(Workspace& ws, const std::vector<const float*>& clouds, const std::vector<uint64_t>& sizes, const double* poses);  // -> ws.accu
+uint32_t run_radius_filter(Workspace& ws, const float4* dev_in, uint32_t n, double radius, unsigned min_pts, float4* dev_out);
 void check_arena(Workspace& ws, const int32_t* h_flags);  // throws ArenaOverflow when the grid build flagged it (h_flags: synchronised copy)
 void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& params, const double* guesses, s3d_result* out);
 

@@ -102,7 +102,10 @@ Transform align(PointCloudMeasurement::Ptr source, PointCloudMeasurement::Ptr ta
 }
 
 PointCloudSensor::PointCloudSensor(const std::string& n, Logger* l) : mName(n), mLogger(l), mCovarianceScale(1.0) {
-  mScanResolution = 0.1;  // :179
+  mScanResolution = 0.1;  // :179-182
+  mMapResolution = 0.1;
+  mMapOutlierRadius = 0.2;
+  mMapOutlierNeighbors = 3;
 }
 
 PointCloudSensor::~PointCloudSensor() {}
@@ -130,15 +133,55 @@ PointCloud::Ptr PointCloudSensor::downsampleScan(PointCloud::Ptr source) {
 PointCloud::Ptr PointCloudSensor::transform(PointCloud::ConstPtr source, const Transform tf) const {
   PointCloud::Ptr out(new PointCloud);
   out->points.resize(source->size());
-  for (size_t i = 0; i < source->size(); ++i) {
-    const PointType& p = source->points[i];
-    PointType q;
-    q.x = static_cast<float>(tf(0, 0) * p.x + tf(0, 1) * p.y + tf(0, 2) * p.z + tf(0, 3));
-    q.y = static_cast<float>(tf(1, 0) * p.x + tf(1, 1) * p.y + tf(1, 2) * p.z + tf(1, 3));
-    q.z = static_cast<float>(tf(2, 0) * p.x + tf(2, 1) * p.y + tf(2, 2) * p.z + tf(2, 3));
-    out->points[i] = q;
+  if (source->size()) {
+    s3d_cloud in{&source->points[0].x, source->size()};
+    if (s3d_transform_cloud(defaultContext(), in, tf.data(), &out->points[0].x) != S3D_OK) throw std::runtime_error(s3d_last_error());
   }
   return out;
+}
+
+// :211-226
+PointCloud::Ptr PointCloudSensor::removeOutliers(PointCloud::Ptr in, double radius, unsigned min_neighbors) const {
+  if (in->size() > 0 && radius > 0 && min_neighbors > 0) {
+    PointCloud::Ptr out(new PointCloud);
+    out->points.resize(in->size());
+    uint64_t n = 0;
+    if (s3d_remove_outliers(defaultContext(), asCloud(in), radius, min_neighbors, &out->points[0].x, &n) != S3D_OK) throw std::runtime_error(s3d_last_error());
+    out->points.resize(n);
+    return out;
+  }
+  return in;
+}
+
+// :235-256  (pose = vertex.correctedPose * measurement.sensorPose, accumulated in list order)
+PointCloud::Ptr PointCloudSensor::getAccumulatedCloud(const PosedMeasurements& vertices) const {
+  PointCloud::Ptr accu(new PointCloud);
+  for (size_t i = 0; i < vertices.size(); ++i) {
+    PointCloud::Ptr t = transform(vertices[i].first->getPointCloud(), vertices[i].second * vertices[i].first->getSensorPose());
+    accu->points.insert(accu->points.end(), t->points.begin(), t->points.end());
+  }
+  return accu;
+}
+
+// :301-318  one device pass: accumulate -> removeOutliers -> downsample
+PointCloud::Ptr PointCloudSensor::buildMap(const PosedMeasurements& vertices) const {
+  PointCloud::Ptr map(new PointCloud);
+  std::vector<s3d_cloud> clouds(vertices.size());
+  std::vector<double> poses(16 * vertices.size());
+  size_t total = 0;
+  for (size_t i = 0; i < vertices.size(); ++i) {
+    clouds[i] = asCloud(vertices[i].first->getPointCloud());
+    const Transform p = vertices[i].second * vertices[i].first->getSensorPose();
+    for (int j = 0; j < 16; ++j) poses[16 * i + j] = p.m[j];
+    total += clouds[i].n;
+  }
+  map->points.resize(total);
+  uint64_t n = 0;
+  const int st = s3d_build_map(defaultContext(), clouds.data(), poses.data(), (int)vertices.size(), mMapOutlierRadius, mMapOutlierNeighbors,
+                               mMapResolution, total ? &map->points[0].x : nullptr, &n);
+  if (st != S3D_OK && mLogger) mLogger->message(ERROR, s3d_last_error());  // :309-312 logs and returns what it has
+  map->points.resize(st == S3D_OK ? n : 0);
+  return map;
 }
 
 // :269-299
@@ -164,7 +207,9 @@ void PointCloudSensor::setRegistrationParameters(const RegistrationParameters& c
   if (mLogger) mLogger->message(INFO, coarse ? " = RegistrationParameters (Coarse) =" : " = RegistrationParameters (Fine) =");
 }
 
-// :342-346
+// :342-360
 void PointCloudSensor::setScanResolution(double r) { mScanResolution = r; }
+void PointCloudSensor::setMapResolution(double r) { mMapResolution = r; }
+void PointCloudSensor::setMapOutlierRemoval(double r, unsigned n) { mMapOutlierRadius = r; mMapOutlierNeighbors = n; }
 
 }  // namespace slam3d_b200

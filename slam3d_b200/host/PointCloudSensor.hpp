@@ -45,9 +45,17 @@ class PointCloudSensor {
   virtual Constraint::Ptr createConstraint(const Measurement::Ptr& source, const Measurement::Ptr& target, const Transform& odometry, bool loop);
   void setRegistrationParameters(const RegistrationParameters& param, bool coarse);
   void setScanResolution(double r);
+  void setMapResolution(double r);                            // :348-352
+  void setMapOutlierRemoval(double r, unsigned n);            // :354-360
   static PointCloud::Ptr downsample(PointCloud::Ptr source, double resolution);
   PointCloud::Ptr downsampleScan(PointCloud::Ptr source);
   PointCloud::Ptr transform(PointCloud::ConstPtr source, const Transform tf) const;
+  PointCloud::Ptr removeOutliers(PointCloud::Ptr source, double radius, unsigned min_neighbors) const;   // :211-226
+  // getAccumulatedCloud / buildMap take the graph's VertexObjectList in the reference (:235-256, :301-318); without a graph
+  // the caller passes the same information explicitly: each measurement with its corrected vertex pose.
+  typedef std::vector<std::pair<PointCloudMeasurement::Ptr, Transform> > PosedMeasurements;
+  PointCloud::Ptr getAccumulatedCloud(const PosedMeasurements& vertices) const;
+  PointCloud::Ptr buildMap(const PosedMeasurements& vertices) const;
 
  protected:
   std::string mName;
@@ -56,6 +64,9 @@ class PointCloudSensor {
   RegistrationParameters mFineConfiguration;
   RegistrationParameters mCoarseConfiguration;
   double mScanResolution;
+  double mMapResolution;
+  double mMapOutlierRadius;
+  unsigned mMapOutlierNeighbors;
 };
 
 }  // namespace slam3d_b200

@@ -72,6 +72,29 @@ int64_t s3dhost_downsample(const float* in, uint64_t n, double leaf, float* out)
   return m;
 }
 
+// PointCloudSensor::buildMap on n posed scans (sensor pose = identity); out must hold the sum of the sizes. Returns the map size or -1.
+int64_t s3dhost_build_map(void* s, const float* const* scans, const uint64_t* sizes, int n, const double* poses, double resolution,
+                          double outlier_radius, unsigned outlier_neighbors, float* out) {
+  int64_t m = -1;
+  wrap([&] {
+    PointCloudSensor* sensor = static_cast<PointCloudSensor*>(s);
+    sensor->setMapResolution(resolution);
+    sensor->setMapOutlierRemoval(outlier_radius, outlier_neighbors);
+    PointCloudSensor::PosedMeasurements v;
+    for (int i = 0; i < n; ++i)
+      v.emplace_back(PointCloudMeasurement::Ptr(new PointCloudMeasurement(makeCloud(scans[i], sizes[i]), "robot", sensor->getName(), Transform())),
+                     makeTransform(poses + 16 * i));
+    PointCloud::Ptr map = sensor->buildMap(v);
+    PointCloud::Ptr accu = sensor->getAccumulatedCloud(v);
+    PointCloud::Ptr filt = sensor->removeOutliers(accu, outlier_radius, outlier_neighbors);
+    PointCloud::Ptr map2 = PointCloudSensor::downsample(filt, resolution);   // the three public steps give the same map
+    if (map2->size() != map->size() || (map->size() && std::memcmp(&map->points[0].x, &map2->points[0].x, 16 * map->size()) != 0)) { m = -2; return; }
+    m = (int64_t)map->size();
+    if (m) std::memcpy(out, &map->points[0].x, 16 * m);
+  });
+  return m;
+}
+
 // Mini-host: n scans fed to addMeasurement(m, odom) in order (link-to-previous), from `threads` host threads when > 1
 // (each thread owns a MiniHost but all share the sensor and the process-wide context => concurrent createConstraint).
 // out_T: (n-1) x 16 doubles per thread-0 run; returns the number of recorded edges of run 0 or -1.

@@ -29,6 +29,8 @@ def host():
                                               C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.s3dhost_downsample.restype = C.c_int64
     lib.s3dhost_downsample.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_void_p]
+    lib.s3dhost_build_map.restype = C.c_int64
+    lib.s3dhost_build_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_uint, C.c_void_p]
     lib.s3dhost_set_cache_capacity.argtypes = [C.c_uint64]
     lib.s3dhost_cache_hits.restype = C.c_uint64
     lib.s3dhost_run_odometry.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
@@ -161,3 +163,22 @@ def test_host_downsample(host, oracle_mod, kitti):
     eo, _, _ = oracle_mod.voxel_downsample(kitti[2], 0.1)
     assert m == eo.shape[0] and np.array_equal(out[:m].view(np.uint32), eo.view(np.uint32))
     assert host.s3dhost_downsample(a.ctypes.data, 0, 0.1, out.ctypes.data) == 0  # empty in, empty out (:193)
+
+
+def test_host_build_map(host, oracle_mod, kitti):
+    """PointCloudSensor::buildMap through the mirror == accumulate + removeOutliers + downsample step by step == oracle."""
+    import slam3d_b200
+    sensor = host.s3dhost_sensor_create(b"velodyne")
+    scans = [slam3d_b200.as_xyzw(k) for k in kitti]
+    ptrs = (C.c_void_p * 4)(*[s.ctypes.data for s in scans])
+    sizes = (C.c_uint64 * 4)(*[s.shape[0] for s in scans])
+    poses = []
+    for i in range(4):
+        P = np.eye(4); P[0, 3] = 0.69 * i
+        poses.append(P)
+    pc = np.ascontiguousarray(np.stack([p.T for p in poses]))
+    out = np.zeros((sum(s.shape[0] for s in scans), 4), np.float32)
+    m = host.s3dhost_build_map(sensor, ptrs, sizes, 4, pc.ctypes.data, 0.1, 0.2, 3, out.ctypes.data)
+    want = oracle_mod.build_map(kitti, poses, 0.2, 3, 0.1)
+    assert m == want.shape[0] and np.array_equal(out[:m].view(np.uint32), want.view(np.uint32))
+    host.s3dhost_sensor_destroy(sensor)

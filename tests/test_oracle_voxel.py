@@ -79,3 +79,29 @@ def test_voxel_edge_cases(oracle_mod):
     dup = np.tile(np.array([[0.3, -0.7, 1.1]], np.float32), (7, 1))
     out, li, ov = oracle_mod.voxel_downsample(dup, 0.2)
     assert out.shape[0] == 1
+
+
+def test_map_building_oracle(oracle_mod, kitti):
+    """Oracle restatement of transform / RadiusOutlierRemoval / buildMap against numpy + scipy re-derivations."""
+    from scipy.spatial import cKDTree
+    c = kitti[0][:30000]
+    T = np.eye(4); T[:3, 3] = [3.0, -1.0, 0.2]
+    a = 0.4
+    T[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+    got = oracle_mod.transform_cloud(c, T)
+    x, y, z = (c[:, i].astype(np.float64) for i in range(3))
+    for r in range(3):
+        ref = (x * T[r, 0] + (y * T[r, 1] + (z * T[r, 2] + T[r, 3]))).astype(np.float32)
+        assert np.array_equal(got[:, r], ref)
+    out, keep = oracle_mod.remove_outliers(c, 0.2, 3)
+    tree = cKDTree(c.astype(np.float64))
+    cnt = np.array([len(v) for v in tree.query_ball_point(c.astype(np.float64), 0.2)])
+    assert (keep == (cnt >= 4)).mean() > 0.9995          # float32 vs float64 distances differ only on the boundary
+    assert np.array_equal(out[:, :3], c[keep])
+    # buildMap == the three steps
+    m = oracle_mod.build_map([c, kitti[1][:30000]], [np.eye(4), T], 0.2, 3, 0.1)
+    accu = np.concatenate([oracle_mod.transform_cloud(c, np.eye(4)), oracle_mod.transform_cloud(kitti[1][:30000], T)], 0)
+    filt, _ = oracle_mod.remove_outliers(accu, 0.2, 3)
+    ds, _, _ = oracle_mod.voxel_downsample(filt, 0.1)
+    assert np.array_equal(m, ds)
+    assert oracle_mod.build_map([np.zeros((0, 3), np.float32)], [np.eye(4)], 0.2, 3, 0.1).shape[0] == 0
