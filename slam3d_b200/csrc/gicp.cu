@@ -14,6 +14,9 @@
 //   gicp_eval_kernel   pairs whose optimiser asked for f at a trial state: one pass over the stored correspondences with the
 //                      residual formed exactly as PCL forms it (float32 T(x)*p, float subtraction) -> 13 sums per tile.
 //   gicp_ctrl_kernel   again.
+// (Tried and dropped, B200, 64 pairs per step: a separate search kernel in which one thread handles 2/3/4 consecutive points
+// and passes each result on as a hint for the next — 10.1 / 11.6 / 13.0 ms per step against 8.6 ms: the saved instructions
+// do not make up for the probe latency that fewer threads in flight can hide.)
 // Because every float operation that PCL's decisions depend on is mirrored and the double sums differ only in order, the
 // GPU follows the oracle's iterate sequence (same inner/outer iteration counts, bit-identical poses in the test-suite).
 // Reductions use fixed trees: results are bit-reproducible run to run and independent of batch composition.

@@ -109,23 +109,34 @@ __device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int
 }
 
 // Exact 1-NN.  cutoff2: distances above it are of no interest (search may stop once the block covers that radius);
-// hint_pos: sorted position of a candidate whose distance bounds the search (previous correspondence) or kNoIndex.
-__device__ __forceinline__ NNResult nn_search(const GridView& g, float qx, float qy, float qz, float cutoff2, uint32_t hint_pos) {
+// hint_pos / hint2_pos: sorted positions of candidates whose distance bounds the search (the previous correspondence of this
+// query, the fresh result of the neighbouring query) or kNoIndex.  Hints only steer the level and the pruning; the result is
+// the exact nearest neighbour either way.
+__device__ __forceinline__ NNResult nn_search(const GridView& g, float qx, float qy, float qz, float cutoff2, uint32_t hint_pos,
+                                              uint32_t hint2_pos = kNoIndex) {
   NNResult best{INFINITY, kNoIndex, kNoIndex, INFINITY};
   if (g.n == 0 || g.cap == 0) return best;
   const float ux = clamp_coord(grid_coord(qx, g.ox, g.inv_h0));
   const float uy = clamp_coord(grid_coord(qy, g.oy, g.inv_h0));
   const float uz = clamp_coord(grid_coord(qz, g.oz, g.inv_h0));
   int L = 0;
-  if (hint_pos < g.n) {
-    const float4 v = __ldg(g.pts + hint_pos);
-    const float d2 = dist2_pcl(qx, qy, qz, v.x, v.y, v.z);
-    if (d2 == d2) {  // not NaN
-      best.d2 = d2; best.idx = __float_as_uint(v.w); best.pos = hint_pos;
-      const float need = fminf(d2, cutoff2);
-      int cx, cy, cz;
-      while (L < g.nlev - 1 && block_guarantee2(g, ux, uy, uz, L, cx, cy, cz) < need) ++L;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t hp = h == 0 ? hint_pos : hint2_pos;
+    if (hp < g.n && hp != best.pos) {
+      const float4 v = __ldg(g.pts + hp);
+      const float d2 = dist2_pcl(qx, qy, qz, v.x, v.y, v.z);
+      const uint32_t id = __float_as_uint(v.w);
+      if (d2 == d2) {  // not NaN
+        if (cand_less(d2, id, best.d2, best.idx)) { best.lb2 = fminf(best.lb2, best.d2); best.d2 = d2; best.idx = id; best.pos = hp; }
+        else best.lb2 = fminf(best.lb2, d2);
+      }
     }
+  }
+  if (best.pos != kNoIndex) {
+    const float need = fminf(best.d2, cutoff2);
+    int cx, cy, cz;
+    while (L < g.nlev - 1 && block_guarantee2(g, ux, uy, uz, L, cx, cy, cz) < need) ++L;
   }
   for (;; ++L) {
     int cx, cy, cz;
