@@ -126,10 +126,8 @@ __device__ __forceinline__ bool certified_same_nn(const GridView& g, float3 q, f
   return true;
 }
 
-#ifndef S3D_ITER_MINBLOCKS
-#define S3D_ITER_MINBLOCKS 1
-#endif
-__global__ void __launch_bounds__(kIterTile, S3D_ITER_MINBLOCKS) gicp_iter_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
+// (register allocation: the compiler's own choice — 64 registers, 4 CTAs/SM — beat forced 5/6/7 CTAs/SM on B200)
+__global__ void __launch_bounds__(kIterTile) gicp_iter_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
                                                               const float4* __restrict__ moved,
                                                               uint32_t* __restrict__ prev_nn, float* __restrict__ sec_lb, uint32_t* __restrict__ corr,
                                                               double* __restrict__ mahal, double* __restrict__ moments) {

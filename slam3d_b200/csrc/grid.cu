@@ -32,7 +32,10 @@ __global__ void grid_params_kernel(SlotInfo* __restrict__ slots, uint32_t n_slot
     return;
   }
   const float span = ext * 1.001f + 1e-6f;
-  float h0 = leaf_hint > 0.f ? 3.0f * leaf_hint : span / 1024.f;
+#ifndef S3D_H0_FACTOR
+#define S3D_H0_FACTOR 3.0f
+#endif
+  float h0 = leaf_hint > 0.f ? S3D_H0_FACTOR * leaf_hint : span / 1024.f;  // finest cell = 3 voxel leaves (swept 2..4 on B200)
   int nlev = 1;
   while (nlev < kMaxLevels && h0 * (float)(1 << nlev) <= span) ++nlev;
   if (h0 * (float)(1 << nlev) <= span) h0 = span / (float)(1 << nlev);

@@ -76,14 +76,17 @@ __global__ void __launch_bounds__(kKnnThreads, S3D_KNN_MINBLOCKS) knn_cov_kernel
   const float uz = clamp_coord(grid_coord(qv.z, g.oz, g.inv_h0));
 
   KSTAT(0, 1);
-  // ---- start level: smallest L whose parent cell (level L+1) already holds >= 12 points ------------------------------
+  // ---- start level: smallest L whose parent cell (level L+1) already holds >= 20 points (swept 8..40 on B200) ------------------------------
   int L = g.nlev - 1;
   {
     const int c0x = (int)floorf(ux), c0y = (int)floorf(uy), c0z = (int)floorf(uz);
     for (int lv = 1; lv < g.nlev; ++lv) {
       uint32_t b, e;
       KSTAT(7, 1);
-      if (cell_range(g.table, g.cap, g.nlev, lv, c0x >> lv, c0y >> lv, c0z >> lv, b, e) && (e - b) >= 12u) { L = lv - 1; break; }
+#ifndef S3D_KNN_START
+#define S3D_KNN_START 20u
+#endif
+      if (cell_range(g.table, g.cap, g.nlev, lv, c0x >> lv, c0y >> lv, c0z >> lv, b, e) && (e - b) >= S3D_KNN_START) { L = lv - 1; break; }
     }
   }
 
