@@ -656,6 +656,8 @@ static bool gicp_register(const std::vector<P4>& pcl_source, const std::vector<P
   return true;
 }
 
+#include "ndt_oracle.inc"  // NDT branch (PointCloudSensor.cpp:84-117)
+
 // ------------------------------------------------------------------------------------------------
 // slam3d align()   (PointCloudSensor.cpp:119-174)
 // ------------------------------------------------------------------------------------------------
@@ -726,9 +728,7 @@ static int align_impl(const P4* src, size_t nsrc, const P4* tgt, size_t ntgt, co
     case S3D_ALG_NDT_OMP:
       g_err = "OMP is not available, you need to rebuild SLAM3D with OMP or use another matching algorithm.";
       return res.status = S3D_UNKNOWN_ALGORITHM;
-    case S3D_ALG_NDT:
-      g_err = "NDT is outside the scope of this oracle (SURVEY 8f rank 4).";
-      return res.status = S3D_UNKNOWN_ALGORITHM;
+    case S3D_ALG_NDT: break;
     default:
       g_err = "Unknown registration algorithm specified.";
       return res.status = S3D_UNKNOWN_ALGORITHM;
@@ -736,6 +736,14 @@ static int align_impl(const P4* src, size_t nsrc, const P4* tgt, size_t ntgt, co
   M4f guess_f;
   for (int i = 0; i < 16; ++i) guess_f.m[i] = static_cast<float>(guess[i]);  // guess.matrix().cast<float>()  :70
   GicpOutput out{};
+  const bool ndt = cfg.registration_algorithm == S3D_ALG_NDT;
+  if (ndt) {
+    // ndt.setInputSource(target); ndt.setInputTarget(source);   :99-100
+    NdtOutput no{};
+    if (!ndt_register(ftgt, fsrc, guess_f, cfg, no)) return res.status = S3D_INTERNAL_ERROR;
+    out.final_T = no.final_T; out.converged = no.converged; out.outer_iterations = no.outer_iterations;
+    out.inner_iterations = no.inner_iterations; out.n_corr = no.n_corr; out.fitness = no.fitness;
+  } else
   // icp.setInputSource(target); icp.setInputTarget(source);   :68-69
   if (!gicp_register(ftgt, fsrc, guess_f, cfg, out)) return res.status = S3D_INTERNAL_ERROR;
   for (int i = 0; i < 16; ++i) res.T[i] = static_cast<double>(out.final_T.m[i]);  // Isometry3f -> Transform  :80
@@ -745,7 +753,7 @@ static int align_impl(const P4* src, size_t nsrc, const P4* tgt, size_t ntgt, co
   res.inner_iterations = out.inner_iterations;
   res.n_correspondences = out.n_corr;
   if (!out.converged || out.fitness > cfg.max_fitness_score) {  // :74-77
-    g_err = "ICP failed with Fitness-Score " + std::to_string(out.fitness) + " > " + std::to_string(cfg.max_fitness_score);
+    g_err = std::string(ndt ? "NDT" : "ICP") + " failed with Fitness-Score " + std::to_string(out.fitness) + " > " + std::to_string(cfg.max_fitness_score);
     return res.status = S3D_NOT_CONVERGED;
   }
   double ginv[16], delta[16];  // :167-172
@@ -1006,3 +1014,32 @@ int s3d_oracle_build_map(const s3d_cloud* clouds, const double* poses, int n, do
 
 }  // extern "C"
 
+
+extern "C" {
+// Test hook: NDT score, gradient and Hessian (row-major) of `source` against the voxel grid of `target` at the state x
+// (the cloud is transformed by convertTransform(x) as computeStepLengthMT does), for finite-difference checks.
+int s3d_oracle_test_ndt_derivatives(s3d_cloud target, s3d_cloud source, float resolution, double outlier_ratio, const double x[6],
+                                    double* score, double g[6], double H[36], uint32_t* n_leaves) {
+  std::vector<P4> tgt(reinterpret_cast<const P4*>(target.xyzw), reinterpret_cast<const P4*>(target.xyzw) + target.n);
+  std::vector<P4> src(reinterpret_cast<const P4*>(source.xyzw), reinterpret_cast<const P4*>(source.xyzw) + source.n);
+  NdtGrid G;
+  ndt_build_grid(tgt, resolution, G);
+  if (n_leaves) *n_leaves = static_cast<uint32_t>(G.leaves.size());
+  NdtProblem P;
+  P.input = &src; P.grid = &G;
+  std::memset(&P.S, 0, sizeof P.S);
+  const double res = static_cast<double>(resolution);
+  const double c1 = 10.0 * (1 - outlier_ratio), c2 = outlier_ratio / std::pow(res, 3), d3 = -std::log(c2);
+  P.S.gauss_d1 = -std::log(c1 + c2) - d3;
+  P.S.gauss_d2 = -2 * std::log((-std::log(c1 * std::exp(-0.5) + c2) - d3) / P.S.gauss_d1);
+  P.S.r2 = static_cast<float>(res * res);
+  for (int r = 0; r < 3; ++r) P.S.pj[r][r] = 1.0;
+  const M4f T = ndt_convert_transform(x);
+  std::vector<P4> tc(src.size());
+  for (size_t i = 0; i < src.size(); ++i) tc[i] = transform_se3(T, src[i]);
+  double gg[6], HH[6][6];
+  *score = ndt_compute_derivatives(P, gg, HH, tc, x, true);
+  for (int i = 0; i < 6; ++i) { g[i] = gg[i]; for (int j = 0; j < 6; ++j) H[6 * i + j] = HH[i][j]; }
+  return S3D_OK;
+}
+}

@@ -8,6 +8,7 @@
 // There is NO CPU fallback: without a CUDA device every entry point returns S3D_INTERNAL_ERROR.
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -142,8 +143,10 @@ static void align_chunk_body(Workspace& ws, const std::vector<const float*>& clo
   const float leaf = cfg.point_cloud_density > 0 ? (float)cfg.point_cloud_density : 0.f;  // :127, setLeafSize(float)
   run_voxel(ws, leaf);
   const bool gicp = cfg.registration_algorithm == S3D_ALG_GICP;
+  const bool ndt = cfg.registration_algorithm == S3D_ALG_NDT;
   const bool k_ok = cfg.correspondence_randomness >= 1 && cfg.correspondence_randomness <= kMaxK;
-  if (!gicp || !k_ok) {
+  const bool ndt_ok = cfg.resolution > 0.f && std::isfinite(cfg.resolution);
+  if (!(gicp && k_ok) && !(ndt && ndt_ok)) {
     // the reference evaluates the <100 gate before the algorithm switch (:134-135 then :139-165)
     SlotInfo* hs = ws.h_slots.as<SlotInfo>();
     S3D_CUDA(cudaMemcpyAsync(hs, ws.slots.p, sizeof(SlotInfo) * ws.n_slots, cudaMemcpyDeviceToHost, ws.stream));
@@ -154,16 +157,21 @@ static void align_chunk_body(Workspace& ws, const std::vector<const float*>& clo
       for (int j = 0; j < 16; ++j) out[i].T[j] = (j % 5 == 0) ? 1.0 : 0.0;
       out[i].n_source = hs[2 * i].n_pts; out[i].n_target = hs[2 * i + 1].n_pts;
       if (out[i].n_source < 100 || out[i].n_target < 100) out[i].status = S3D_TOO_FEW_POINTS;
-      else out[i].status = gicp ? S3D_INVALID_ARGUMENT : S3D_UNKNOWN_ALGORITHM;
+      else out[i].status = (gicp || ndt) ? S3D_INVALID_ARGUMENT : S3D_UNKNOWN_ALGORITHM;
     }
     if (gicp) set_error("correspondence_randomness must be in [1, 200] on the GPU path");
+    else if (ndt) set_error("NDT resolution must be positive");
     else if (cfg.registration_algorithm == S3D_ALG_GICP_OMP || cfg.registration_algorithm == S3D_ALG_NDT_OMP)
       set_error("OMP is not available, you need to rebuild SLAM3D with OMP or use another matching algorithm.");
-    else if (cfg.registration_algorithm == S3D_ALG_NDT) set_error("NDT is not implemented by the B200 path (SURVEY 8f rank 4).");
     else set_error("Unknown registration algorithm specified.");
     return;
   }
   run_grid(ws, leaf);
+  if (ndt) {  // doNDT  :84-117
+    std::vector<s3d_registration_parameters> params(n, cfg);
+    run_ndt(ws, params, guesses, out);
+    return;
+  }
   run_knn_covariances(ws, cfg.correspondence_randomness, nullptr, nullptr);
   std::vector<s3d_registration_parameters> params(n, cfg);
   run_gicp(ws, params, guesses, out);
@@ -173,7 +181,8 @@ static const char* status_text(int st, const s3d_result& r, const s3d_registrati
   switch (st) {
     case S3D_TOO_FEW_POINTS: return "Too few points after filtering, you may have to decrease 'point_cloud_density'.";
     case S3D_NOT_CONVERGED:
-      buf = "ICP failed with Fitness-Score " + std::to_string(r.fitness) + " > " + std::to_string(cfg.max_fitness_score);
+      buf = std::string(cfg.registration_algorithm == S3D_ALG_NDT ? "NDT" : "ICP") + " failed with Fitness-Score " + std::to_string(r.fitness) + " > " +
+            std::to_string(cfg.max_fitness_score);
       return buf.c_str();
     case S3D_TOO_FAR_FROM_GUESS: return "ICP result is to far away from guess";
     default: return nullptr;
@@ -525,7 +534,8 @@ static void align_prepared_chunk(s3d_context* ctx, int slot, const s3d_prepared_
     S3D_CUDA(cudaStreamSynchronize(ws.stream));
     if (cfg.registration_algorithm == S3D_ALG_GICP_OMP || cfg.registration_algorithm == S3D_ALG_NDT_OMP)
       set_error("OMP is not available, you need to rebuild SLAM3D with OMP or use another matching algorithm.");
-    else if (cfg.registration_algorithm == S3D_ALG_NDT) set_error("NDT is not implemented by the B200 path (SURVEY 8f rank 4).");
+    else if (cfg.registration_algorithm == S3D_ALG_NDT)
+      set_error("NDT voxelises the filtered source scan itself: use s3d_gicp_align / s3d_gicp_align_batch (prepared clouds hold GICP data only).");
     else set_error("Unknown registration algorithm specified.");
     return;
   }

@@ -501,6 +501,8 @@ static double rotation_angle(const double T[16]) {
   return 2.0 * atan2(sqrt(x * x + y * y + z * z), fabs(w));
 }
 
+double rotation_angle_of(const double T[16]) { return rotation_angle(T); }  // shared with ndt.cu
+
 void check_arena(Workspace& ws, const int32_t* h_flags) {
   if (h_flags[0] & kErrHashArena) throw ArenaOverflow{(size_t)h_flags[3] + (size_t)h_flags[3] / 8 + 64};
 }

@@ -117,6 +117,7 @@ struct Workspace {
   uint32_t iter_tiles = 0;
   DevBuf fit_partial;                         // double[iter_tiles*2]
   DevBuf accu, accu2, map_aux;                // map building: accumulated cloud, filtered cloud, poses / keep flags
+  DevBuf ndt_pairs, ndt_leaves, ndt_hash, ndt_part;  // NDT: NdtPair[n_pairs], NdtLeaf[], uint2 hash arena, double[tiles * 44]
   DevBuf flags;                               // int32[16]: [0] error bits, [1] active pairs, [2] hash entries used, [3] entries needed, [8] long voxel runs, [9] kept points
   PinnedBuf h_slots, h_pairs, h_small, h_tiles;  // pinned host mirrors
   uint64_t launches = 0, h2d = 0, d2h = 0;
@@ -162,5 +163,6 @@ uint32_t run_accumulate(Workspace& ws, const std::vector<const float*>& clouds, 
 uint32_t run_radius_filter(Workspace& ws, const float4* dev_in, uint32_t n, double radius, unsigned min_pts, float4* dev_out);
 void check_arena(Workspace& ws, const int32_t* h_flags);  // throws ArenaOverflow when the grid build flagged it (h_flags: synchronised copy)
 void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& params, const double* guesses, s3d_result* out);
+void run_ndt(Workspace& ws, const std::vector<s3d_registration_parameters>& params, const double* guesses, s3d_result* out);  // ndt.cu
 
 }  // namespace s3d

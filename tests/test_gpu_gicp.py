@@ -84,7 +84,7 @@ def test_gates_match_oracle(ctx, oracle_mod, kitti):
         check(ctx.gicp_align(src, tgt, None, p), oracle_mod.gicp_align(src, tgt, None, p))
     r = ctx.gicp_align(src[:500], tgt[:500], None, RegistrationParameters.defaults(point_cloud_density=20.0))
     assert r.status == _abi.S3D_TOO_FEW_POINTS
-    for alg in (_abi.ALG_ICP, _abi.ALG_GICP_OMP, _abi.ALG_NDT, _abi.ALG_NDT_OMP, 17):
+    for alg in (_abi.ALG_ICP, _abi.ALG_GICP_OMP, _abi.ALG_NDT_OMP, 17):  # ALG_NDT runs: tests/test_gpu_ndt.py
         r = ctx.gicp_align(src, tgt, None, RegistrationParameters.defaults(point_cloud_density=0.5, registration_algorithm=alg))
         assert r.status == _abi.S3D_UNKNOWN_ALGORITHM
     # too few points wins over the algorithm switch (:134 before :139)

@@ -15,8 +15,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def host():
+def load_host():
     import slam3d_b200
     slam3d_b200.lib()
     lib = C.CDLL(os.path.join(ROOT, "slam3d_b200", "libs3d_host.so"))
@@ -35,6 +34,11 @@ def host():
     lib.s3dhost_cache_hits.restype = C.c_uint64
     lib.s3dhost_run_odometry.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
     return lib
+
+
+@pytest.fixture(scope="module")
+def host():
+    return load_host()
 
 
 def cm(T):

@@ -14,8 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def hm():
     src = os.path.join(ROOT, "tests", "hostmath.cpp")
     out = os.path.join(ROOT, "tests", "_hostmath.so")
-    hdr = os.path.join(ROOT, "slam3d_b200", "csrc", "gicp_math.h")
-    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "slam3d_b200", "csrc", h) for h in ("gicp_math.h", "ndt_math.h")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", out, src])
     lib = C.CDLL(out)
     return lib
