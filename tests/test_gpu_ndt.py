@@ -77,9 +77,10 @@ def test_gates_match_oracle(ctx, oracle_mod, kitti):
     assert r.status == _abi.S3D_NOT_CONVERGED and r.outer_iterations == 0 and np.array_equal(r.pose(), np.eye(4))
     r = ctx.gicp_align(src[:500], tgt[:500], None, ndt_params(point_cloud_density=20.0))
     assert r.status == _abi.S3D_TOO_FEW_POINTS
-    r = ctx.gicp_align(src, tgt, None, ndt_params(resolution=0.0))
-    assert r.status == _abi.S3D_INVALID_ARGUMENT
-    r = ctx.gicp_align(src, tgt, None, ndt_params(registration_algorithm=_abi.ALG_NDT_OMP))
+    import slam3d_b200
+    with pytest.raises(slam3d_b200.S3DError, match="resolution must be positive"):
+        ctx.gicp_align(src, tgt, None, ndt_params(resolution=0.0))
+    r = ctx.gicp_align(src, tgt, None, RegistrationParameters.defaults(registration_algorithm=_abi.ALG_NDT_OMP))
     assert r.status == _abi.S3D_UNKNOWN_ALGORITHM
 
 
