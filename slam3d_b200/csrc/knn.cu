@@ -130,22 +130,34 @@ __global__ void __launch_bounds__(kKnnThreads, S3D_KNN_MINBLOCKS) knn_cov_kernel
       KSTAT(2, 1);
       if (!cell_range_key(g.table, g.cap, key, L, begin, end)) continue;
       KSTAT(4, end - begin);
-      for (uint32_t p = begin; p < end; ++p) {
-        const float4 v = __ldg(g.pts + p);
-        const float cd = dist2_pcl(qv.x, qv.y, qv.z, v.x, v.y, v.z);
-        if (!(cd == cd)) continue;  // NaN never enters
-        const uint64_t ck = ((uint64_t)__float_as_uint(cd) << 32) | (uint64_t)__float_as_uint(v.w);
-        if (cnt < kk) {
-          if (ck <= bound) {  // fill phase: append, and heapify once when the k-th candidate arrives
-            h[cnt * kKnnThreads] = ck; ++cnt; KSTAT(5, 1);
-            if (cnt == kk) {
-              for (int i = kk / 2 - 1; i >= 0; --i) heap_sift_down(h, kk, h[i * kKnnThreads], i);
-              tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
+#ifndef S3D_KNN_BATCH
+#define S3D_KNN_BATCH 4
+#endif
+      // S3D_KNN_BATCH points are fetched before the first of them is examined, so their load latencies overlap
+      // (B200, 32 pairs per step: 4.41 / 4.30 / 4.06 ms for batches of 1 / 2 / 4)
+      for (uint32_t p0 = begin; p0 < end; p0 += S3D_KNN_BATCH) {
+        float4 vb[S3D_KNN_BATCH];
+#pragma unroll
+        for (int u = 0; u < S3D_KNN_BATCH; ++u) vb[u] = __ldg(g.pts + min(p0 + u, end - 1));
+#pragma unroll
+        for (int u = 0; u < S3D_KNN_BATCH; ++u) {
+          if (u > 0 && p0 + u >= end) break;
+          const float4 v = vb[u];
+          const float cd = dist2_pcl(qv.x, qv.y, qv.z, v.x, v.y, v.z);
+          if (!(cd == cd)) continue;  // NaN never enters
+          const uint64_t ck = ((uint64_t)__float_as_uint(cd) << 32) | (uint64_t)__float_as_uint(v.w);
+          if (cnt < kk) {
+            if (ck <= bound) {  // fill phase: append, and heapify once when the k-th candidate arrives
+              h[cnt * kKnnThreads] = ck; ++cnt; KSTAT(5, 1);
+              if (cnt == kk) {
+                for (int i = kk / 2 - 1; i >= 0; --i) heap_sift_down(h, kk, h[i * kKnnThreads], i);
+                tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
+              }
             }
+          } else if (ck < tau) {
+            heap_sift_down(h, kk, ck); KSTAT(6, 1);
+            tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
           }
-        } else if (ck < tau) {
-          heap_sift_down(h, kk, ck); KSTAT(6, 1);
-          tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
         }
       }
     }
