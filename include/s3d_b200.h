@@ -101,7 +101,12 @@ int s3d_voxel_downsample(s3d_context* ctx, s3d_cloud in, float leaf, float* out_
                          uint32_t* leaf_index, int32_t* overflow);
 
 /* align(source, target, guess, config) — PointCloudSensor.cpp:119-174.  Always fills *out (status inside
- * is the same value as the return code). */
+ * is the same value as the return code).  registration_algorithm selects the branch of the reference's switch (:139-165):
+ *   GICP  doICP<pcl::GeneralizedIterativeClosestPoint>  (:52-82)
+ *   NDT   doNDT<pcl::NormalDistributionsTransform>      (:84-117): resolution, step_size, outlier_ratio, maximum_iterations,
+ *         transformation_epsilon are read; out->outer_iterations = nr_iterations_, out->inner_iterations = More-Thuente
+ *         line-search iterations, out->n_correspondences = (point, voxel) pairs of the last evaluation
+ *   GICP_OMP / NDT_OMP / anything else -> S3D_UNKNOWN_ALGORITHM with the reference's two messages (:158-164). */
 int s3d_gicp_align(s3d_context* ctx, s3d_cloud source, s3d_cloud target, const double guess[16],
                    const s3d_registration_parameters* params, s3d_result* out);
 
@@ -147,6 +152,8 @@ int s3d_prepare_clouds(s3d_context* ctx, int device_slot, const s3d_cloud* cloud
                        s3d_prepared_cloud** out);
 int s3d_release_cloud(s3d_context* ctx, s3d_prepared_cloud* cloud);
 uint64_t s3d_prepared_cloud_size(const s3d_prepared_cloud* cloud); /* points after filtering */
+/* Prepared clouds carry GICP data (Morton-sorted points, normals, NN grid); an NDT request on them returns
+ * S3D_UNKNOWN_ALGORITHM with a message pointing at s3d_gicp_align(_batch), which voxelises the filtered source itself. */
 int s3d_gicp_align_prepared(s3d_context* ctx, const s3d_prepared_cloud* source, const s3d_prepared_cloud* target,
                             const double guess[16], const s3d_registration_parameters* params, s3d_result* out);
 int s3d_gicp_align_prepared_batch(s3d_context* ctx, const s3d_prepared_cloud* const* sources,
@@ -168,8 +175,9 @@ int s3d_build_map(s3d_context* ctx, const s3d_cloud* clouds, const double* poses
                   unsigned outlier_neighbors, double resolution, float* out_xyzw, uint64_t* n_out);
 
 /* Optional per-stage device timing (CUDA events on the launching stream, read back at the call's final
- * synchronisation).  Stage ids: 0 voxel filter, 1 NN grid build, 2 kNN+covariances, 3 GICP correspondence/
- * linearisation kernel, 4 GICP solve kernel, 5 fitness.  ms[i] / launches[i] accumulate since the last reset. */
+ * synchronisation).  Stage ids: 0 voxel filter, 1 NN grid build, 2 kNN+covariances (NDT: the target's Gaussian voxel
+ * grid), 3 GICP correspondence/linearisation kernel (NDT: derivative evaluation), 4 GICP solve kernel (NDT: line-search
+ * control), 5 fitness.  ms[i] / launches[i] accumulate since the last reset. */
 #define S3D_N_STAGES 6
 int s3d_set_profiling(s3d_context* ctx, int enabled);
 int s3d_get_stage_times(s3d_context* ctx, double ms[S3D_N_STAGES], uint64_t launches[S3D_N_STAGES], int reset);
