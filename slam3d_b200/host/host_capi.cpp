@@ -121,4 +121,33 @@ int s3dhost_run_odometry(void* s, const float* const* scans, const uint64_t* siz
   return (int)all[0].size();
 }
 
+// BASELINE configs[4] (trajectory): n scans through addMeasurement(m, odom) + linkLastToNeighbors() after every new vertex.
+// edges_out: per recorded edge {source, target, loop} as 3 ints followed by nothing; T_out: 16 doubles per edge (relative pose);
+// poses_out: n x 16 doubles (corrected poses).  Returns the number of edges (<= max_edges) or -1.
+int s3dhost_run_trajectory(void* s, const float* const* scans, const uint64_t* sizes, int n, const double* odoms, double neighbor_radius,
+                           int max_links, int min_loop_length, int max_edges, int* edges_out, double* T_out, double* poses_out, int* n_warnings) {
+  PointCloudSensor* sensor = static_cast<PointCloudSensor*>(s);
+  try {
+    MiniHost host(sensor);
+    host.setNeighborRadius((float)neighbor_radius, max_links);
+    host.setMinLoopLength((unsigned)min_loop_length);
+    for (int i = 0; i < n; ++i) {
+      Measurement::Ptr m(new PointCloudMeasurement(makeCloud(scans[i], sizes[i]), "robot", sensor->getName(), Transform()));
+      if (host.addMeasurement(m, makeTransform(odoms + 16 * i))) host.linkLastToNeighbors();
+    }
+    const int ne = (int)std::min<size_t>(host.edges.size(), (size_t)max_edges);
+    for (int e = 0; e < ne; ++e) {
+      edges_out[3 * e] = (int)host.edges[e].source; edges_out[3 * e + 1] = (int)host.edges[e].target; edges_out[3 * e + 2] = host.edges[e].loop ? 1 : 0;
+      for (int i = 0; i < 16; ++i) T_out[16 * e + i] = host.edges[e].relative.m[i];
+    }
+    if (poses_out) for (int v = 0; v < n; ++v) for (int i = 0; i < 16; ++i) poses_out[16 * v + i] = host.correctedPose((unsigned)v).m[i];
+    if (n_warnings) *n_warnings = (int)host.warnings.size();
+    g_msg = host.warnings.empty() ? "" : host.warnings.back();
+    return ne;
+  } catch (std::exception& e) {
+    g_msg = e.what();
+    return -1;
+  }
+}
+
 }  // extern "C"

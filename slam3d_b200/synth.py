@@ -86,13 +86,40 @@ def make_pose(t, rpy):
     return T
 
 
-def scan(scene, pose, rng, noise=0.02):
-    """One scan taken at `pose` (4x4 sensor->world). Returns (131072, 3) float32 points in the sensor frame."""
+def scan(scene, pose, rng, noise=0.02, azimuth_stride=1):
+    """One scan taken at `pose` (4x4 sensor->world). Returns (131072 / azimuth_stride, 3) float32 points in the sensor frame."""
     d_local = beam_directions()
+    if azimuth_stride > 1:
+        d_local = d_local.reshape(N_BEAMS, N_AZIMUTH, 3)[:, ::azimuth_stride].reshape(-1, 3)
     d_world = d_local @ pose[:3, :3].T
     rng_m = scene.cast(pose[:3, 3], d_world)
     rng_m = rng_m + rng.normal(0.0, noise, rng_m.shape)
     return (d_local * rng_m[:, None]).astype(np.float32)
+
+
+def ranges(scene, pose):
+    """Noise-free ranges of the 131072 beams at `pose` (for trajectories that revisit poses: cast once, add noise per visit)."""
+    return scene.cast(pose[:3, 3], beam_directions() @ pose[:3, :3].T).astype(np.float32)
+
+
+def scan_from_ranges(rng_m, rng, noise=0.02):
+    return (beam_directions() * (rng_m.astype(np.float64) + rng.normal(0.0, noise, rng_m.shape))[:, None]).astype(np.float32)
+
+
+def figure_eight_poses(n, radius=1.5, step=0.7, lateral=0.0):
+    """closed figure-eight (two tangent circles of `radius` around the origin, inside the scene's free zone),
+    `step` metres per frame, heading along the path; `lateral` shifts the whole lap sideways (a second visit of a place)."""
+    poses = []
+    for i in range(n):
+        u = (i * step / radius) % (4 * np.pi)
+        if u < 2 * np.pi:
+            x, y, yaw = radius * np.sin(u), radius * (1 - np.cos(u)), u
+        else:
+            v = u - 2 * np.pi
+            x, y, yaw = radius * np.sin(v), -radius * (1 - np.cos(v)), -v
+        # sideways offset along the path normal
+        poses.append(make_pose([x - lateral * np.sin(yaw), y + lateral * np.cos(yaw), 0.0], [0.0, 0.0, yaw]))
+    return poses
 
 
 def odometry_motion(rng):

@@ -186,3 +186,46 @@ def test_host_build_map(host, oracle_mod, kitti):
     want = oracle_mod.build_map(kitti, poses, 0.2, 3, 0.1)
     assert m == want.shape[0] and np.array_equal(out[:m].view(np.uint32), want.view(np.uint32))
     host.s3dhost_sensor_destroy(sensor)
+
+
+def test_minihost_trajectory_links_to_neighbors(host):
+    """BASELINE configs[4] in small: a closed figure-eight through addMeasurement(m, odom) + linkLastToNeighbors()
+    (ScanSensor.cpp:94-135, :170-213): consecutive scans are linked through the odometry guess, revisited places get loop
+    edges (coarse + fine align, guess = relative pose in the recorded graph), every edge agrees with the true motion."""
+    from slam3d_b200 import synth
+    import slam3d_b200
+    host.s3dhost_run_trajectory.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    lap, radius = 20, 0.8
+    step = 4 * np.pi * radius / lap
+    n = lap + 4
+    truth = synth.figure_eight_poses(n, radius, step)
+    scene = synth.Scene(3)
+    rng = np.random.default_rng(3)
+    scans = [slam3d_b200.as_xyzw(synth.scan(scene, p, rng, azimuth_stride=8)) for p in truth]
+    odoms = [np.linalg.inv(truth[0]) @ p for p in truth]
+    sensor = host.s3dhost_sensor_create(b"velodyne")
+    fine = RegistrationParameters.defaults(point_cloud_density=0.2)
+    coarse = RegistrationParameters.defaults(point_cloud_density=0.5, max_correspondence_distance=5.0)
+    host.s3dhost_sensor_set_params(sensor, C.byref(fine), 0)
+    host.s3dhost_sensor_set_params(sensor, C.byref(coarse), 1)
+    ptrs = (C.c_void_p * n)(*[s.ctypes.data for s in scans])
+    sizes = (C.c_uint64 * n)(*[s.shape[0] for s in scans])
+    od = np.ascontiguousarray(np.stack([o.T for o in odoms]))
+    edges = np.zeros((4 * n, 3), np.int32); T = np.zeros((4 * n, 16)); poses = np.zeros((n, 16)); nw = C.c_int(0)
+    ne = host.s3dhost_run_trajectory(sensor, ptrs, sizes, n, od.ctypes.data, 1.0, 1, 10, 4 * n, edges.ctypes.data, T.ctypes.data,
+                                     poses.ctypes.data, C.byref(nw))
+    assert ne >= n - 1, host.s3dhost_last_message()
+    edges = edges[:ne]; T = T[:ne].reshape(ne, 4, 4).transpose(0, 2, 1)
+    odo = edges[edges[:, 2] == 0]
+    assert len(odo) == n - 1 and np.array_equal(odo[:, 0] + 1, odo[:, 1])       # every scan linked to its predecessor
+    loops = edges[edges[:, 2] == 1]
+    assert len(loops) >= 3                                                        # the crossing and the second visit of the start
+    assert all(abs(int(t) - int(s)) >= 10 for s, t, _ in loops)                   # mMinLoopLength in graph hops
+    for (s, t, _), rel in zip(edges, T):
+        dt, dr = pose_delta(np.linalg.inv(truth[s]) @ truth[t], rel)
+        assert dt < 0.05 and dr < 0.01, (s, t, dt, dr)
+    P = poses.reshape(n, 4, 4).transpose(0, 2, 1)
+    dt, _ = pose_delta(np.linalg.inv(truth[0]) @ truth[-1], P[-1])              # chained corrected poses follow the path
+    assert dt < 0.2
+    host.s3dhost_sensor_destroy(sensor)
