@@ -16,7 +16,10 @@
 //   gicp_ctrl_kernel   again.
 // (Tried and dropped, B200, 64 pairs per step: a separate search kernel in which one thread handles 2/3/4 consecutive points
 // and passes each result on as a hint for the next — 10.1 / 11.6 / 13.0 ms per step against 8.6 ms: the saved instructions
-// do not make up for the probe latency that fewer threads in flight can hide.)
+// do not make up for the probe latency that fewer threads in flight can hide.  Also tried and dropped: splitting this kernel
+// into a barrier-free search kernel (CTAs of 32 / 64 / 128 / 256 threads) and a separate 74-sum tile kernel, because 37 % of the
+// stall samples of a late-iteration launch sit at the reduction barrier (profiles/r01g_summary.md) — results bit-identical,
+// stage time 4.6-4.9 ms against 4.55 ms fused per 32 pairs: the waiting warps cost no issue slots and the extra launch does.)
 // Because every float operation that PCL's decisions depend on is mirrored and the double sums differ only in order, the
 // GPU follows the oracle's iterate sequence (same inner/outer iteration counts, bit-identical poses in the test-suite).
 // Reductions use fixed trees: results are bit-reproducible run to run and independent of batch composition.
