@@ -60,6 +60,16 @@ def main():
                 "status": r.status, "converged": r.converged, "outer_iterations": r.outer_iterations,
                 "inner_iterations": r.inner_iterations, "n_source": r.n_source, "n_target": r.n_target,
                 "n_correspondences": r.n_correspondences, "fitness": r.fitness, "T": r.pose().tolist()}
+    from slam3d_b200 import _abi  # noqa: E402
+    g["align_ndt"] = {}
+    for density in (0.1, 0.2):  # the NDT branch (PointCloudSensor.cpp:84-117) with slam3d's NDT defaults
+        p = RegistrationParameters.defaults(point_cloud_density=density, registration_algorithm=_abi.ALG_NDT)
+        for a, b in ((0, 1), (1, 2), (2, 3)):
+            r = oracle.gicp_align(clouds[a], clouds[b], None, p)
+            g["align_ndt"][f"cloud{a+1}->cloud{b+1}@{density}"] = {
+                "status": r.status, "converged": r.converged, "outer_iterations": r.outer_iterations,
+                "inner_iterations": r.inner_iterations, "n_source": r.n_source, "n_target": r.n_target,
+                "n_correspondences": r.n_correspondences, "fitness": r.fitness, "T": r.pose().tolist()}
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(g, f, indent=1)
     print(json.dumps(g["align"], indent=1))

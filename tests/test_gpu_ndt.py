@@ -118,3 +118,18 @@ def test_host_mirror_runs_ndt(kitti, oracle_mod):
     st, T, info, msg = th.create_constraint(host, sensor, kitti[0], kitti[1], I, I, I)
     assert st == 1 and "NDT failed with Fitness-Score" in msg
     host.s3dhost_sensor_destroy(sensor)
+
+
+@pytest.mark.parametrize("density", [0.1, 0.2])
+def test_kitti_pairs_vs_golden(ctx, kitti, golden, density):
+    """Committed fixtures (tests/golden/golden.json "align_ndt", frozen oracle outputs on the reference's test/cloud1-4.bin)."""
+    p = ndt_params(point_cloud_density=density)
+    for a, b in ((0, 1), (1, 2), (2, 3)):
+        g = golden["align_ndt"][f"cloud{a+1}->cloud{b+1}@{density}"]
+        r = ctx.gicp_align(kitti[a], kitti[b], None, p)
+        assert r.status == g["status"] and r.converged == g["converged"]
+        assert (r.n_source, r.n_target) == (g["n_source"], g["n_target"])
+        dt, dr = pose_delta(g["T"], r.pose())
+        assert dt < TOL_T and dr < TOL_R, (dt, dr)
+        assert abs(r.fitness - g["fitness"]) <= TOL_FIT * g["fitness"]
+        assert (r.outer_iterations, r.inner_iterations, r.n_correspondences) == (g["outer_iterations"], g["inner_iterations"], g["n_correspondences"])

@@ -166,3 +166,12 @@ def test_svd_solve(hm):
     v = rng.normal(size=(6, 3)); H = v @ v.T; b = H @ rng.normal(size=6); x = np.zeros(6)
     hm.hm_ndt_svd_solve(ptr(np.ascontiguousarray(H)), ptr(b), ptr(x))
     assert np.allclose(x, np.linalg.pinv(H) @ b, rtol=1e-8, atol=1e-10)
+
+
+def test_ndt_golden(oracle_mod, kitti, golden):
+    """The frozen fixture pins the oracle's NDT branch against regressions (it is an oracle output, not a PCL output)."""
+    g = golden["align_ndt"]["cloud1->cloud2@0.2"]
+    r = oracle_mod.gicp_align(kitti[0], kitti[1], None, ndt_params(point_cloud_density=0.2))
+    assert (r.status, r.converged, r.outer_iterations, r.inner_iterations, r.n_correspondences) == (
+        g["status"], g["converged"], g["outer_iterations"], g["inner_iterations"], g["n_correspondences"])
+    assert np.abs(r.pose() - np.array(g["T"])).max() == 0.0 and r.fitness == g["fitness"]
