@@ -116,6 +116,16 @@ int s3d_gicp_align_batch(s3d_context* ctx, const s3d_cloud* sources, const s3d_c
                          const double* guesses, const s3d_registration_parameters* params, int n_pairs,
                          s3d_result* out);
 
+/* n_pairs loop-closure constraints, i.e. the align sequence of createConstraint(source, target, odometry, loop = true)
+ * (PointCloudSensor.cpp:286-292): align with the coarse parameters and `guesses`, then align with the fine parameters and
+ * the coarse result as the guess.  Same results as two s3d_gicp_align_batch calls, but every scan is uploaded once and a
+ * chunk's fine pass overlaps the other chunks' coarse pass.  out_fine[i] is what the caller turns into the edge; when the
+ * coarse align of pair i fails (the reference throws there and never runs the fine align) out_fine[i] = out_coarse[i].
+ * out_coarse may be NULL. */
+int s3d_gicp_align_loop_batch(s3d_context* ctx, const s3d_cloud* sources, const s3d_cloud* targets, const double* guesses,
+                              const s3d_registration_parameters* coarse, const s3d_registration_parameters* fine, int n_pairs,
+                              s3d_result* out_coarse, s3d_result* out_fine);
+
 /* ---- stage-level entry points (used by the parity tests and the bench; same kernels as align) ---------- */
 
 /* GICP computeCovariances: exact kNN (k neighbours, self included, ascending (d2, index)),

@@ -43,6 +43,8 @@ def lib():
         L.s3d_gicp_align.argtypes = [C.c_void_p, Cloud, Cloud, C.c_void_p, C.POINTER(RegistrationParameters), C.POINTER(Result)]
         L.s3d_gicp_align_batch.argtypes = [C.c_void_p, C.POINTER(Cloud), C.POINTER(Cloud), C.c_void_p, C.POINTER(RegistrationParameters),
                                            C.c_int, C.POINTER(Result)]
+        L.s3d_gicp_align_loop_batch.argtypes = [C.c_void_p, C.POINTER(Cloud), C.POINTER(Cloud), C.c_void_p, C.POINTER(RegistrationParameters),
+                                                C.POINTER(RegistrationParameters), C.c_int, C.POINTER(Result), C.POINTER(Result)]
         L.s3d_transform_cloud.argtypes = [C.c_void_p, Cloud, C.c_void_p, C.c_void_p]
         L.s3d_remove_outliers.argtypes = [C.c_void_p, Cloud, C.c_double, C.c_uint, C.c_void_p, C.POINTER(C.c_uint64)]
         L.s3d_build_map.argtypes = [C.c_void_p, C.POINTER(Cloud), C.c_void_p, C.c_int, C.c_double, C.c_uint, C.c_double, C.c_void_p,
@@ -194,6 +196,22 @@ class Context:
         st = lib().s3d_gicp_align_batch(self._h, sc, tc, g.ctypes.data, C.byref(p), n, res)
         self._check(st, "s3d_gicp_align_batch")
         return list(res)
+
+    def gicp_align_loop_batch(self, sources, targets, guesses, coarse, fine):
+        """createConstraint(loop=true) for a batch: coarse align, then fine align from the coarse pose. Returns (coarse, fine)."""
+        n = len(sources)
+        keep = []
+        sc = (Cloud * n)()
+        tc = (Cloud * n)()
+        for i in range(n):
+            a, c = _cloud(sources[i]); keep.append(a); sc[i] = c
+            a, c = _cloud(targets[i]); keep.append(a); tc[i] = c
+        g = np.ascontiguousarray(np.stack([_colmajor(None if guesses is None else guesses[i]) for i in range(n)]))
+        rc = (Result * n)()
+        rf = (Result * n)()
+        st = lib().s3d_gicp_align_loop_batch(self._h, sc, tc, g.ctypes.data, C.byref(coarse), C.byref(fine), n, rc, rf)
+        self._check(st, "s3d_gicp_align_loop_batch")
+        return list(rc), list(rf)
 
 
 class PreparedCloud:

@@ -123,9 +123,12 @@ static void copy_out(Workspace& ws, void* dst, const void* src_dev, size_t bytes
 static void align_chunk_body(Workspace& ws, const std::vector<const float*>& clouds, const std::vector<uint64_t>& sizes, const double* guesses,
                              const s3d_registration_parameters& cfg, int n, s3d_result* out);
 
-// One sub-batch of align() calls on one device.
+// One sub-batch of align() calls on one device.  With `fine` set, the chunk runs createConstraint's loop-closure sequence
+// (PointCloudSensor.cpp:286-292): align with `cfg` (coarse), then align again with `fine` and the coarse result as the guess;
+// the scans are uploaded once and the second pass reads them from the device staging buffer.
 static void align_chunk(s3d_context* ctx, int slot, const s3d_cloud* sources, const s3d_cloud* targets, const double* guesses,
-                        const s3d_registration_parameters& cfg, int n, s3d_result* out) {
+                        const s3d_registration_parameters& cfg, int n, s3d_result* out, const s3d_registration_parameters* fine = nullptr,
+                        s3d_result* out_fine = nullptr) {
   WsLease lease(ctx, slot);
   Workspace& ws = *lease;
   std::vector<const float*> clouds(2 * n);
@@ -135,6 +138,18 @@ static void align_chunk(s3d_context* ctx, int slot, const s3d_cloud* sources, co
     clouds[2 * i + 1] = targets[i].xyzw; sizes[2 * i + 1] = targets[i].n;
   }
   with_arena_retry(ws, [&] { align_chunk_body(ws, clouds, sizes, guesses, cfg, n, out); });
+  if (!fine) return;
+  // second pass: every slot's raw points already sit on the device (user device memory or the staging buffer)
+  SlotInfo* hs = ws.h_slots.as<SlotInfo>();
+  std::vector<const float*> dev(2 * n);
+  for (int s = 0; s < 2 * n; ++s) dev[s] = sizes[s] ? reinterpret_cast<const float*>(hs[s].raw) : nullptr;
+  std::vector<double> g2(16 * (size_t)n);
+  for (int i = 0; i < n; ++i) memcpy(&g2[16 * (size_t)i], out[i].T, sizeof(double) * 16);
+  with_arena_retry(ws, [&] { align_chunk_body(ws, dev, sizes, g2.data(), *fine, n, out_fine); });
+  for (int i = 0; i < n; ++i)
+    if (out[i].status != S3D_OK) {  // the coarse align threw: createConstraint never reaches the fine align (:286-289)
+      out_fine[i] = out[i];
+    }
 }
 
 static void align_chunk_body(Workspace& ws, const std::vector<const float*>& clouds, const std::vector<uint64_t>& sizes, const double* guesses,
@@ -672,8 +687,9 @@ int s3d_build_map(s3d_context* ctx, const s3d_cloud* clouds, const double* poses
   });
 }
 
-int s3d_gicp_align_batch(s3d_context* ctx, const s3d_cloud* sources, const s3d_cloud* targets, const double* guesses,
-                         const s3d_registration_parameters* params, int n_pairs, s3d_result* out) {
+static int align_batch_impl(s3d_context* ctx, const s3d_cloud* sources, const s3d_cloud* targets, const double* guesses,
+                            const s3d_registration_parameters* params, int n_pairs, s3d_result* out, const s3d_registration_parameters* fine,
+                            s3d_result* out_fine) {
   if (!ctx || !params || !out || n_pairs < 0 || (n_pairs > 0 && (!sources || !targets || !guesses))) return S3D_INVALID_ARGUMENT;
   if (n_pairs == 0) return S3D_OK;
   const int nd = (int)ctx->devs.size();
@@ -696,7 +712,7 @@ int s3d_gicp_align_batch(s3d_context* ctx, const s3d_cloud* sources, const s3d_c
         const int b = lo + c * chunk;
         if (b >= hi) break;
         const int n = std::min(chunk, hi - b);
-        align_chunk(ctx, d, sources + b, targets + b, guesses + 16 * (size_t)b, *params, n, out + b);
+        align_chunk(ctx, d, sources + b, targets + b, guesses + 16 * (size_t)b, *params, n, out + b, fine, fine ? out_fine + b : nullptr);
       }
       return S3D_OK;
     });
@@ -711,6 +727,20 @@ int s3d_gicp_align_batch(s3d_context* ctx, const s3d_cloud* sources, const s3d_c
   for (int i = 0; i < nd * W; ++i)
     if (st[i] != S3D_OK) { set_error(errs[i]); return st[i]; }
   return S3D_OK;
+}
+
+int s3d_gicp_align_batch(s3d_context* ctx, const s3d_cloud* sources, const s3d_cloud* targets, const double* guesses,
+                         const s3d_registration_parameters* params, int n_pairs, s3d_result* out) {
+  return align_batch_impl(ctx, sources, targets, guesses, params, n_pairs, out, nullptr, nullptr);
+}
+
+int s3d_gicp_align_loop_batch(s3d_context* ctx, const s3d_cloud* sources, const s3d_cloud* targets, const double* guesses,
+                              const s3d_registration_parameters* coarse, const s3d_registration_parameters* fine, int n_pairs,
+                              s3d_result* out_coarse, s3d_result* out_fine) {
+  if (!fine || !out_fine) return S3D_INVALID_ARGUMENT;
+  std::vector<s3d_result> tmp;
+  if (!out_coarse && n_pairs > 0) { tmp.resize(n_pairs); out_coarse = tmp.data(); }
+  return align_batch_impl(ctx, sources, targets, guesses, coarse, n_pairs, out_coarse, fine, out_fine);
 }
 
 int s3d_gicp_align(s3d_context* ctx, s3d_cloud source, s3d_cloud target, const double guess[16], const s3d_registration_parameters* params,

@@ -168,3 +168,35 @@ def test_in_process_multi_device_context(kitti):
     many.close()
     for a, b in zip(got, ref):
         assert a.status == b.status and np.array_equal(a.pose(), b.pose()) and a.fitness == b.fitness
+
+
+def test_loop_batch_equals_two_batches(ctx, kitti):
+    """s3d_gicp_align_loop_batch == coarse batch followed by a fine batch from the coarse poses (createConstraint, loop = true,
+    PointCloudSensor.cpp:286-292), bit for bit; a failed coarse align ends the pair like the reference's exception does."""
+    from slam3d_b200 import synth
+    pairs = [synth.scan_pair(seed=100 + i, loop=True) for i in range(2)]
+    srcs = [pairs[0][0][::2], pairs[1][0][::2], kitti[0], kitti[2][:90]]
+    tgts = [pairs[0][1][::2], pairs[1][1][::2], kitti[1], kitti[3][:90]]
+    coarse = RegistrationParameters.defaults(point_cloud_density=0.5, max_correspondence_distance=5.0, max_translation=5.0)
+    fine = RegistrationParameters.defaults(point_cloud_density=0.2, max_translation=5.0)
+    rc = ctx.gicp_align_batch(srcs, tgts, None, coarse)
+    rf = ctx.gicp_align_batch(srcs, tgts, [r.pose() for r in rc], fine)
+    lc, lf = ctx.gicp_align_loop_batch(srcs, tgts, None, coarse, fine)
+    for i in range(4):
+        assert lc[i].status == rc[i].status and np.array_equal(lc[i].pose(), rc[i].pose()) and lc[i].fitness == rc[i].fitness
+        if rc[i].status == _abi.S3D_OK:
+            assert lf[i].status == rf[i].status and np.array_equal(lf[i].pose(), rf[i].pose()) and lf[i].fitness == rf[i].fitness
+            assert (lf[i].outer_iterations, lf[i].inner_iterations) == (rf[i].outer_iterations, rf[i].inner_iterations)
+    assert rc[0].status == _abi.S3D_OK and rc[2].status == _abi.S3D_OK
+    assert lc[3].status == _abi.S3D_TOO_FEW_POINTS and lf[3].status == _abi.S3D_TOO_FEW_POINTS
+    # a coarse failure (fitness gate) is what the caller sees; the fine pass does not overwrite it
+    strict = RegistrationParameters.defaults(point_cloud_density=0.5, max_correspondence_distance=5.0, max_translation=5.0, max_fitness_score=1e-6)
+    lc, lf = ctx.gicp_align_loop_batch(srcs[:1], tgts[:1], None, strict, fine)
+    assert lc[0].status == _abi.S3D_NOT_CONVERGED and lf[0].status == _abi.S3D_NOT_CONVERGED and lf[0].fitness == lc[0].fitness
+    # device-resident inputs take the same path without staging
+    import torch
+    ds = [torch.from_numpy(__import__("slam3d_b200").as_xyzw(a)).cuda() for a in srcs[:3]]
+    dt_ = [torch.from_numpy(__import__("slam3d_b200").as_xyzw(a)).cuda() for a in tgts[:3]]
+    dc, df = ctx.gicp_align_loop_batch(ds, dt_, None, coarse, fine)
+    for i in range(3):
+        assert np.array_equal(df[i].pose(), rf[i].pose())
