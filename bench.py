@@ -307,11 +307,14 @@ def main():
     dom_ms = stages[dom]["ms"]
     dom_launches = max(stages[dom]["launches"], 1)
     achieved = bytes_by_stage[dom] / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
-    # DRAM traffic of the dominant kernel from the committed ncu capture (profiles/r01f_summary.md: knn_cov_kernel, 16 clouds of
-    # ~47k points: dram read 36.2 MB + write 8.2 MB, cold cache) scaled to this run's launch size; null for other kernels
+    # DRAM traffic of the dominant kernel from the committed ncu captures (profiles/r01g_summary.md, cold cache), scaled to this
+    # run's launch size: knn_cov_kernel on 8 clouds of ~47k points read 17.39 MB + wrote 0.61 MB; gicp_iter_kernel on 6 pairs
+    # (one outer iteration each) read 21.46 MB + wrote 0.01 MB.  null for other kernels.
     traffic = None
     if dom == "knn_cov":
-        traffic = 44.4e6 / (16 * 47000.0) * (m_tgt + m_src) * B * prof_steps / dom_launches
+        traffic = 18.0e6 / (8 * 47000.0) * (m_tgt + m_src) * B * prof_steps / dom_launches
+    elif dom == "gicp_iter":
+        traffic = 21.47e6 / (6 * 47000.0) * m_tgt * iters_total / dom_launches
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "avg_launch_us": 1e3 * dom_ms / dom_launches, "launches": dom_launches,
                 "algorithmic_bytes_per_launch": bytes_by_stage[dom] / dom_launches,
