@@ -98,25 +98,14 @@ __device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int
     const uint32_t key = (dx == 0 ? sx0 : (dx == 1 ? sx1 : sx2)) | (dy == 0 ? sy0 : (dy == 1 ? sy1 : sy2)) | (dz == 0 ? sz0 : (dz == 1 ? sz1 : sz2));
     uint32_t begin, end;
     if (!cell_range_key(g.table, g.cap, key, L, begin, end)) continue;
-#ifndef S3D_NN_BATCH
-#define S3D_NN_BATCH 1
-#endif
-    // S3D_NN_BATCH points fetched before the first of them is examined: measured SLOWER for the 1-NN walk on B200
-    // (gicp_iter 4.55 -> 5.55 ms per 32 pairs at 2 and 4: most cells are left after one or two points), so it stays 1
-    for (uint32_t p0 = begin; p0 < end; p0 += S3D_NN_BATCH) {
-      float4 vb[S3D_NN_BATCH];
-#pragma unroll
-      for (int u = 0; u < S3D_NN_BATCH; ++u) vb[u] = __ldg(g.pts + min(p0 + u, end - 1));
-#pragma unroll
-      for (int u = 0; u < S3D_NN_BATCH; ++u) {
-        const uint32_t p = p0 + u;
-        if (u > 0 && p >= end) break;
-        const float4 v = vb[u];
-        const float d2 = dist2_pcl(qx, qy, qz, v.x, v.y, v.z);
-        const uint32_t id = __float_as_uint(v.w);
-        if (cand_less(d2, id, best.d2, best.idx)) { best.lb2 = fminf(best.lb2, best.d2); best.d2 = d2; best.idx = id; best.pos = p; }
-        else if (id != best.idx) best.lb2 = fminf(best.lb2, d2);  // the winner itself is met again when a level is rescanned
-      }
+    // (fetching 2 or 4 points before examining the first was measured SLOWER for this 1-NN walk on B200: gicp_iter 4.55 ->
+    // 5.55 ms per 32 pairs — most cells are left after one or two points; the kNN kernel, which visits every point, gains 8 %)
+    for (uint32_t p = begin; p < end; ++p) {
+      const float4 v = __ldg(g.pts + p);
+      const float d2 = dist2_pcl(qx, qy, qz, v.x, v.y, v.z);
+      const uint32_t id = __float_as_uint(v.w);
+      if (cand_less(d2, id, best.d2, best.idx)) { best.lb2 = fminf(best.lb2, best.d2); best.d2 = d2; best.idx = id; best.pos = p; }
+      else if (id != best.idx) best.lb2 = fminf(best.lb2, d2);  // the winner itself is met again when a level is rescanned
     }
   }
 }
