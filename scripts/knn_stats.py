@@ -5,8 +5,12 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 csrc = os.path.join(ROOT, "slam3d_b200", "csrc")
 out = "/tmp/libs3d_stats.so"
-srcs = [os.path.join(csrc, f) for f in ("voxel.cu", "grid.cu", "knn.cu", "gicp.cu", "map.cu", "api.cu")]
-subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-fmad=false", "-DS3D_KNN_STATS", "-Xcompiler", "-fPIC",
+srcs = [os.path.join(csrc, f) for f in ("voxel.cu", "grid.cu", "knn.cu", "gicp.cu", "ndt.cu", "map.cu", "api.cu")]
+prebuilt = os.path.join(ROOT, "slam3d_b200", "build", "libs3d_stats.so")  # built on the CPU box, travels with the snapshot
+if os.path.exists(prebuilt):
+    out = prebuilt
+else:
+  subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-fmad=false", "-DS3D_KNN_STATS", "-Xcompiler", "-fPIC",
                        "-shared", "-o", out] + srcs + ["-lcudart"])
 import slam3d_b200
 slam3d_b200.LIB_PATH = out
