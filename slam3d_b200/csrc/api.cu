@@ -24,6 +24,7 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 struct DeviceCtx {
   int device = 0;
   std::mutex mu;
+  std::mutex upload_mu;  // one chunk uploads at a time (Workspace::upload_gate)
   std::vector<std::pair<void*, size_t>> free_blocks;  // recycled allocations of released prepared clouds
   std::vector<std::unique_ptr<Workspace>> pool;  // idle workspaces
   std::vector<Workspace*> all;
@@ -48,10 +49,24 @@ struct s3d_context {
   double stage_ms[S3D_N_STAGES] = {0, 0, 0, 0, 0, 0};
   uint64_t stage_launches[S3D_N_STAGES] = {0, 0, 0, 0, 0, 0};
   int max_pairs_per_launch = 32;
-  int streams_per_device = 3;
+  int streams_per_device = 6;  // swept 3..16 on B200 with 64 pairs per call: 6 is best for host inputs (profiles/r01h_summary.md)
 };
 
 namespace s3d {
+
+// Set by the worker threads of a batch call: their chunks take turns on the host-to-device link, so the first chunk is on the
+// device after 1/W of the upload time and its kernels run while the next chunk uploads.  (Left to themselves the W streams
+// share the link and all uploads end together, with the GPU idle until then: 64 pairs, 268 MB, measured in DESIGN.md 5.)
+static thread_local bool t_gate_uploads = false;
+
+// Chunk size for `n` work items on W streams: the number of chunks is a multiple of W (every stream gets the same number of
+// chunks — 4 chunks on 3 streams measured 15 % slower than 3 or 6) and no chunk exceeds `cap` items.
+static int balanced_chunk(int n, int W, int cap) {
+  if (n <= 0) return 1;
+  const int waves = (n + W * cap - 1) / (W * cap);
+  const int chunks = W * std::max(1, waves);
+  return std::max(1, (n + chunks - 1) / chunks);
+}
 
 struct WsLease {
   s3d_context* ctx; DeviceCtx* dc; std::unique_ptr<Workspace> ws;
@@ -63,6 +78,8 @@ struct WsLease {
     }
     if (!ws) { ws.reset(new Workspace()); ws->init(dc->device); std::lock_guard<std::mutex> g(dc->mu); dc->all.push_back(ws.get()); }
     ws->profiling = ctx->profiling;
+    static const bool gate_enabled = [] { const char* e = getenv("S3D_GATE_UPLOADS"); return !e || atoi(e) != 0; }();  // 0: A/B measurements
+    ws->upload_gate = (t_gate_uploads && gate_enabled) ? &dc->upload_mu : nullptr;
   }
   ~WsLease() {
     {
@@ -463,7 +480,7 @@ int s3d_prepare_clouds(s3d_context* ctx, int device_slot, const s3d_cloud* cloud
   if (k < 1 || k > kMaxK) { set_error("correspondence_randomness must be in [1, 200] on the GPU path"); return S3D_INVALID_ARGUMENT; }
   if (n == 0) return S3D_OK;
   const int W = std::max(1, ctx->streams_per_device);
-  const int chunk = std::max(1, std::min(2 * ctx->max_pairs_per_launch, (n + W - 1) / W));
+  const int chunk = balanced_chunk(n, W, 2 * ctx->max_pairs_per_launch);
   std::vector<int> st(W, S3D_OK);
   std::vector<std::string> errs(W);
   std::atomic<int> next{0};
@@ -481,7 +498,7 @@ int s3d_prepare_clouds(s3d_context* ctx, int device_slot, const s3d_cloud* cloud
   if (W == 1 || n <= 2) worker(0);
   else {
     std::vector<std::thread> th;
-    for (int w = 0; w < W; ++w) th.emplace_back(worker, w);
+    for (int w = 0; w < W; ++w) th.emplace_back([&worker, w] { t_gate_uploads = true; worker(w); });
     for (auto& t : th) t.join();
   }
   for (int w = 0; w < W; ++w)
@@ -577,7 +594,7 @@ int s3d_gicp_align_prepared_batch(s3d_context* ctx, const s3d_prepared_cloud* co
   std::vector<int> st(W, S3D_OK);
   std::vector<std::string> errs(W);
   std::atomic<int> next{0};
-  const int chunk = std::max(1, std::min(ctx->max_pairs_per_launch, (n_pairs + W - 1) / W));
+  const int chunk = balanced_chunk(n_pairs, W, ctx->max_pairs_per_launch);
   auto worker = [&](int w) {
     st[w] = guarded([&]() -> int {
       for (;;) {
@@ -593,7 +610,7 @@ int s3d_gicp_align_prepared_batch(s3d_context* ctx, const s3d_prepared_cloud* co
   if (W == 1 || n_pairs == 1) worker(0);
   else {
     std::vector<std::thread> th;
-    for (int w = 0; w < W; ++w) th.emplace_back(worker, w);
+    for (int w = 0; w < W; ++w) th.emplace_back([&worker, w] { t_gate_uploads = true; worker(w); });
     for (auto& t : th) t.join();
   }
   for (int w = 0; w < W; ++w) if (st[w] != S3D_OK) { set_error(errs[w]); return st[w]; }
@@ -705,7 +722,7 @@ static int align_batch_impl(s3d_context* ctx, const s3d_cloud* sources, const s3
     const int lo = (int)((int64_t)n_pairs * d / nd), hi = (int)((int64_t)n_pairs * (d + 1) / nd);
     const int shard = hi - lo;
     if (shard <= 0) return;
-    const int chunk = std::max(1, std::min(ctx->max_pairs_per_launch, (shard + W - 1) / W));
+    const int chunk = balanced_chunk(shard, W, ctx->max_pairs_per_launch);
     st[d * W + w] = guarded([&]() -> int {
       for (;;) {
         const int c = next[d].fetch_add(1);
@@ -721,7 +738,7 @@ static int align_batch_impl(s3d_context* ctx, const s3d_cloud* sources, const s3
   if (nd * W == 1 || n_pairs == 1) worker(0, 0);
   else {
     std::vector<std::thread> th;
-    for (int d = 0; d < nd; ++d) for (int w = 0; w < W; ++w) th.emplace_back(worker, d, w);
+    for (int d = 0; d < nd; ++d) for (int w = 0; w < W; ++w) th.emplace_back([&worker, d, w, W] { t_gate_uploads = W > 1; worker(d, w); });
     for (auto& t : th) t.join();
   }
   for (int i = 0; i < nd * W; ++i)

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -89,6 +90,7 @@ constexpr int kIterTile = 256;   // source points per CTA in the fused correspon
 struct Workspace {
   int device = 0;
   cudaStream_t stream = nullptr;
+  std::mutex* upload_gate = nullptr;          // when set, setup_batch holds it from its first host-to-device copy until the copies have landed
   // sizes of the current batch
   uint32_t n_slots = 0, n_pairs = 0, total = 0, n_tiles = 0;
   std::vector<uint32_t> h_off, h_n;           // per slot

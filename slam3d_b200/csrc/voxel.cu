@@ -108,6 +108,8 @@ void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const s
   }
   if (need_stage) ws.raw_stage.reserve(16 * tot);
 
+  std::unique_lock<std::mutex> gate;  // uploads of concurrent chunks take turns (api.cu, t_gate_uploads)
+  if (need_stage && ws.upload_gate) gate = std::unique_lock<std::mutex>(*ws.upload_gate);
   SlotInfo* hs = ws.h_slots.as<SlotInfo>();
   uint32_t* ht = ws.h_tiles.as<uint32_t>();
   uint32_t* h_tile_slot = ht; uint32_t* h_tile_first = ht + n_tiles; uint32_t* h_begin = ht + 2 * size_t(n_tiles);
@@ -132,6 +134,7 @@ void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const s
     for (uint64_t f = 0; f < sizes[s]; f += kSortTile) { h_tile_slot[t] = s; h_tile_first[t] = static_cast<uint32_t>(f); ++t; }
   }
   h_begin[ns] = t;
+  if (gate.owns_lock()) { S3D_CUDA(cudaStreamSynchronize(ws.stream)); gate.unlock(); }
   S3D_CUDA(cudaMemcpyAsync(ws.slots.p, hs, sizeof(SlotInfo) * ns, cudaMemcpyHostToDevice, ws.stream));
   if (n_tiles) {
     S3D_CUDA(cudaMemcpyAsync(ws.tile_slot.p, h_tile_slot, 4 * size_t(n_tiles), cudaMemcpyHostToDevice, ws.stream));
