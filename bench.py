@@ -228,7 +228,7 @@ def main():
             ctx.gicp_align_batch(dev_src, dev_tgt, None, p)
         ev_ms, wall_ms, cnt, last = timed(dev_src, dev_tgt, args.steps)
     # per-kernel durations for the roofline: same workload, same process, right after the timed region, but on ONE stream
-    # (with 3 concurrent streams an event pair also spans other streams' kernels, so a kernel's own duration is undefined)
+    # (with several concurrent streams an event pair also spans other streams' kernels, so a kernel's own duration is undefined)
     os.environ["S3D_STREAMS_PER_DEVICE"] = "1"
     ctx_serial = slam3d_b200.Context([local_rank])
     ctx_serial.gicp_align_batch(dev_src, dev_tgt, None, p)
@@ -307,14 +307,14 @@ def main():
     dom_ms = stages[dom]["ms"]
     dom_launches = max(stages[dom]["launches"], 1)
     achieved = bytes_by_stage[dom] / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
-    # DRAM traffic of the dominant kernel from the committed ncu captures (profiles/r01g_summary.md, cold cache), scaled to this
-    # run's launch size: knn_cov_kernel on 8 clouds of ~47k points read 17.39 MB + wrote 0.61 MB; gicp_iter_kernel on 6 pairs
-    # (one outer iteration each) read 21.46 MB + wrote 0.01 MB.  null for other kernels.
+    # DRAM traffic of the dominant kernel from the committed ncu captures (profiles/r01h_summary.md, cold cache), scaled to this
+    # run's launch size: knn_cov_kernel on 12 clouds of ~47k points read 26.43 MB + wrote 2.88 MB; gicp_iter_kernel on 6 pairs
+    # (one outer iteration each) read 26.56 MB + wrote 0.35 MB (first iteration of a chunk: 31.12 + 0.41 MB).  null for other kernels.
     traffic = None
     if dom == "knn_cov":
-        traffic = 18.0e6 / (8 * 47000.0) * (m_tgt + m_src) * B * prof_steps / dom_launches
+        traffic = 29.31e6 / (12 * 47000.0) * (m_tgt + m_src) * B * prof_steps / dom_launches
     elif dom == "gicp_iter":
-        traffic = 21.47e6 / (6 * 47000.0) * m_tgt * iters_total / dom_launches
+        traffic = 26.91e6 / (6 * 47000.0) * m_tgt * iters_total / dom_launches
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "avg_launch_us": 1e3 * dom_ms / dom_launches, "launches": dom_launches,
                 "algorithmic_bytes_per_launch": bytes_by_stage[dom] / dom_launches,

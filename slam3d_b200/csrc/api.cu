@@ -49,7 +49,11 @@ struct s3d_context {
   double stage_ms[S3D_N_STAGES] = {0, 0, 0, 0, 0, 0};
   uint64_t stage_launches[S3D_N_STAGES] = {0, 0, 0, 0, 0, 0};
   int max_pairs_per_launch = 32;
-  int streams_per_device = 6;  // swept 3..16 on B200 with 64 pairs per call: 6 is best for host inputs (profiles/r01h_summary.md)
+  // Host threads / streams per device, swept 3..16 on B200 (profiles/r01h_summary.md): GICP on raw host scans is fastest with
+  // 6 (smaller chunks: the first kernels start after 1/6 of the upload); the prepare + prepared-align path and the NDT branch
+  // (252-register kernels) are fastest with 3.
+  int streams_per_device = 6;
+  int streams_small = 3;
 };
 
 namespace s3d {
@@ -264,7 +268,7 @@ int s3d_create_context(const int* devices, int n_devices, s3d_context** out) {
       ctx->devs.push_back(std::move(dc));
     }
     if (const char* env = getenv("S3D_MAX_PAIRS_PER_LAUNCH")) ctx->max_pairs_per_launch = std::max(1, atoi(env));
-    if (const char* env = getenv("S3D_STREAMS_PER_DEVICE")) ctx->streams_per_device = std::max(1, atoi(env));
+    if (const char* env = getenv("S3D_STREAMS_PER_DEVICE")) ctx->streams_per_device = ctx->streams_small = std::max(1, atoi(env));
     *out = ctx.release();
     return S3D_OK;
   });
@@ -479,7 +483,7 @@ int s3d_prepare_clouds(s3d_context* ctx, int device_slot, const s3d_cloud* cloud
   for (int i = 0; i < n; ++i) out[i] = nullptr;
   if (k < 1 || k > kMaxK) { set_error("correspondence_randomness must be in [1, 200] on the GPU path"); return S3D_INVALID_ARGUMENT; }
   if (n == 0) return S3D_OK;
-  const int W = std::max(1, ctx->streams_per_device);
+  const int W = std::max(1, ctx->streams_small);
   const int chunk = balanced_chunk(n, W, 2 * ctx->max_pairs_per_launch);
   std::vector<int> st(W, S3D_OK);
   std::vector<std::string> errs(W);
@@ -590,7 +594,7 @@ int s3d_gicp_align_prepared_batch(s3d_context* ctx, const s3d_prepared_cloud* co
         return S3D_INVALID_ARGUMENT;
       }
   }
-  const int W = std::max(1, ctx->streams_per_device);
+  const int W = std::max(1, ctx->streams_small);
   std::vector<int> st(W, S3D_OK);
   std::vector<std::string> errs(W);
   std::atomic<int> next{0};
@@ -713,7 +717,7 @@ static int align_batch_impl(s3d_context* ctx, const s3d_cloud* sources, const s3
   // Contiguous shards, one per device; no device-to-device traffic (registrations are independent).  Inside a device the
   // shard is cut into chunks that `streams_per_device` host threads push through their own workspace/stream, so the H2D
   // copies and the per-iteration host polls of one chunk overlap with the kernels of another.
-  const int W = std::max(1, ctx->streams_per_device);
+  const int W = std::max(1, params->registration_algorithm == S3D_ALG_NDT ? ctx->streams_small : ctx->streams_per_device);
   std::vector<int> st(nd * W, S3D_OK);
   std::vector<std::string> errs(nd * W);
   std::vector<std::atomic<int>> next(nd);
