@@ -84,7 +84,13 @@ typedef struct s3d_result {
 
 typedef struct s3d_context s3d_context;
 
-/* Library / device bring-up.  `devices` = CUDA ordinals to shard batches over (NULL/0: current device). */
+/* Library / device bring-up.  `devices` = CUDA ordinals to shard batches over (NULL/0: current device).
+ * Scheduling knobs, read from the environment when the context is created (measurement aids; results never depend on them,
+ * tests/test_gpu_gicp.py::test_batch_scheduling_is_invisible):
+ *   S3D_STREAMS_PER_DEVICE   host threads / streams that push chunks of a batch call through one device (default: 6 for GICP
+ *                            on raw scans, 3 for prepared clouds and NDT)
+ *   S3D_MAX_PAIRS_PER_LAUNCH upper bound of a chunk (default 32 pairs)
+ *   S3D_GATE_UPLOADS=0       lets the chunks of a device upload concurrently instead of one after the other */
 int s3d_create_context(const int* devices, int n_devices, s3d_context** out);
 int s3d_destroy_context(s3d_context* ctx);
 

@@ -170,6 +170,30 @@ def test_in_process_multi_device_context(kitti):
         assert a.status == b.status and np.array_equal(a.pose(), b.pose()) and a.fitness == b.fitness
 
 
+def test_batch_scheduling_is_invisible(ctx, kitti, monkeypatch):
+    """How a batch is cut into chunks and spread over host threads / streams (api.cu: balanced_chunk, upload_gate) must not show
+    in the results: 14 host-memory pairs through 1 stream, through 6 streams with 2 pairs per launch (several chunks per
+    worker, uploads taking turns) and through the default schedule give bit-identical poses and fitness scores."""
+    import slam3d_b200
+    p = RegistrationParameters.defaults(point_cloud_density=0.2)
+    srcs = [kitti[i % 3][(i % 4)::4] for i in range(14)]
+    tgts = [kitti[i % 3 + 1][(i % 4)::4] for i in range(14)]
+    ref = ctx.gicp_align_batch(srcs, tgts, None, p)
+    assert sum(r.status == _abi.S3D_OK for r in ref) >= 12
+    for env in ({"S3D_STREAMS_PER_DEVICE": "1"}, {"S3D_STREAMS_PER_DEVICE": "6", "S3D_MAX_PAIRS_PER_LAUNCH": "2"},
+                {"S3D_STREAMS_PER_DEVICE": "4", "S3D_MAX_PAIRS_PER_LAUNCH": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        other = slam3d_b200.Context()  # the knobs are read when the context is created
+        got = other.gicp_align_batch(srcs, tgts, None, p)
+        other.close()
+        for k in env:
+            monkeypatch.delenv(k)
+        for a, b in zip(got, ref):
+            assert a.status == b.status and a.outer_iterations == b.outer_iterations
+            assert np.array_equal(a.pose(), b.pose()) and a.fitness == b.fitness
+
+
 def test_loop_batch_equals_two_batches(ctx, kitti):
     """s3d_gicp_align_loop_batch == coarse batch followed by a fine batch from the coarse poses (createConstraint, loop = true,
     PointCloudSensor.cpp:286-292), bit for bit; a failed coarse align ends the pair like the reference's exception does."""
