@@ -70,10 +70,40 @@ def main():
                 "status": r.status, "converged": r.converged, "outer_iterations": r.outer_iterations,
                 "inner_iterations": r.inner_iterations, "n_source": r.n_source, "n_target": r.n_target,
                 "n_correspondences": r.n_correspondences, "fitness": r.fitness, "T": r.pose().tolist()}
+    g["map"] = map_golden(clouds)
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(g, f, indent=1)
     print(json.dumps(g["align"], indent=1))
 
 
+def pose(tx, ty, yaw):
+    T = np.eye(4)
+    T[:2, :2] = [[np.cos(yaw), -np.sin(yaw)], [np.sin(yaw), np.cos(yaw)]]
+    T[:3, 3] = [tx, ty, 0.01]
+    return T
+
+
+def map_golden(clouds):
+    """patch / map building (PointCloudSensor.cpp:211-233, :301-318): frozen oracle outputs, same cases as tests/test_gpu_map.py"""
+    m = {"transform cloud1": {"sha": sha(oracle.transform_cloud(clouds[0], pose(12.3, -4.5, 0.7)))}}
+    out, keep = oracle.remove_outliers(clouds[1], 0.2, 3)
+    m["remove_outliers cloud2 r=0.2 n=3"] = {"kept": int(keep.sum()), "sha": sha(out)}
+    poses = [pose(0.69 * i, 0.004 * i, 0.0035 * i) for i in range(4)]
+    mp = oracle.build_map(clouds, poses, 0.2, 3, 0.1)
+    m["build_map 4 clouds"] = {"n_out": int(mp.shape[0]), "sha": sha(mp)}
+    return m
+
+
+def add_map_only():
+    """python make_golden.py --map: adds the "map" entry to an existing golden.json without touching the other entries"""
+    clouds = [np.frombuffer(lzma.decompress(open(os.path.join(HERE, f"cloud{i}.xyz.f32.xz"), "rb").read()), np.float32).reshape(-1, 3) for i in range(1, 5)]
+    path = os.path.join(HERE, "golden.json")
+    g = json.load(open(path))
+    g["map"] = map_golden(clouds)
+    with open(path, "w") as f:
+        json.dump(g, f, indent=1)
+    print(json.dumps(g["map"], indent=1))
+
+
 if __name__ == "__main__":
-    main()
+    add_map_only() if "--map" in sys.argv else main()
