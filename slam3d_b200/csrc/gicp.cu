@@ -19,7 +19,10 @@
 // do not make up for the probe latency that fewer threads in flight can hide.  Also tried and dropped: splitting this kernel
 // into a barrier-free search kernel (CTAs of 32 / 64 / 128 / 256 threads) and a separate 74-sum tile kernel, because 37 % of the
 // stall samples of a late-iteration launch sit at the reduction barrier (profiles/r01g_summary.md) — results bit-identical,
-// stage time 4.6-4.9 ms against 4.55 ms fused per 32 pairs: the waiting warps cost no issue slots and the extra launch does.)
+// stage time 4.6-4.9 ms against 4.55 ms fused per 32 pairs: the waiting warps cost no issue slots and the extra launch does.
+// Also dropped: per-lane cell cursors (+12 %) and CTA-level compaction of the points that still need a search (equal):
+// profiles/r01h_summary.md.
+// Kept: the two-pass 27-block of nn_search.cuh (scan_block<true>; cells noted in s_cells) — gicp_iter 8.60 -> 8.26 ms per 64 pairs.)
 // Because every float operation that PCL's decisions depend on is mirrored and the double sums differ only in order, the
 // GPU follows the oracle's iterate sequence (same inner/outer iteration counts, bit-identical poses in the test-suite).
 // Reductions use fixed trees: results are bit-reproducible run to run and independent of batch composition.
@@ -130,12 +133,23 @@ __device__ __forceinline__ bool certified_same_nn(const GridView& g, float3 q, f
 }
 
 // (register allocation: the compiler's own choice — 64 registers, 4 CTAs/SM — beat forced 5/6/7 CTAs/SM on B200)
-__global__ void __launch_bounds__(kIterTile) gicp_iter_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
+#ifndef S3D_NN_GATHER
+#define S3D_NN_GATHER 1
+#endif
+#if S3D_NN_GATHER
+#define S3D_ITER_BOUNDS __launch_bounds__(kIterTile, 4)  // 64 registers: 4 CTAs per SM as before (the compiler's own choice would be 78)
+#else
+#define S3D_ITER_BOUNDS __launch_bounds__(kIterTile)
+#endif
+__global__ void S3D_ITER_BOUNDS gicp_iter_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
                                                               const float4* __restrict__ moved,
                                                               uint32_t* __restrict__ prev_nn, float* __restrict__ sec_lb, uint32_t* __restrict__ corr,
                                                               double* __restrict__ mahal, double* __restrict__ moments) {
   __shared__ double feat[kIterTile][kFeat];
   __shared__ double part[3][kNumMoments];
+#if S3D_NN_GATHER
+  __shared__ uint2 s_cells[kNNGatherCap * kIterTile];  // cell ranges noted by the gathering search (nn_search.cuh)
+#endif
   const uint32_t p = blockIdx.y;
   const PairState& ps = pairs[p];
   if (ps.phase != kPhaseNeedNN) return;
@@ -157,7 +171,11 @@ __global__ void __launch_bounds__(kIterTile) gicp_iter_kernel(const SlotInfo* __
     NNResult nn;
     float lb_new;
     if (!certified_same_nn(g, q, transform_mv(ps.T_search, mv.x, mv.y, mv.z), hint, sec_lb[ps.pt_off + r], nn, lb_new)) {
+#if S3D_NN_GATHER
+      nn = nn_search<true>(g, q.x, q.y, q.z, cutoff, hint, kNoIndex, s_cells + threadIdx.x);
+#else
       nn = nn_search(g, q.x, q.y, q.z, cutoff, hint);
+#endif
       prev_nn[ps.pt_off + r] = nn.pos;
       lb_new = sqrtf(nn.lb2) * 0.99999f;
     }

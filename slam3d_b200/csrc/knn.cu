@@ -77,6 +77,41 @@ constexpr uint64_t KMAX = 0xFFFFFFFFFFFFFFFFull;
 #define S3D_KNN_BATCH 4
 #endif
 
+// scans the points [begin, end) of one cell for the query qv: fill phase (append, heapify once when the k-th candidate
+// arrives), then replace-the-root insertions.  S3D_KNN_BATCH points are fetched before the first of them is examined, so
+// their load latencies overlap (B200, 32 pairs per step: 4.41 / 4.30 / 4.06 ms for batches of 1 / 2 / 4).
+__device__ __forceinline__ void knn_scan_range(const GridView& g, const float4 qv, uint32_t begin, uint32_t end, uint64_t bound, uint64_t* h, int kk,
+                                               int& cnt, uint64_t& tau, float& tau_d2) {
+  for (uint32_t p0 = begin; p0 < end; p0 += S3D_KNN_BATCH) {
+    float4 vb[S3D_KNN_BATCH];
+#pragma unroll
+    for (int u = 0; u < S3D_KNN_BATCH; ++u) vb[u] = __ldg(g.pts + min(p0 + u, end - 1));
+#pragma unroll
+    for (int u = 0; u < S3D_KNN_BATCH; ++u) {
+      if (u > 0 && p0 + u >= end) break;
+      const float4 v = vb[u];
+      const float cd = dist2_pcl(qv.x, qv.y, qv.z, v.x, v.y, v.z);
+      if (!(cd == cd)) continue;  // NaN never enters
+      const uint64_t ck = ((uint64_t)__float_as_uint(cd) << 32) | (uint64_t)__float_as_uint(v.w);
+      if (cnt < kk) {
+        if (ck <= bound) {
+          h[cnt * kKnnThreads] = ck; ++cnt; KSTAT(5, 1);
+          if (cnt == kk) {
+            for (int i = heap_last_parent(kk); i >= 0; --i) heap_sift_down(h, kk, h[i * kKnnThreads], i);
+            tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
+          }
+        }
+      } else if (ck < tau) {
+        heap_sift_down(h, kk, ck); KSTAT(6, 1);
+        tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
+      }
+    }
+  }
+}
+
+// (Tried and dropped, B200: noting the occupied cells of the 27-block in a first lockstep pass and letting every lane scan its
+// noted cells back to back in a second pass — the variant that speeds up the 1-NN walk of nn_search.cuh by 4 % — costs the kNN
+// kernel 27 %: while the heap is filling nothing can be pruned, so all 27 cells are probed, and the list takes shared memory.)
 __device__ __forceinline__ int thread_walk(const GridView& g, const float4 qv, float ux, float uy, float uz, int L, uint64_t bound, uint64_t* h, int kk) {
   int cnt = 0;
   for (;; ++L) {
@@ -117,33 +152,7 @@ __device__ __forceinline__ int thread_walk(const GridView& g, const float4 qv, f
       KSTAT(2, 1);
       if (!cell_range_key(g.table, g.cap, key, L, begin, end)) continue;
       KSTAT(4, end - begin);
-      // S3D_KNN_BATCH points are fetched before the first of them is examined, so their load latencies overlap
-      // (B200, 32 pairs per step: 4.41 / 4.30 / 4.06 ms for batches of 1 / 2 / 4)
-      for (uint32_t p0 = begin; p0 < end; p0 += S3D_KNN_BATCH) {
-        float4 vb[S3D_KNN_BATCH];
-#pragma unroll
-        for (int u = 0; u < S3D_KNN_BATCH; ++u) vb[u] = __ldg(g.pts + min(p0 + u, end - 1));
-#pragma unroll
-        for (int u = 0; u < S3D_KNN_BATCH; ++u) {
-          if (u > 0 && p0 + u >= end) break;
-          const float4 v = vb[u];
-          const float cd = dist2_pcl(qv.x, qv.y, qv.z, v.x, v.y, v.z);
-          if (!(cd == cd)) continue;  // NaN never enters
-          const uint64_t ck = ((uint64_t)__float_as_uint(cd) << 32) | (uint64_t)__float_as_uint(v.w);
-          if (cnt < kk) {
-            if (ck <= bound) {  // fill phase: append, and heapify once when the k-th candidate arrives
-              h[cnt * kKnnThreads] = ck; ++cnt; KSTAT(5, 1);
-              if (cnt == kk) {
-                for (int i = heap_last_parent(kk); i >= 0; --i) heap_sift_down(h, kk, h[i * kKnnThreads], i);
-                tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
-              }
-            }
-          } else if (ck < tau) {
-            heap_sift_down(h, kk, ck); KSTAT(6, 1);
-            tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
-          }
-        }
-      }
+      knn_scan_range(g, qv, begin, end, bound, h, kk, cnt, tau, tau_d2);
     }
     const bool full = cnt == kk;
     if ((full && tau_d2 <= g2) || top) break;

@@ -69,8 +69,26 @@ __device__ __forceinline__ int cell_order(int i) {
 // its distance (gap along each axis, shrunk by the float slack) already exceeds the best candidate — with a warm start
 // that leaves 1-4 of the 27 cells.  (ax,ay,az) = position of the query inside its cell in [0,1); prune = false at the
 // top level, where the block is anchored at cell 0 instead of the query.
+constexpr int kNNGatherCap = 8;  // noted cells per thread in the gathering variant (8 bytes each)
+
+__device__ __forceinline__ void scan_range(const GridView& g, uint32_t begin, uint32_t end, float qx, float qy, float qz, NNResult& best) {
+  // (fetching 2 or 4 points before examining the first was measured SLOWER for this 1-NN walk on B200: gicp_iter 4.55 ->
+  // 5.55 ms per 32 pairs — most cells are left after one or two points; the kNN kernel, which visits every point, gains 8 %)
+  for (uint32_t p = begin; p < end; ++p) {
+    const float4 v = __ldg(g.pts + p);
+    const float d2 = dist2_pcl(qx, qy, qz, v.x, v.y, v.z);
+    const uint32_t id = __float_as_uint(v.w);
+    if (cand_less(d2, id, best.d2, best.idx)) { best.lb2 = fminf(best.lb2, best.d2); best.d2 = d2; best.idx = id; best.pos = p; }
+    else if (id != best.idx) best.lb2 = fminf(best.lb2, d2);  // the winner itself is met again when a level is rescanned
+  }
+}
+
+// kGather: the lockstep pass scans only the own cell and notes the other surviving cells in `lst` (entry j of a thread at
+// lst[j * blockDim.x]); a second pass then lets every lane scan ITS noted cells back to back, in the same order and with the
+// same pruning rule evaluated at scan time — the same scans as the single-pass walk, so the same result and the same lb2.
+template <bool kGather>
 __device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int cy, int cz, float ax, float ay, float az, bool prune,
-                                           float qx, float qy, float qz, NNResult& best) {
+                                           float qx, float qy, float qz, NNResult& best, uint2* lst = nullptr) {
   const int dim = 1 << (g.nlev - L);
   const float hl = g.h0 * (float)(1 << L) * 0.9999f;
   // Morton bits of the three cell coordinates per axis, spread once per block instead of once per cell
@@ -85,6 +103,8 @@ __device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int
     const float c0 = fmaxf(az * hl - g.margin, 0.f), c1 = fmaxf((1.f - az) * hl - g.margin, 0.f);
     glx = a0 * a0; gux = a1 * a1; gly = b0 * b0; guy = b1 * b1; glz = c0 * c0; guz = c1 * c1;
   }
+  uint32_t found = 0;
+  int n_list = 0;
 #pragma unroll 1
   for (int i = 0; i < 27; ++i) {
     const int c = cell_order(i);
@@ -98,14 +118,21 @@ __device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int
     const uint32_t key = (dx == 0 ? sx0 : (dx == 1 ? sx1 : sx2)) | (dy == 0 ? sy0 : (dy == 1 ? sy1 : sy2)) | (dz == 0 ? sz0 : (dz == 1 ? sz1 : sz2));
     uint32_t begin, end;
     if (!cell_range_key(g.table, g.cap, key, L, begin, end)) continue;
-    // (fetching 2 or 4 points before examining the first was measured SLOWER for this 1-NN walk on B200: gicp_iter 4.55 ->
-    // 5.55 ms per 32 pairs — most cells are left after one or two points; the kNN kernel, which visits every point, gains 8 %)
-    for (uint32_t p = begin; p < end; ++p) {
-      const float4 v = __ldg(g.pts + p);
-      const float d2 = dist2_pcl(qx, qy, qz, v.x, v.y, v.z);
-      const uint32_t id = __float_as_uint(v.w);
-      if (cand_less(d2, id, best.d2, best.idx)) { best.lb2 = fminf(best.lb2, best.d2); best.d2 = d2; best.idx = id; best.pos = p; }
-      else if (id != best.idx) best.lb2 = fminf(best.lb2, d2);  // the winner itself is met again when a level is rescanned
+    if (!kGather || i == 0 || n_list == kNNGatherCap) scan_range(g, begin, end, qx, qy, qz, best);
+    else { lst[n_list * blockDim.x] = make_uint2(begin, end); found |= 1u << i; ++n_list; }
+  }
+  if (kGather) {
+    for (int j = 0; found; ++j) {
+      const int i = __ffs(found) - 1;
+      found &= found - 1;
+      const uint2 be = lst[j * blockDim.x];
+      if (prune) {
+        const int c = cell_order(i);
+        const int dx = c % 3, dy = (c / 3) % 3, dz = c / 9;
+        const float cell_lb = ((dx == 0 ? glx : (dx == 1 ? 0.f : gux)) + (dy == 0 ? gly : (dy == 1 ? 0.f : guy)) + (dz == 0 ? glz : (dz == 1 ? 0.f : guz))) * 0.99999f;
+        if (cell_lb > best.d2) { best.lb2 = fminf(best.lb2, cell_lb); continue; }
+      }
+      scan_range(g, be.x, be.y, qx, qy, qz, best);
     }
   }
 }
@@ -114,8 +141,9 @@ __device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int
 // hint_pos / hint2_pos: sorted positions of candidates whose distance bounds the search (the previous correspondence of this
 // query, the fresh result of the neighbouring query) or kNoIndex.  Hints only steer the level and the pruning; the result is
 // the exact nearest neighbour either way.
+template <bool kGather = false>
 __device__ __forceinline__ NNResult nn_search(const GridView& g, float qx, float qy, float qz, float cutoff2, uint32_t hint_pos,
-                                              uint32_t hint2_pos = kNoIndex) {
+                                              uint32_t hint2_pos = kNoIndex, uint2* lst = nullptr) {
   NNResult best{INFINITY, kNoIndex, kNoIndex, INFINITY};
   if (g.n == 0 || g.cap == 0) return best;
   const float ux = clamp_coord(grid_coord(qx, g.ox, g.inv_h0));
@@ -146,7 +174,7 @@ __device__ __forceinline__ NNResult nn_search(const GridView& g, float qx, float
     const float g2 = block_guarantee2(g, ux, uy, uz, L, cx, cy, cz, ax, ay, az);
     const bool top = L >= g.nlev - 1;
     if (top) cx = cy = cz = 0;  // 2 cells per axis: the block around cell 0 is the whole cloud, wherever the query is
-    scan_block(g, L, cx, cy, cz, ax, ay, az, !top, qx, qy, qz, best);
+    scan_block<kGather>(g, L, cx, cy, cz, ax, ay, az, !top, qx, qy, qz, best, lst);
     if (top) break;                                   // the block was the whole cloud
     if (best.d2 <= g2 || g2 >= cutoff2) { best.lb2 = fminf(best.lb2, g2); break; }  // everything outside the block is farther than sqrt(g2)
   }
