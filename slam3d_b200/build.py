@@ -11,9 +11,7 @@ LIB = os.path.join(HERE, "libs3d_b200.so")
 SOURCES = ["voxel.cu", "grid.cu", "knn.cu", "gicp.cu", "ndt.cu", "map.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: every float/double expression keeps its written operation order (PCL parity)
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-         "-Xcompiler", "-fPIC,-O2", "--use_fast_math=false"] if False else \
-        ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC,-O2"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC,-O2"]
 
 
 def _deps():
