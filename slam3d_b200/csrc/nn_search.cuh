@@ -84,8 +84,11 @@ __device__ __forceinline__ void scan_range(const GridView& g, uint32_t begin, ui
 }
 
 // kGather: the lockstep pass scans only the own cell and notes the other surviving cells in `lst` (entry j of a thread at
-// lst[j * blockDim.x]); a second pass then lets every lane scan ITS noted cells back to back, in the same order and with the
-// same pruning rule evaluated at scan time — the same scans as the single-pass walk, so the same result and the same lb2.
+// lst[j * blockDim.x]); a second pass then lets every lane scan ITS noted cells back to back, in the same near-first order and
+// with the same pruning rule evaluated at scan time.  The winner is the exact nearest neighbour either way.  lb2 stays a
+// valid lower bound for every other point but need not be the single-pass value: when more than kNNGatherCap cells survive
+// the first pass (own cell empty), the surplus is scanned before the noted ones, so a cell may be scanned where the single
+// pass would have pruned it, or the other way round (tests/test_hostsearch.py checks both walks on the host).
 template <bool kGather>
 __device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int cy, int cz, float ax, float ay, float az, bool prune,
                                            float qx, float qy, float qz, NNResult& best, uint2* lst = nullptr) {
