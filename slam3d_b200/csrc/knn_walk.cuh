@@ -142,6 +142,7 @@ __device__ __forceinline__ int thread_walk(const GridView& g, const float4 qv, f
       KSTAT(2, 1);
       if (!cell_range_key(g.table, g.cap, key, L, begin, end)) continue;
       KSTAT(4, end - begin);
+      S3D_SCAN_TRACE(L, i, end - begin);
       knn_scan_range(g, qv, begin, end, bound, h, kk, cnt, tau, tau_d2);
     }
     const bool full = cnt == kk;

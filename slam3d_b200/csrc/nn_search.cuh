@@ -71,6 +71,11 @@ __device__ __forceinline__ int cell_order(int i) {
 // top level, where the block is anchored at cell 0 instead of the query.
 constexpr int kNNGatherCap = 8;  // noted cells per thread in the gathering variant (8 bytes each)
 
+// host-side work statistics (tests/hostsearch.cpp defines it to record which cell slot scanned how many points); nothing on the device
+#ifndef S3D_SCAN_TRACE
+#define S3D_SCAN_TRACE(level, slot, count)
+#endif
+
 __device__ __forceinline__ void scan_range(const GridView& g, uint32_t begin, uint32_t end, float qx, float qy, float qz, NNResult& best) {
   // (fetching 2 or 4 points before examining the first was measured SLOWER for this 1-NN walk on B200: gicp_iter 4.55 ->
   // 5.55 ms per 32 pairs — most cells are left after one or two points; the kNN kernel, which visits every point, gains 8 %)
@@ -121,7 +126,7 @@ __device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int
     const uint32_t key = (dx == 0 ? sx0 : (dx == 1 ? sx1 : sx2)) | (dy == 0 ? sy0 : (dy == 1 ? sy1 : sy2)) | (dz == 0 ? sz0 : (dz == 1 ? sz1 : sz2));
     uint32_t begin, end;
     if (!cell_range_key(g.table, g.cap, key, L, begin, end)) continue;
-    if (!kGather || i == 0 || n_list == kNNGatherCap) scan_range(g, begin, end, qx, qy, qz, best);
+    if (!kGather || i == 0 || n_list == kNNGatherCap) { S3D_SCAN_TRACE(L, i, end - begin); scan_range(g, begin, end, qx, qy, qz, best); }
     else { lst[n_list * blockDim.x] = make_uint2(begin, end); found |= 1u << i; ++n_list; }
   }
   if (kGather) {
@@ -135,6 +140,7 @@ __device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int
         const float cell_lb = ((dx == 0 ? glx : (dx == 1 ? 0.f : gux)) + (dy == 0 ? gly : (dy == 1 ? 0.f : guy)) + (dz == 0 ? glz : (dz == 1 ? 0.f : guz))) * 0.99999f;
         if (cell_lb > best.d2) { best.lb2 = fminf(best.lb2, cell_lb); continue; }
       }
+      S3D_SCAN_TRACE(L, i, be.y - be.x);
       scan_range(g, be.x, be.y, qx, qy, qz, best);
     }
   }

@@ -8,6 +8,19 @@
 #include <numeric>
 #include <vector>
 
+// work statistics: every cell scan of the walks reports (level, slot of the 27-block, points in the cell)
+struct HsTrace { std::vector<uint32_t> query, visit, slot, count; uint32_t cur_query = 0, cur_visit = 0; int last_level = -1; };
+static HsTrace* g_trace = nullptr;
+static inline void hs_trace(int level, int slot, uint32_t count) {
+  if (!g_trace) return;
+  if (g_trace->last_level >= 0 && level != g_trace->last_level) ++g_trace->cur_visit;  // the walk moved on to a coarser level
+  g_trace->last_level = level;
+  g_trace->query.push_back(g_trace->cur_query); g_trace->visit.push_back(g_trace->cur_visit);
+  g_trace->slot.push_back((uint32_t)slot); g_trace->count.push_back(count);
+}
+static inline void hs_trace_next_query(uint32_t q) { if (g_trace) { g_trace->cur_query = q; g_trace->cur_visit = 0; g_trace->last_level = -1; } }
+#define S3D_SCAN_TRACE(level, slot, count) hs_trace((level), (slot), (uint32_t)(count))
+
 #include "../slam3d_b200/csrc/knn_walk.cuh"
 
 namespace {
@@ -90,6 +103,7 @@ void hs_nn(void* grid, const float* q, uint64_t nq, float cutoff2, int gather, c
   const s3d::GridView& g = static_cast<HostGrid*>(grid)->view;
   uint2 cells[s3d::kNNGatherCap];
   for (uint64_t i = 0; i < nq; ++i) {
+    hs_trace_next_query((uint32_t)i);
     const uint32_t hint = hints ? hints[i] : s3d::kNoIndex;
     const s3d::NNResult r = gather ? s3d::nn_search<true>(g, q[3 * i], q[3 * i + 1], q[3 * i + 2], cutoff2, hint, s3d::kNoIndex, cells)
                                    : s3d::nn_search<false>(g, q[3 * i], q[3 * i + 1], q[3 * i + 2], cutoff2, hint);
@@ -105,6 +119,7 @@ void hs_knn(void* grid, int k, uint32_t* idx, float* d2) {
   std::vector<uint64_t> heap((size_t)k * s3d::kKnnThreads);
   uint64_t* h = heap.data();
   for (uint32_t r = 0; r < n; ++r) {
+    hs_trace_next_query(r);  // sorted position = thread number
     const float4 qv = g.pts[r];
     const uint32_t q_orig = __float_as_uint(qv.w);
     const float ux = s3d::clamp_coord(s3d::grid_coord(qv.x, g.ox, g.inv_h0));
@@ -123,6 +138,17 @@ void hs_knn(void* grid, int k, uint32_t* idx, float* d2) {
       d2[(size_t)q_orig * k + j] = have ? __uint_as_float((uint32_t)(h[j * s3d::kKnnThreads] >> 32)) : INFINITY;
     }
   }
+}
+
+// work statistics: start recording / fetch the records (query, level visit, cell slot, points scanned) and stop
+void hs_trace_begin() { delete g_trace; g_trace = new HsTrace(); }
+uint64_t hs_trace_size() { return g_trace ? g_trace->query.size() : 0; }
+void hs_trace_end(uint32_t* query, uint32_t* visit, uint32_t* slot, uint32_t* count) {
+  if (!g_trace) return;
+  const size_t n = g_trace->query.size();
+  std::copy_n(g_trace->query.begin(), n, query); std::copy_n(g_trace->visit.begin(), n, visit);
+  std::copy_n(g_trace->slot.begin(), n, slot); std::copy_n(g_trace->count.begin(), n, count);
+  delete g_trace; g_trace = nullptr;
 }
 
 }  // extern "C"
