@@ -12,7 +12,11 @@
  *   - point clouds are arrays of 16-byte points {x,y,z,w} == pcl::PointXYZ memory
  *     (PointCloudSensor.hpp:43-44); `w` is ignored on input and written as 1.0f on output;
  *   - cloud pointers may be HOST or DEVICE pointers (the library asks cudaPointerGetAttributes);
- *     result structs and 4x4 poses are always host memory;
+ *     result structs and 4x4 poses are always host memory.  Host clouds may be pageable (a std::vector, a pcl::PointCloud);
+ *     pinned memory (cudaHostRegister on the cloud's buffer, or cudaMallocHost) roughly doubles the upload rate;
+ *   - DEVICE inputs are read in place on the library's own (non-blocking) streams: they must be complete before the call.
+ *     Either synchronise the producing stream first, or name it once with s3d_set_input_stream() and every call orders its
+ *     work after what that stream holds at the time of the call.  Every call is synchronous: outputs are complete on return;
  *   - 4x4 poses are column-major doubles == Eigen::Isometry3d::matrix().data() (core/Types.hpp:53);
  *   - every entry point is re-entrant (ScanSensor.cpp:209-210 enters createConstraint from two threads);
  *   - functions return an s3d_status; they never throw across the boundary.  s3d_last_error() returns a
@@ -112,7 +116,9 @@ int s3d_voxel_downsample(s3d_context* ctx, s3d_cloud in, float leaf, float* out_
  *   NDT   doNDT<pcl::NormalDistributionsTransform>      (:84-117): resolution, step_size, outlier_ratio, maximum_iterations,
  *         transformation_epsilon are read; out->outer_iterations = nr_iterations_, out->inner_iterations = More-Thuente
  *         line-search iterations, out->n_correspondences = (point, voxel) pairs of the last evaluation
- *   GICP_OMP / NDT_OMP / anything else -> S3D_UNKNOWN_ALGORITHM with the reference's two messages (:158-164). */
+ *   GICP_OMP / NDT_OMP  (:149-157, pclomp's multi-threaded builds of the same two algorithms) run the GICP / NDT branch of this
+ *         library; a build with -DS3D_OMP_UNAVAILABLE keeps the error of a reference build without pclomp (:158-161)
+ *   anything else -> S3D_UNKNOWN_ALGORITHM with the reference's message (:162-164). */
 int s3d_gicp_align(s3d_context* ctx, s3d_cloud source, s3d_cloud target, const double guess[16],
                    const s3d_registration_parameters* params, s3d_result* out);
 
@@ -145,13 +151,24 @@ int s3d_knn_covariances(s3d_context* ctx, s3d_cloud cloud, int k, uint32_t* knn_
 int s3d_nearest_neighbors(s3d_context* ctx, s3d_cloud reference, s3d_cloud queries, const double* transform,
                           uint32_t* nn_index, float* nn_dist2);
 
-/* The CUDA stream (cudaStream_t) the context launches on for device slot `device_slot`; lets a caller
- * bracket calls with events on the right stream.  Returns NULL on a bad slot. */
+/* The CUDA stream (cudaStream_t) of the FIRST workspace of device slot `device_slot`: single (non-batch) calls issued by one
+ * host thread run on it, so a caller can bracket such calls with events.  Batch calls and concurrent callers use further
+ * streams of their own — this handle is a measurement aid, not a way to order work; calls are synchronous anyway.
+ * Returns NULL on a bad slot. */
 void* s3d_context_stream(s3d_context* ctx, int device_slot);
+
+/* Names the CUDA stream (cudaStream_t; NULL = the legacy default stream) on which the caller produces DEVICE-pointer inputs.
+ * While enabled, every call records an event on that stream and lets its own streams wait for it before they touch an input.
+ * enabled = 0 switches the ordering off again (inputs must then be complete before a call, see "Conventions"). */
+int s3d_set_input_stream(s3d_context* ctx, void* stream, int enabled);
 
 /* Counters since context creation: kernel launches issued by this library, bytes copied H2D / D2H. */
 typedef struct s3d_counters { uint64_t kernel_launches, h2d_bytes, d2h_bytes; } s3d_counters;
 int s3d_get_counters(s3d_context* ctx, s3d_counters* out);
+
+/* Work done by the GICP loop kernel since context creation (or the last reset): 256-point tiles processed by its search,
+ * trial and fitness passes, and control steps (optimiser advances) — the units behind bench.py's algorithmic bytes. */
+int s3d_get_loop_stats(s3d_context* ctx, uint64_t* tiles, uint64_t* control_steps, int reset);
 
 /* ---- per-measurement device cache ------------------------------------------------------
  * The reference rebuilds the voxel filter, both kd-trees and all covariances inside every align()
@@ -192,8 +209,9 @@ int s3d_build_map(s3d_context* ctx, const s3d_cloud* clouds, const double* poses
 
 /* Optional per-stage device timing (CUDA events on the launching stream, read back at the call's final
  * synchronisation).  Stage ids: 0 voxel filter, 1 NN grid build, 2 kNN+covariances (NDT: the target's Gaussian voxel
- * grid), 3 GICP correspondence/linearisation kernel (NDT: derivative evaluation), 4 GICP solve kernel (NDT: line-search
- * control), 5 fitness.  ms[i] / launches[i] accumulate since the last reset. */
+ * grid), 3 the GICP loop kernel — search, trial and fitness passes and the control steps of all outer iterations (NDT:
+ * derivative evaluation), 4 GICP loop set-up kernel (NDT: line-search control), 5 NDT fitness (GICP: part of stage 3).
+ * ms[i] / launches[i] accumulate since the last reset. */
 #define S3D_N_STAGES 6
 int s3d_set_profiling(s3d_context* ctx, int enabled);
 int s3d_get_stage_times(s3d_context* ctx, double ms[S3D_N_STAGES], uint64_t launches[S3D_N_STAGES], int reset);

@@ -34,6 +34,31 @@ def lib():
     return _lib
 
 
+_NATIVE_DIR = os.path.join(_HERE, "_native")
+
+
+def use_native():
+    """bench.py legs only (cpu_baseline, --impl reference): switch to a build made ON THIS MACHINE with g++ -O3 -march=native
+    (BASELINE.md 3).  The portable -O2 library travels with the repo; a -march=native one must not (oracle/_native/ is
+    git- and gpurun-ignored), so it is compiled on first use.  Returns a one-line description of what is loaded."""
+    global _lib
+    src = os.path.join(_HERE, "s3d_oracle.cpp")
+    out = os.path.join(_NATIVE_DIR, "libs3d_oracle_native.so")
+    try:
+        os.makedirs(_NATIVE_DIR, exist_ok=True)
+        newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("s3d_oracle.cpp", "ndt_oracle.inc"))
+        if not os.path.exists(out) or os.path.getmtime(out) < newest:
+            subprocess.check_call(["/usr/bin/g++", "-O3", "-march=native", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-pthread",
+                                   "-shared", "-o", out, src], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        L = C.CDLL(out)
+        L.s3d_oracle_last_error.restype = C.c_char_p
+        _lib = L
+        return "g++ -O3 -march=native -ffp-contract=off, built on this host"
+    except Exception:
+        lib()
+        return "portable g++ -O2 build (the -march=native build failed on this host)"
+
+
 def _cloud(a):
     a = as_xyzw(a)
     return a, Cloud(a.ctypes.data, a.shape[0])

@@ -35,6 +35,8 @@ def lib():
         L.s3d_create_context.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.s3d_destroy_context.argtypes = [C.c_void_p]
         L.s3d_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+        L.s3d_set_input_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.s3d_get_loop_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
         L.s3d_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.s3d_get_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.s3d_voxel_downsample.argtypes = [C.c_void_p, Cloud, C.c_float, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_int32)]
@@ -81,10 +83,15 @@ def _is_torch(a):
     return type(a).__module__.startswith("torch")
 
 
-def _cloud(a):
+def _cloud(ctx, a):
     a = as_xyzw(a)
-    ptr = a.data_ptr() if _is_torch(a) else a.ctypes.data
-    return a, Cloud(ptr, a.shape[0])
+    if _is_torch(a):
+        if a.is_cuda:
+            # the library reads device inputs on its own streams: order them after the torch stream that produced the tensor
+            import torch
+            lib().s3d_set_input_stream(ctx._h, C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream), 1)
+        return a, Cloud(a.data_ptr(), a.shape[0])
+    return a, Cloud(a.ctypes.data, a.shape[0])
 
 
 def _colmajor(T):
@@ -133,6 +140,11 @@ class Context:
         lib().s3d_get_stage_times(self._h, ms, n, int(reset))
         return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(self.STAGES)}
 
+    def loop_stats(self, reset=False):
+        t, c = C.c_uint64(0), C.c_uint64(0)
+        lib().s3d_get_loop_stats(self._h, C.byref(t), C.byref(c), int(reset))
+        return {"tiles": t.value, "control_steps": c.value}
+
     def counters(self):
         c = Counters()
         lib().s3d_get_counters(self._h, C.byref(c))
@@ -140,7 +152,7 @@ class Context:
 
     # PointCloudSensor::downsample (PointCloudSensor.cpp:190-201)
     def voxel_downsample(self, cloud, leaf, want_leaf_index=True):
-        a, c = _cloud(cloud)
+        a, c = _cloud(self, cloud)
         n = a.shape[0]
         out = np.empty((max(n, 1), 4), np.float32)
         leaf_index = np.empty(max(n, 1), np.uint32) if want_leaf_index else None
@@ -151,7 +163,7 @@ class Context:
         return out[: n_out.value].copy(), (leaf_index[:n].copy() if want_leaf_index else None), bool(ov.value)
 
     def knn_covariances(self, cloud, k):
-        a, c = _cloud(cloud)
+        a, c = _cloud(self, cloud)
         n = a.shape[0]
         idx = np.empty((n, k), np.uint32)
         d2 = np.empty((n, k), np.float32)
@@ -161,8 +173,8 @@ class Context:
         return idx, d2, cov.reshape(n, 3, 3).transpose(0, 2, 1).copy()
 
     def nearest_neighbors(self, reference, queries, transform=None):
-        r, rc = _cloud(reference)
-        q, qc = _cloud(queries)
+        r, rc = _cloud(self, reference)
+        q, qc = _cloud(self, queries)
         idx = np.empty(q.shape[0], np.uint32)
         d2 = np.empty(q.shape[0], np.float32)
         t = _colmajor(transform) if transform is not None else None
@@ -172,8 +184,8 @@ class Context:
 
     # align() (PointCloudSensor.cpp:119-174); returns the Result struct, status inside (0 ok, 1..3 = NoMatch reasons)
     def gicp_align(self, source, target, guess=None, params=None):
-        s, sc = _cloud(source)
-        t, tc = _cloud(target)
+        s, sc = _cloud(self, source)
+        t, tc = _cloud(self, target)
         g = _colmajor(guess)
         p = params if params is not None else RegistrationParameters.defaults()
         res = Result()
@@ -188,8 +200,8 @@ class Context:
         sc = (Cloud * n)()
         tc = (Cloud * n)()
         for i in range(n):
-            a, c = _cloud(sources[i]); keep.append(a); sc[i] = c
-            a, c = _cloud(targets[i]); keep.append(a); tc[i] = c
+            a, c = _cloud(self, sources[i]); keep.append(a); sc[i] = c
+            a, c = _cloud(self, targets[i]); keep.append(a); tc[i] = c
         g = np.ascontiguousarray(np.stack([_colmajor(None if guesses is None else guesses[i]) for i in range(n)]))
         p = params if params is not None else RegistrationParameters.defaults()
         res = (Result * n)()
@@ -204,8 +216,8 @@ class Context:
         sc = (Cloud * n)()
         tc = (Cloud * n)()
         for i in range(n):
-            a, c = _cloud(sources[i]); keep.append(a); sc[i] = c
-            a, c = _cloud(targets[i]); keep.append(a); tc[i] = c
+            a, c = _cloud(self, sources[i]); keep.append(a); sc[i] = c
+            a, c = _cloud(self, targets[i]); keep.append(a); tc[i] = c
         g = np.ascontiguousarray(np.stack([_colmajor(None if guesses is None else guesses[i]) for i in range(n)]))
         rc = (Result * n)()
         rf = (Result * n)()
@@ -238,7 +250,7 @@ class PreparedCloud:
 
 
 def _prepare_cloud(self, cloud, density, k=20, device_slot=0):
-    a, c = _cloud(cloud)
+    a, c = _cloud(self, cloud)
     h = C.c_void_p()
     st = lib().s3d_prepare_cloud(self._h, device_slot, c, float(density), int(k), C.byref(h))
     self._check(st, "s3d_prepare_cloud")
@@ -250,7 +262,7 @@ def _prepare_clouds(self, clouds, density, k=20, device_slot=0):
     keep = []
     cc = (Cloud * n)()
     for i in range(n):
-        a, c = _cloud(clouds[i]); keep.append(a); cc[i] = c
+        a, c = _cloud(self, clouds[i]); keep.append(a); cc[i] = c
     hh = (C.c_void_p * n)()
     st = lib().s3d_prepare_clouds(self._h, device_slot, cc, n, float(density), int(k), hh)
     self._check(st, "s3d_prepare_clouds")
@@ -280,7 +292,7 @@ def _gicp_align_prepared_batch(self, sources, targets, guesses=None, params=None
 
 
 def _transform_cloud(self, cloud, T):
-    a, c = _cloud(cloud)
+    a, c = _cloud(self, cloud)
     t = _colmajor(T)
     out = np.empty((a.shape[0], 4), np.float32)
     self._check(lib().s3d_transform_cloud(self._h, c, t.ctypes.data, out.ctypes.data), "s3d_transform_cloud")
@@ -288,7 +300,7 @@ def _transform_cloud(self, cloud, T):
 
 
 def _remove_outliers(self, cloud, radius, min_neighbors):
-    a, c = _cloud(cloud)
+    a, c = _cloud(self, cloud)
     out = np.empty((max(a.shape[0], 1), 4), np.float32)
     n = C.c_uint64(0)
     self._check(lib().s3d_remove_outliers(self._h, c, float(radius), int(min_neighbors), out.ctypes.data, C.byref(n)), "s3d_remove_outliers")
@@ -302,7 +314,7 @@ def _build_map(self, clouds, poses, outlier_radius=0.2, outlier_neighbors=3, res
     cc = (Cloud * max(n, 1))()
     total = 0
     for i in range(n):
-        a, c = _cloud(clouds[i]); keep.append(a); cc[i] = c; total += a.shape[0]
+        a, c = _cloud(self, clouds[i]); keep.append(a); cc[i] = c; total += a.shape[0]
     P = np.ascontiguousarray(np.stack([_colmajor(p) for p in poses])) if n else np.zeros((1, 4, 4))
     out = np.empty((max(total, 1), 4), np.float32)
     m = C.c_uint64(0)

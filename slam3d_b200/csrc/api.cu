@@ -8,7 +8,10 @@
 // There is NO CPU fallback: without a CUDA device every entry point returns S3D_INTERNAL_ERROR.
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -32,6 +35,52 @@ struct DeviceCtx {
 
 }  // namespace s3d
 
+namespace s3d {
+// Long-lived host threads of a context: batch calls hand their per-stream workers to the pool instead of spawning and
+// joining std::threads on every call (round 1: 6 spawns per call and device).  A second batch call that arrives while the
+// pool is busy (the API is re-entrant) falls back to threads of its own.
+class WorkerPool {
+ public:
+  ~WorkerPool() {
+    { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
+    cv_job_.notify_all();
+    for (auto& t : threads_) t.join();
+  }
+  std::mutex call_mu;  // held by the batch call that owns the pool
+  // runs f(0) .. f(n-1) concurrently, one index per thread, and returns when all have finished
+  void run(int n, const std::function<void(int)>& f) {
+    std::unique_lock<std::mutex> lk(mu_);
+    while ((int)threads_.size() < n) { const int id = (int)threads_.size(); threads_.emplace_back([this, id] { loop(id); }); }
+    job_ = &f; n_job_ = n; pending_ = n; ++generation_;
+    cv_job_.notify_all();
+    cv_done_.wait(lk, [this] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+ private:
+  void loop(int id) {
+    uint64_t seen = 0;
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+      cv_job_.wait(lk, [&] { return stop_ || (generation_ != seen && id < n_job_); });
+      if (stop_) return;
+      seen = generation_;
+      const std::function<void(int)>* f = job_;
+      lk.unlock();
+      (*f)(id);
+      lk.lock();
+      if (--pending_ == 0) cv_done_.notify_all();
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex mu_;
+  std::condition_variable cv_job_, cv_done_;
+  const std::function<void(int)>* job_ = nullptr;
+  int n_job_ = 0, pending_ = 0;
+  uint64_t generation_ = 0;
+  bool stop_ = false;
+};
+}  // namespace s3d
+
 struct s3d_prepared_cloud {
   int device_slot = 0;
   s3d::SlotInfo info;        // host copy; gpts / normals / table point into `block`
@@ -45,6 +94,7 @@ struct s3d_context {
   std::vector<std::unique_ptr<s3d::DeviceCtx>> devs;
   std::mutex mu;
   uint64_t launches = 0, h2d = 0, d2h = 0;
+  uint64_t loop_tiles = 0, loop_ctrl_steps = 0;
   bool profiling = false;
   double stage_ms[S3D_N_STAGES] = {0, 0, 0, 0, 0, 0};
   uint64_t stage_launches[S3D_N_STAGES] = {0, 0, 0, 0, 0, 0};
@@ -54,6 +104,17 @@ struct s3d_context {
   // (252-register kernels) are fastest with 3.
   int streams_per_device = 6;
   int streams_small = 3;
+  cudaStream_t input_stream = nullptr;  // s3d_set_input_stream: device-pointer inputs are produced on this stream
+  bool have_input_stream = false;
+  s3d::WorkerPool pool;
+  // n workers through the pool, or through threads of the call's own when another batch call holds the pool
+  void parallel(int n, const std::function<void(int)>& f) {
+    std::unique_lock<std::mutex> lk(pool.call_mu, std::try_to_lock);
+    if (lk.owns_lock()) { pool.run(n, f); return; }
+    std::vector<std::thread> th;
+    for (int i = 0; i < n; ++i) th.emplace_back([&f, i] { f(i); });
+    for (auto& t : th) t.join();
+  }
 };
 
 namespace s3d {
@@ -62,6 +123,7 @@ namespace s3d {
 // device after 1/W of the upload time and its kernels run while the next chunk uploads.  (Left to themselves the W streams
 // share the link and all uploads end together, with the GPU idle until then: 64 pairs, 268 MB, measured in DESIGN.md 5.)
 static thread_local bool t_gate_uploads = false;
+static thread_local bool t_blocking_sync = false;  // worker of a multi-threaded batch call: sleep in Workspace::sync()
 
 // Chunk size for `n` work items on W streams: the number of chunks is a multiple of W (every stream gets the same number of
 // chunks — 4 chunks on 3 streams measured 15 % slower than 3 or 6) and no chunk exceeds `cap` items.
@@ -84,12 +146,16 @@ struct WsLease {
     ws->profiling = ctx->profiling;
     static const bool gate_enabled = [] { const char* e = getenv("S3D_GATE_UPLOADS"); return !e || atoi(e) != 0; }();  // 0: A/B measurements
     ws->upload_gate = (t_gate_uploads && gate_enabled) ? &dc->upload_mu : nullptr;
+    static const bool blocking_enabled = [] { const char* e = getenv("S3D_BLOCKING_SYNC"); return !e || atoi(e) != 0; }();  // 0: A/B measurements
+    ws->blocking_sync = t_blocking_sync && blocking_enabled;
+    ws->wait_input = ctx->have_input_stream; ws->input_stream = ctx->input_stream;
   }
   ~WsLease() {
     {
       std::lock_guard<std::mutex> g(ctx->mu);
       ctx->launches += ws->launches; ctx->h2d += ws->h2d; ctx->d2h += ws->d2h;
-      ws->launches = ws->h2d = ws->d2h = 0;
+      ctx->loop_tiles += ws->passes; ctx->loop_ctrl_steps += ws->ctrl_steps;
+      ws->launches = ws->h2d = ws->d2h = 0; ws->passes = ws->ctrl_steps = 0;
       if (ws->profiling) { cudaStreamSynchronize(ws->stream); ws->collect_spans(); }
       for (int i = 0; i < S3D_N_STAGES; ++i) {
         ctx->stage_ms[i] += ws->stage_ms[i]; ctx->stage_launches[i] += ws->stage_launches[i];
@@ -173,11 +239,48 @@ static void align_chunk(s3d_context* ctx, int slot, const s3d_cloud* sources, co
     }
 }
 
+// GICP_OMP / NDT_OMP (PointCloudSensor.cpp:149-157) are pclomp's multi-threaded builds of the same two algorithms — same
+// objective, same parameters — so on the GPU path they select the GICP / NDT branch.  Building with
+// -DS3D_OMP_UNAVAILABLE keeps the behaviour of a reference build without pclomp (:158-161: std::runtime_error).
+static int effective_algorithm(int alg) {
+#ifndef S3D_OMP_UNAVAILABLE
+  if (alg == S3D_ALG_GICP_OMP) return S3D_ALG_GICP;
+  if (alg == S3D_ALG_NDT_OMP) return S3D_ALG_NDT;
+#endif
+  return alg;
+}
+
+// S3D_TIMELINE=1 (measurement aid): device time stamps of a chunk's stages relative to one process-wide base event, printed
+// to stderr after the chunk — the Gantt chart of the streams of a batch call (profiles/r02_summary.md).
+struct Timeline {
+  static bool enabled() { static const bool e = getenv("S3D_TIMELINE") != nullptr; return e; }
+  static cudaEvent_t base(cudaStream_t st) {
+    static std::mutex mu; static cudaEvent_t ev = nullptr;
+    std::lock_guard<std::mutex> g(mu);
+    if (!ev) { cudaEventCreate(&ev); cudaEventRecord(ev, st); }
+    return ev;
+  }
+  cudaStream_t st; cudaEvent_t b; std::vector<std::pair<const char*, cudaEvent_t>> marks; int n;
+  Timeline(Workspace& ws, int n_) : st(ws.stream), b(nullptr), n(n_) { if (enabled()) { b = base(st); mark("begin"); } }
+  void mark(const char* what) { if (!b) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); marks.emplace_back(what, e); }
+  ~Timeline() {
+    if (!b) return;
+    std::string line = "[s3d timeline] stream " + std::to_string((unsigned long long)(uintptr_t)st % 100000) + " pairs " + std::to_string(n) + ":";
+    for (auto& m : marks) { float ms = 0.f; cudaEventSynchronize(m.second); cudaEventElapsedTime(&ms, b, m.second); char buf[64]; snprintf(buf, sizeof buf, " %s %.3f", m.first, ms); line += buf; cudaEventDestroy(m.second); }
+    fprintf(stderr, "%s\n", line.c_str());
+  }
+};
+
 static void align_chunk_body(Workspace& ws, const std::vector<const float*>& clouds, const std::vector<uint64_t>& sizes, const double* guesses,
-                             const s3d_registration_parameters& cfg, int n, s3d_result* out) {
+                             const s3d_registration_parameters& cfg_in, int n, s3d_result* out) {
+  s3d_registration_parameters cfg = cfg_in;
+  cfg.registration_algorithm = effective_algorithm(cfg_in.registration_algorithm);
+  Timeline tl(ws, n);
   setup_batch(ws, clouds, sizes, n);
+  tl.mark("setup");
   const float leaf = cfg.point_cloud_density > 0 ? (float)cfg.point_cloud_density : 0.f;  // :127, setLeafSize(float)
   run_voxel(ws, leaf);
+  tl.mark("voxel");
   const bool gicp = cfg.registration_algorithm == S3D_ALG_GICP;
   const bool ndt = cfg.registration_algorithm == S3D_ALG_NDT;
   const bool k_ok = cfg.correspondence_randomness >= 1 && cfg.correspondence_randomness <= kMaxK;
@@ -186,7 +289,7 @@ static void align_chunk_body(Workspace& ws, const std::vector<const float*>& clo
     // the reference evaluates the <100 gate before the algorithm switch (:134-135 then :139-165)
     SlotInfo* hs = ws.h_slots.as<SlotInfo>();
     S3D_CUDA(cudaMemcpyAsync(hs, ws.slots.p, sizeof(SlotInfo) * ws.n_slots, cudaMemcpyDeviceToHost, ws.stream));
-    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.sync();
     ws.d2h += sizeof(SlotInfo) * ws.n_slots;
     for (int i = 0; i < n; ++i) {
       memset(&out[i], 0, sizeof out[i]);
@@ -208,9 +311,12 @@ static void align_chunk_body(Workspace& ws, const std::vector<const float*>& clo
     run_ndt(ws, params, guesses, out);
     return;
   }
+  tl.mark("grid");
   run_knn_covariances(ws, cfg.correspondence_randomness, nullptr, nullptr);
+  tl.mark("knn");
   std::vector<s3d_registration_parameters> params(n, cfg);
   run_gicp(ws, params, guesses, out);
+  tl.mark("gicp");
 }
 
 static const char* status_text(int st, const s3d_result& r, const s3d_registration_parameters& cfg, std::string& buf) {
@@ -294,10 +400,27 @@ void* s3d_context_stream(s3d_context* ctx, int device_slot) {
   return dc->all.empty() ? nullptr : (void*)dc->all[0]->stream;
 }
 
+int s3d_set_input_stream(s3d_context* ctx, void* stream, int enabled) {
+  if (!ctx) return S3D_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->input_stream = static_cast<cudaStream_t>(stream);
+  ctx->have_input_stream = enabled != 0;
+  return S3D_OK;
+}
+
 int s3d_get_counters(s3d_context* ctx, s3d_counters* out) {
   if (!ctx || !out) return S3D_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(ctx->mu);
   out->kernel_launches = ctx->launches; out->h2d_bytes = ctx->h2d; out->d2h_bytes = ctx->d2h;
+  return S3D_OK;
+}
+
+int s3d_get_loop_stats(s3d_context* ctx, uint64_t* tiles, uint64_t* control_steps, int reset) {
+  if (!ctx) return S3D_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (tiles) *tiles = ctx->loop_tiles;
+  if (control_steps) *control_steps = ctx->loop_ctrl_steps;
+  if (reset) ctx->loop_tiles = ctx->loop_ctrl_steps = 0;
   return S3D_OK;
 }
 
@@ -334,13 +457,13 @@ int s3d_voxel_downsample(s3d_context* ctx, s3d_cloud in, float leaf, float* out_
     run_voxel(ws, leaf, leaf_index ? lk.as<uint32_t>() : nullptr);
     SlotInfo* hs = ws.h_slots.as<SlotInfo>();
     S3D_CUDA(cudaMemcpyAsync(hs, ws.slots.p, sizeof(SlotInfo), cudaMemcpyDeviceToHost, ws.stream));
-    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.sync();
     ws.d2h += sizeof(SlotInfo);
     *n_out = hs[0].n_pts;
     if (overflow) *overflow = hs[0].overflow;
     copy_out(ws, out_xyzw, ws.work.p, 16 * size_t(hs[0].n_pts));
     copy_out(ws, leaf_index, lk.p, 4 * size_t(in.n));
-    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.sync();
     return S3D_OK;
   });
 }
@@ -364,12 +487,12 @@ int s3d_knn_covariances(s3d_context* ctx, s3d_cloud cloud, int k, uint32_t* knn_
     if (covariances) { dc.reserve(72 * n); run_expand_cov(ws, dc.as<double>()); }
     int32_t* hf = ws.h_small.as<int32_t>();
     S3D_CUDA(cudaMemcpyAsync(hf, ws.flags.p, 16, cudaMemcpyDeviceToHost, ws.stream));
-    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.sync();
     check_arena(ws, hf);
     copy_out(ws, knn_index, di.p, 4 * n * k);
     copy_out(ws, knn_dist2, dd.p, 4 * n * k);
     copy_out(ws, covariances, dc.p, 72 * n);
-    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.sync();
     });
     return rc;
   });
@@ -398,11 +521,11 @@ int s3d_nearest_neighbors(s3d_context* ctx, s3d_cloud reference, s3d_cloud queri
     run_nn_stage(ws, 0, 1, Td, di.as<uint32_t>(), dd.as<float>());
     int32_t* hf = ws.h_small.as<int32_t>();
     S3D_CUDA(cudaMemcpyAsync(hf, ws.flags.p, 16, cudaMemcpyDeviceToHost, ws.stream));
-    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.sync();
     check_arena(ws, hf);
     copy_out(ws, nn_index, di.p, 4 * queries.n);
     copy_out(ws, nn_dist2, dd.p, 4 * queries.n);
-    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.sync();
     });
     return S3D_OK;
   });
@@ -444,13 +567,21 @@ static void prepare_chunk(s3d_context* ctx, int device_slot, const s3d_cloud* cl
     int32_t* hf = ws.h_small.as<int32_t>();
     S3D_CUDA(cudaMemcpyAsync(hs, ws.slots.p, sizeof(SlotInfo) * n, cudaMemcpyDeviceToHost, ws.stream));
     S3D_CUDA(cudaMemcpyAsync(hf, ws.flags.p, 16, cudaMemcpyDeviceToHost, ws.stream));
-    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.sync();
     ws.d2h += sizeof(SlotInfo) * n + 16;
     ws.collect_spans();
     check_arena(ws, hf);
   });
   auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
   std::vector<std::unique_ptr<s3d_prepared_cloud>> hh(n);
+  struct BlockGuard {  // a failure below (allocation, copy, synchronise) hands the device blocks back instead of leaking them
+    std::vector<std::unique_ptr<s3d_prepared_cloud>>& hh; DeviceCtx* dc; bool armed = true;
+    ~BlockGuard() {
+      if (!armed) return;
+      std::lock_guard<std::mutex> g(dc->mu);
+      for (auto& h : hh) if (h && h->block) { dc->free_blocks.emplace_back(h->block, h->block_bytes); h->block = nullptr; }
+    }
+  } guard{hh, ctx->devs[device_slot].get()};
   for (int i = 0; i < n; ++i) {
     std::unique_ptr<s3d_prepared_cloud>& h = hh[i];
     h.reset(new s3d_prepared_cloud());
@@ -473,7 +604,8 @@ static void prepare_chunk(s3d_context* ctx, int device_slot, const s3d_cloud* cl
     }
     h->info.hash_off = 0; h->info.off = 0; h->info.raw = nullptr;
   }
-  S3D_CUDA(cudaStreamSynchronize(ws.stream));
+  ws.sync();
+  guard.armed = false;
   for (int i = 0; i < n; ++i) out[i] = hh[i].release();
 }
 }  // namespace s3d
@@ -488,7 +620,10 @@ int s3d_prepare_clouds(s3d_context* ctx, int device_slot, const s3d_cloud* cloud
   std::vector<int> st(W, S3D_OK);
   std::vector<std::string> errs(W);
   std::atomic<int> next{0};
+  const bool threaded = !(W == 1 || n <= 2);
   auto worker = [&](int w) {
+    t_gate_uploads = threaded; t_blocking_sync = threaded;
+    g_last_error.clear();
     st[w] = guarded([&]() -> int {
       for (;;) {
         const int b = next.fetch_add(1) * chunk;
@@ -497,14 +632,11 @@ int s3d_prepare_clouds(s3d_context* ctx, int device_slot, const s3d_cloud* cloud
       }
       return S3D_OK;
     });
-    if (st[w] != S3D_OK) errs[w] = g_last_error;
+    errs[w] = g_last_error;
+    t_gate_uploads = false; t_blocking_sync = false;
   };
-  if (W == 1 || n <= 2) worker(0);
-  else {
-    std::vector<std::thread> th;
-    for (int w = 0; w < W; ++w) th.emplace_back([&worker, w] { t_gate_uploads = true; worker(w); });
-    for (auto& t : th) t.join();
-  }
+  if (!threaded) worker(0);
+  else ctx->parallel(W, worker);
   for (int w = 0; w < W; ++w)
     if (st[w] != S3D_OK) {
       for (int i = 0; i < n; ++i) { s3d_release_cloud(ctx, out[i]); out[i] = nullptr; }
@@ -536,7 +668,9 @@ uint64_t s3d_prepared_cloud_size(const s3d_prepared_cloud* cloud) { return cloud
 namespace s3d {
 // One sub-batch of align() calls on prepared clouds (all on device slot `slot`).
 static void align_prepared_chunk(s3d_context* ctx, int slot, const s3d_prepared_cloud* const* sources, const s3d_prepared_cloud* const* targets,
-                                 const double* guesses, const s3d_registration_parameters& cfg, int n, s3d_result* out) {
+                                 const double* guesses, const s3d_registration_parameters& cfg_in, int n, s3d_result* out) {
+  s3d_registration_parameters cfg = cfg_in;
+  cfg.registration_algorithm = effective_algorithm(cfg_in.registration_algorithm);
   WsLease lease(ctx, slot);
   Workspace& ws = *lease;
   S3D_CUDA(cudaSetDevice(ws.device));
@@ -567,7 +701,7 @@ static void align_prepared_chunk(s3d_context* ctx, int slot, const s3d_prepared_
       out[i].n_source = ws.h_n[2 * i]; out[i].n_target = ws.h_n[2 * i + 1];
       out[i].status = (out[i].n_source < 100 || out[i].n_target < 100) ? S3D_TOO_FEW_POINTS : S3D_UNKNOWN_ALGORITHM;
     }
-    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.sync();
     if (cfg.registration_algorithm == S3D_ALG_GICP_OMP || cfg.registration_algorithm == S3D_ALG_NDT_OMP)
       set_error("OMP is not available, you need to rebuild SLAM3D with OMP or use another matching algorithm.");
     else if (cfg.registration_algorithm == S3D_ALG_NDT)
@@ -589,7 +723,7 @@ int s3d_gicp_align_prepared_batch(s3d_context* ctx, const s3d_prepared_cloud* co
     if (!sources[i] || !targets[i]) return S3D_INVALID_ARGUMENT;
     if (sources[i]->device_slot != slot || targets[i]->device_slot != slot) { set_error("prepared clouds of one call must live on one device"); return S3D_INVALID_ARGUMENT; }
     for (const s3d_prepared_cloud* h : {sources[i], targets[i]})
-      if (h->density != params->point_cloud_density || (params->registration_algorithm == S3D_ALG_GICP && h->k != params->correspondence_randomness)) {
+      if (h->density != params->point_cloud_density || (effective_algorithm(params->registration_algorithm) == S3D_ALG_GICP && h->k != params->correspondence_randomness)) {
         set_error("prepared cloud was built with another point_cloud_density / correspondence_randomness");
         return S3D_INVALID_ARGUMENT;
       }
@@ -599,7 +733,10 @@ int s3d_gicp_align_prepared_batch(s3d_context* ctx, const s3d_prepared_cloud* co
   std::vector<std::string> errs(W);
   std::atomic<int> next{0};
   const int chunk = balanced_chunk(n_pairs, W, ctx->max_pairs_per_launch);
+  const bool threaded = !(W == 1 || n_pairs == 1);
   auto worker = [&](int w) {
+    t_gate_uploads = threaded; t_blocking_sync = threaded;
+    g_last_error.clear();
     st[w] = guarded([&]() -> int {
       for (;;) {
         const int b = next.fetch_add(1) * chunk;
@@ -609,15 +746,13 @@ int s3d_gicp_align_prepared_batch(s3d_context* ctx, const s3d_prepared_cloud* co
       }
       return S3D_OK;
     });
-    if (st[w] != S3D_OK) errs[w] = g_last_error;
+    errs[w] = g_last_error;  // also the message of a per-pair status >= 4 inside a batch that ran (S3D_OK)
+    t_gate_uploads = false; t_blocking_sync = false;
   };
-  if (W == 1 || n_pairs == 1) worker(0);
-  else {
-    std::vector<std::thread> th;
-    for (int w = 0; w < W; ++w) th.emplace_back([&worker, w] { t_gate_uploads = true; worker(w); });
-    for (auto& t : th) t.join();
-  }
+  if (!threaded) worker(0);
+  else ctx->parallel(W, worker);
   for (int w = 0; w < W; ++w) if (st[w] != S3D_OK) { set_error(errs[w]); return st[w]; }
+  for (int w = 0; w < W; ++w) if (!errs[w].empty()) { set_error(errs[w]); break; }
   return S3D_OK;
 }
 
@@ -641,7 +776,7 @@ int s3d_transform_cloud(s3d_context* ctx, s3d_cloud in, const double T[16], floa
     Workspace& ws = *lease;
     const uint32_t n = run_accumulate(ws, {in.xyzw}, {in.n}, T);
     copy_out(ws, out_xyzw, ws.accu.p, 16 * (size_t)n);
-    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.sync();
     return S3D_OK;
   });
 }
@@ -654,9 +789,10 @@ int s3d_remove_outliers(s3d_context* ctx, s3d_cloud in, double radius, unsigned 
     WsLease lease(ctx, 0);
     Workspace& ws = *lease;
     const double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    ws.order_after_input();
     if (!(radius > 0 && min_neighbors > 0)) {  // :214 — the reference hands the input back
       S3D_CUDA(cudaMemcpyAsync(out_xyzw, in.xyzw, 16 * in.n, cudaMemcpyDefault, ws.stream));
-      S3D_CUDA(cudaStreamSynchronize(ws.stream));
+      ws.sync();
       *n_out = in.n;
       return S3D_OK;
     }
@@ -667,7 +803,7 @@ int s3d_remove_outliers(s3d_context* ctx, s3d_cloud in, double radius, unsigned 
     uint32_t kept = 0;
     with_arena_retry(ws, [&] { kept = run_radius_filter(ws, ws.accu.as<float4>(), (uint32_t)in.n, radius, min_neighbors, ws.accu2.as<float4>()); });
     copy_out(ws, out_xyzw, ws.accu2.p, 16 * (size_t)kept);
-    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.sync();
     *n_out = kept;
     return S3D_OK;
   });
@@ -699,11 +835,11 @@ int s3d_build_map(s3d_context* ctx, const s3d_cloud* clouds, const double* poses
     run_voxel(ws, (float)resolution);
     SlotInfo* hs = ws.h_slots.as<SlotInfo>();
     S3D_CUDA(cudaMemcpyAsync(hs, ws.slots.p, sizeof(SlotInfo), cudaMemcpyDeviceToHost, ws.stream));
-    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.sync();
     ws.d2h += sizeof(SlotInfo);
     *n_out = hs[0].n_pts;
     copy_out(ws, out_xyzw, ws.work.p, 16 * (size_t)hs[0].n_pts);
-    S3D_CUDA(cudaStreamSynchronize(ws.stream));
+    ws.sync();
     return S3D_OK;
   });
 }
@@ -722,12 +858,16 @@ static int align_batch_impl(s3d_context* ctx, const s3d_cloud* sources, const s3
   std::vector<std::string> errs(nd * W);
   std::vector<std::atomic<int>> next(nd);
   for (auto& a : next) a.store(0);
-  auto worker = [&](int d, int w) {
+  const bool threaded = !(nd * W == 1 || n_pairs == 1);
+  auto worker = [&](int i) {
+    const int d = i / W, w = i % W;
     const int lo = (int)((int64_t)n_pairs * d / nd), hi = (int)((int64_t)n_pairs * (d + 1) / nd);
     const int shard = hi - lo;
     if (shard <= 0) return;
+    t_gate_uploads = threaded && W > 1; t_blocking_sync = threaded;
+    g_last_error.clear();
     const int chunk = balanced_chunk(shard, W, ctx->max_pairs_per_launch);
-    st[d * W + w] = guarded([&]() -> int {
+    st[i] = guarded([&]() -> int {
       for (;;) {
         const int c = next[d].fetch_add(1);
         const int b = lo + c * chunk;
@@ -737,16 +877,14 @@ static int align_batch_impl(s3d_context* ctx, const s3d_cloud* sources, const s3
       }
       return S3D_OK;
     });
-    if (st[d * W + w] != S3D_OK) errs[d * W + w] = g_last_error;
+    errs[i] = g_last_error;  // also the message of a per-pair status >= 4 inside a batch that ran (S3D_OK)
+    t_gate_uploads = false; t_blocking_sync = false;
   };
-  if (nd * W == 1 || n_pairs == 1) worker(0, 0);
-  else {
-    std::vector<std::thread> th;
-    for (int d = 0; d < nd; ++d) for (int w = 0; w < W; ++w) th.emplace_back([&worker, d, w, W] { t_gate_uploads = W > 1; worker(d, w); });
-    for (auto& t : th) t.join();
-  }
+  if (!threaded) worker(0);
+  else ctx->parallel(nd * W, worker);
   for (int i = 0; i < nd * W; ++i)
     if (st[i] != S3D_OK) { set_error(errs[i]); return st[i]; }
+  for (int i = 0; i < nd * W; ++i) if (!errs[i].empty()) { set_error(errs[i]); break; }
   return S3D_OK;
 }
 

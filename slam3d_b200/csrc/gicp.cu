@@ -1,35 +1,41 @@
 // gicp.cu — the Generalized-ICP loop of pcl::GeneralizedIterativeClosestPoint as driven by slam3d's doICP
 // (slam3d/sensor/pcl/PointCloudSensor.cpp:52-82) and the fitness score of :73.   Semantics: SURVEY A.4-A.6.
 //
-// The loop runs in ROUNDS of four launches for the whole batch; every pair carries its own phase, so pairs advance
-// independently and the host only polls an "active pairs" counter:
-//   gicp_iter_kernel   pairs that start an outer iteration.  One thread per moving point:  q = T_f32 * (guess_f32 * p)  ->
-//                      exact 1-NN in the fixed cloud (nn_search.cuh; skipped when the previous correspondence is provably
-//                      still nearest)  ->  d2 < max_corr^2  ->  M = (R C1 R^T + C2)^-1 (FP64, stored)  ->  the CTA reduces
-//                      the point's 14 features to the 74 sums of gicp_math.h in a fixed order: 60 x-independent sums that
-//                      give the whole Hessian, and the 13 residual sums + count of PCL's first objective evaluation.
-//   gicp_ctrl_kernel   one CTA per pair: fixed-order sum of the tile partials, then ONE thread advances PCL's inner
-//                      optimiser (estimateRigidTransformationNewton as a resumable state machine) to its next objective
-//                      evaluation, or finishes the outer iteration (convergence test of computeTransformation).
-//   gicp_eval_kernel   pairs whose optimiser asked for f at a trial state: one pass over the stored correspondences with the
-//                      residual formed exactly as PCL forms it (float32 T(x)*p, float subtraction) -> 13 sums per tile.
-//   gicp_ctrl_kernel   again.
+// The whole loop of a batch is ONE persistent kernel (gicp_loop_kernel) with a device-side scheduler; the host launches it once
+// and reads the results — no per-iteration launch, no host poll (round 1 spent 4 of 18 ms per 64 pairs in 690 control
+// launches and 10 polls per chunk).  Pairs are independent, so there is no grid-wide barrier either: every pair is a small
+// dataflow machine whose current PASS is published as (epoch, number of 256-point tiles); CTAs claim tiles of any pair with one
+// atomic, and the CTA that delivers the last tile of a pass runs the pair's control step and publishes the next pass:
+//   search pass   (iter_tile)     q = T_f32 * (guess_f32 * p) -> exact 1-NN in the fixed cloud (nn_search.cuh; skipped when the
+//                                 previous correspondence is provably still nearest) -> d2 < max_corr^2 -> M = (R C1 R^T + C2)^-1
+//                                 (FP64, stored) -> the 74 sums of gicp_math.h per tile in a fixed order: 60 x-independent sums
+//                                 that give the whole Hessian, and the 13 residual sums + count of PCL's first objective evaluation
+//   control step  (ctrl_step)     fixed-order sum of the tile partials, then ONE thread advances PCL's inner optimiser
+//                                 (estimateRigidTransformationNewton as a resumable state machine, pair state staged in shared
+//                                 memory) to its next objective evaluation, or finishes the outer iteration (convergence test)
+//   trial pass    (eval_tile)     f at the pending back-tracking trial(s): one pass over the stored correspondences with the
+//                                 residual formed exactly as PCL forms it (float32 T(x)*p, float subtraction) -> 13 sums per tile
+//   fitness pass  (fitness_tile)  getFitnessScore once the outer loop has ended; its last tile closes the pair
+// While one pair sits in its (serial, ~10 us) control step the CTAs work on tiles of the other pairs; a CTA that finds nothing
+// to claim sleeps (nanosleep) until a pass is published or no pair is active.  Progress never depends on a CTA that is not
+// running: waiting CTAs wait only for tiles and control steps that are being executed.  A cycle-count watchdog ends the
+// kernel with an error flag should that invariant ever be broken.
+// Data written and read inside the kernel by different CTAs (pair state, correspondences, Mahalanobis matrices, search hints,
+// tile partials) is handed over with a release atomic on the producer side and read from L2 (ld.global.cg) on the consumer
+// side, because L1 is not coherent; the search structures (points, hash, normals) are immutable and stay on the cached path.
 // (Tried and dropped, B200, 64 pairs per step: a separate search kernel in which one thread handles 2/3/4 consecutive points
-// and passes each result on as a hint for the next — 10.1 / 11.6 / 13.0 ms per step against 8.6 ms: the saved instructions
-// do not make up for the probe latency that fewer threads in flight can hide.  Also tried and dropped: splitting this kernel
-// into a barrier-free search kernel (CTAs of 32 / 64 / 128 / 256 threads) and a separate 74-sum tile kernel, because 37 % of the
-// stall samples of a late-iteration launch sit at the reduction barrier (profiles/r01g_summary.md) — results bit-identical,
-// stage time 4.6-4.9 ms against 4.55 ms fused per 32 pairs: the waiting warps cost no issue slots and the extra launch does.
-// Also dropped: per-lane cell cursors (+12 %) and CTA-level compaction of the points that still need a search (equal):
-// profiles/r01h_summary.md.
-// Kept: the two-pass 27-block of nn_search.cuh (scan_block<true>; cells noted in s_cells) — gicp_iter 8.60 -> 8.26 ms per 64 pairs.)
+// and passes each result on as a hint for the next — 10.1 / 11.6 / 13.0 ms per step against 8.6 ms; splitting the search and
+// the 74-sum reduction into two kernels; per-lane cell cursors (+12 %); CTA-level compaction of the points that still need a
+// search (equal): profiles/r01h_summary.md.  Round 2, first attempt: one launch per pass inside a CUDA-graph WHILE node with
+// the control step fused by the same ticket scheme — correct, but every launch ended with one control step during which the
+// GPU idled, and its __threadfence() calls dropped L1 once per tile: 13.3 ms per 64 pairs against 12.2 ms with separate
+// control launches (profiles/r02_summary.md).)
 // Because every float operation that PCL's decisions depend on is mirrored and the double sums differ only in order, the
 // GPU follows the oracle's iterate sequence (same inner/outer iteration counts, bit-identical poses in the test-suite).
-// Reductions use fixed trees: results are bit-reproducible run to run and independent of batch composition.
+// Reductions use fixed trees: results are bit-reproducible run to run and independent of batch composition and scheduling.
 // Roofline: per outer iteration 16 B (moving point) + 32 B (its normal) + gathered 16 B + 32 B (fixed point + normal) per
 // correspondence, + 48 B (M) written; per evaluation 16 + 16 + 48 B.  The working set is L2 resident; the search is latency
 // bound on the hash probes.
-#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 
@@ -41,22 +47,23 @@ namespace s3d {
 constexpr int kFeat = 14;  // M00 M01 M02 M11 M12 M22 | px py pz | (Md)0 (Md)1 (Md)2 | d^T M d | valid
 
 struct MomentSpec { uint8_t a, b, c; };  // moment = sum f[a]*f[b]*f[c]
-__constant__ MomentSpec c_spec[kNumMoments];
-
-static void build_moment_spec(MomentSpec* spec) {
-  const int Mi[6] = {0, 1, 2, 3, 4, 5};
-  const int phi[4] = {6, 7, 8, 13};
-  int ab = 0;
-  for (int a = 0; a < 3; ++a)
-    for (int b = a; b < 3; ++b, ++ab) {
-      int ce = 0;
-      for (int c = 0; c < 4; ++c)
-        for (int e = c; e < 4; ++e, ++ce) spec[ab * 10 + ce] = {(uint8_t)Mi[ab], (uint8_t)phi[c], (uint8_t)phi[e]};
-    }
-  for (int a = 0; a < 3; ++a) for (int c = 0; c < 4; ++c) spec[60 + a * 4 + c] = {(uint8_t)(9 + a), (uint8_t)phi[c], 13};
-  spec[72] = {12, 13, 13};
-  spec[73] = {13, 13, 13};
-}
+struct SpecTable {                        // built at compile time: no per-device upload, nothing to race on
+  MomentSpec s[kNumMoments];
+  constexpr SpecTable() : s{} {
+    const int phi[4] = {6, 7, 8, 13};
+    int ab = 0;
+    for (int a = 0; a < 3; ++a)
+      for (int b = a; b < 3; ++b, ++ab) {
+        int ce = 0;
+        for (int c = 0; c < 4; ++c)
+          for (int e = c; e < 4; ++e, ++ce) { s[ab * 10 + ce].a = (uint8_t)ab; s[ab * 10 + ce].b = (uint8_t)phi[c]; s[ab * 10 + ce].c = (uint8_t)phi[e]; }
+      }
+    for (int a = 0; a < 3; ++a) for (int c = 0; c < 4; ++c) { s[60 + a * 4 + c].a = (uint8_t)(9 + a); s[60 + a * 4 + c].b = (uint8_t)phi[c]; s[60 + a * 4 + c].c = 13; }
+    s[72].a = 12; s[72].b = 13; s[72].c = 13;
+    s[73].a = 13; s[73].b = 13; s[73].c = 13;
+  }
+};
+__constant__ SpecTable c_spec = SpecTable();
 
 // R = top-left 3x3 of double(T) * double(guess);  RRt = R R^T      (SURVEY A.4 "R <- ...")
 __device__ void update_rotation(PairState& ps) {
@@ -93,7 +100,7 @@ __device__ void begin_outer(PairState& ps) {
 // Registration::align set-up: gates of align() :134-135, output = guess * input (transformPointCloud), state reset.
 __global__ void __launch_bounds__(256) gicp_prepare_kernel(const SlotInfo* __restrict__ slots, PairState* __restrict__ pairs,
                                                            float4* __restrict__ moved, uint32_t* __restrict__ prev_nn, float* __restrict__ sec_lb,
-                                                           int32_t* __restrict__ flags) {
+                                                           PairSched* __restrict__ psched, int32_t* __restrict__ flags) {
   const uint32_t p = blockIdx.y;
   PairState& ps = pairs[p];
   const SlotInfo& sb = slots[2 * p];      // fixed cloud B  (slam3d source = PCL target)
@@ -102,7 +109,11 @@ __global__ void __launch_bounds__(256) gicp_prepare_kernel(const SlotInfo* __res
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ps.active = enough ? 1 : 0;
     ps.phase = kPhaseFinished;
+    ps.ticket = 0;
     if (enough) { begin_outer(ps); atomicAdd(&flags[1], 1); }
+    // first pass (epoch 1): the search pass of outer iteration 1, or nothing for a pair that fails the <100-point gate
+    psched[p].desc = (1ull << 32) | (enough ? (sa.n_pts + kIterTile - 1) / kIterTile : 0u);
+    psched[p].claim = 1ull << 32;
   }
   if (!enough) return;
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,64 +143,68 @@ __device__ __forceinline__ bool certified_same_nn(const GridView& g, float3 q, f
   return true;
 }
 
-// (register allocation: the compiler's own choice — 64 registers, 4 CTAs/SM — beat forced 5/6/7 CTAs/SM on B200)
-#ifndef S3D_NN_GATHER
-#define S3D_NN_GATHER 1
-#endif
-#if S3D_NN_GATHER
-#define S3D_ITER_BOUNDS __launch_bounds__(kIterTile, 4)  // 64 registers: 4 CTAs per SM as before (the compiler's own choice would be 78)
-#else
-#define S3D_ITER_BOUNDS __launch_bounds__(kIterTile)
-#endif
-__global__ void S3D_ITER_BOUNDS gicp_iter_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
-                                                              const float4* __restrict__ moved,
-                                                              uint32_t* __restrict__ prev_nn, float* __restrict__ sec_lb, uint32_t* __restrict__ corr,
-                                                              double* __restrict__ mahal, double* __restrict__ moments) {
-  __shared__ double feat[kIterTile][kFeat];
-  __shared__ double part[3][kNumMoments];
-#if S3D_NN_GATHER
-  __shared__ uint2 s_cells[kNNGatherCap * kIterTile];  // cell ranges noted by the gathering search (nn_search.cuh)
-#endif
-  const uint32_t p = blockIdx.y;
-  const PairState& ps = pairs[p];
-  if (ps.phase != kPhaseNeedNN) return;
-  const SlotInfo& sb = slots[2 * p];
-  const SlotInfo& sa = slots[2 * p + 1];
-  const uint32_t first = blockIdx.x * kIterTile;
-  if (first >= sa.n_pts) return;
-  const uint32_t r = first + threadIdx.x;
+// ---- shared-memory plan of gicp_loop_kernel ---------------------------------------------------------------------------------
+// [0, kSmTile)            tile scratch: search pass = feat[256][14] | part[3][74] | noted cells; the other passes and the control
+//                         step (CtrlShared) reuse the front of it
+// [kSmTile, kSmLoop)      read-only copy of the pair state of the tile being processed (fetched from L2)
+constexpr size_t kSmPart = size_t(kIterTile) * kFeat * 8;                  // after feat[256][14]
+constexpr size_t kSmCells = kSmPart + 3 * kNumMoments * 8;                  // after part[3][74]
+constexpr size_t kSmTile = kSmCells + size_t(kNNGatherCap) * kIterTile * 8; // 46 832 B
+constexpr size_t kSmLoop = kSmTile + ((sizeof(PairState) + 15) & ~size_t(15));
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+__device__ __forceinline__ int32_t ld_volatile_i32(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
+__device__ __forceinline__ uint32_t sm_id() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+// Release-only operations (MEMBAR.ALL.GPU + the atomic).  __threadfence() and every acquire form additionally emit CCTL.IVALL,
+// which drops the SM's whole L1 — the cache the searches of all resident CTAs live on — so the consumer side of every hand-over
+// in this kernel is a relaxed atomic followed by L2 loads (ld.global.cg / volatile) whose addresses depend on its result.
+__device__ __forceinline__ uint32_t atom_add_release(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void exch_release(unsigned long long* p, unsigned long long v) {
+  unsigned long long old;
+  asm volatile("atom.exch.release.gpu.global.b64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+  (void)old;
+}
+__device__ __forceinline__ void red_add_release(int32_t* p, int32_t v) { asm volatile("red.add.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// search pass of one tile; ps = shared-memory copy of the pair state
+__device__ __forceinline__ void iter_tile(const GicpArgs& a, const PairState& ps, const SlotInfo& sb, const SlotInfo& sa, uint32_t p, uint32_t tile,
+                                          unsigned char* smem) {
+  double (*feat)[kFeat] = reinterpret_cast<double (*)[kFeat]>(smem);
+  double (*part)[kNumMoments] = reinterpret_cast<double (*)[kNumMoments]>(smem + kSmPart);
+  uint2* s_cells = reinterpret_cast<uint2*>(smem + kSmCells);  // cell ranges noted by the gathering search (nn_search.cuh)
+  const uint32_t r = tile * kIterTile + threadIdx.x;
   double f[kFeat];
 #pragma unroll
   for (int i = 0; i < kFeat; ++i) f[i] = 0.0;
   if (r < sa.n_pts) {
     const GridView g = make_grid_view(sb);
-    const float4 mv = moved[ps.pt_off + r];
+    const float4 mv = a.moved[ps.pt_off + r];
     const float3 q = transform_mv(ps.T, mv.x, mv.y, mv.z);
     const double thr = ps.max_corr2;
     const float cutoff = __double2float_ru(thr);
-    const uint32_t hint = prev_nn[ps.pt_off + r];
+    const uint32_t hint = __ldcg(a.prev_nn + ps.pt_off + r);  // written by the previous search pass, possibly on another SM
     NNResult nn;
     float lb_new;
-    if (!certified_same_nn(g, q, transform_mv(ps.T_search, mv.x, mv.y, mv.z), hint, sec_lb[ps.pt_off + r], nn, lb_new)) {
-#if S3D_NN_GATHER
+    if (!certified_same_nn(g, q, transform_mv(ps.T_search, mv.x, mv.y, mv.z), hint, __ldcg(a.sec_lb + ps.pt_off + r), nn, lb_new)) {
       nn = nn_search<true>(g, q.x, q.y, q.z, cutoff, hint, kNoIndex, s_cells + threadIdx.x);
-#else
-      nn = nn_search(g, q.x, q.y, q.z, cutoff, hint);
-#endif
-      prev_nn[ps.pt_off + r] = nn.pos;
+      a.prev_nn[ps.pt_off + r] = nn.pos;
       lb_new = sqrtf(nn.lb2) * 0.99999f;
     }
-    sec_lb[ps.pt_off + r] = lb_new;
+    a.sec_lb[ps.pt_off + r] = lb_new;
     uint32_t c = kNoIndex;
     if (nn.pos != kNoIndex && (double)nn.d2 < thr) {
       c = nn.pos;
       const double4 n1 = sa.normals[r];
       const double4 n2 = sb.normals[nn.pos];
-      double a[3], b[3] = {n2.x, n2.y, n2.z};
-      for (int i = 0; i < 3; ++i) a[i] = ps.R[i][0] * n1.x + ps.R[i][1] * n1.y + ps.R[i][2] * n1.z;
+      double av[3], bv[3] = {n2.x, n2.y, n2.z};
+      for (int i = 0; i < 3; ++i) av[i] = ps.R[i][0] * n1.x + ps.R[i][1] * n1.y + ps.R[i][2] * n1.z;
       double M[6];
-      mahalanobis6(ps.RRt, a, b, M);
-      double* mo = mahal + 6 * (size_t)(ps.pt_off + r);
+      mahalanobis6(ps.RRt, av, bv, M);
+      double* mo = a.mahal + 6 * (size_t)(ps.pt_off + r);
 #pragma unroll
       for (int i = 0; i < 6; ++i) mo[i] = M[i];
       // PCL's first objective evaluation of this outer iteration: d = float(T(x0) * p) - q, float subtraction, then double
@@ -206,7 +221,7 @@ __global__ void S3D_ITER_BOUNDS gicp_iter_kernel(const SlotInfo* __restrict__ sl
       f[12] = d0 * Md0 + d1 * Md1 + d2 * Md2;
       f[13] = 1.0;
     }
-    corr[ps.pt_off + r] = c;
+    a.corr[ps.pt_off + r] = c;
   }
 #pragma unroll
   for (int i = 0; i < kFeat; ++i) feat[threadIdx.x][i] = f[i];
@@ -214,7 +229,7 @@ __global__ void S3D_ITER_BOUNDS gicp_iter_kernel(const SlotInfo* __restrict__ sl
   // 74 sums x 3 sub-ranges of the tile, each summed in ascending point order
   if (threadIdx.x < 3 * kNumMoments) {
     const int m = threadIdx.x % kNumMoments, sub = threadIdx.x / kNumMoments;
-    const MomentSpec sp = c_spec[m];
+    const MomentSpec sp = c_spec.s[m];
     const int lo = sub * 86, hi = min(kIterTile, lo + 86);
     double s = 0.0;
     for (int i = lo; i < hi; ++i) s += feat[i][sp.a] * feat[i][sp.b] * feat[i][sp.c];
@@ -222,43 +237,34 @@ __global__ void S3D_ITER_BOUNDS gicp_iter_kernel(const SlotInfo* __restrict__ sl
   }
   __syncthreads();
   if (threadIdx.x < kNumMoments) {
-    const size_t tile = (size_t)p * gridDim.x + blockIdx.x;
-    moments[tile * kNumMoments + threadIdx.x] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x];
+    const size_t t = (size_t)p * a.tiles_per_pair + tile;
+    a.moments[t * kNumMoments + threadIdx.x] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x];
   }
 }
 
-// Objective evaluations at the pending back-tracking trials of every pair in kPhaseEval: 13 residual sums per trial and
-// 256-point tile, residual formed exactly as PCL forms it.
-__global__ void __launch_bounds__(kIterTile) gicp_eval_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
-                                                              const float4* __restrict__ moved,
-                                                              const uint32_t* __restrict__ corr, const double* __restrict__ mahal,
-                                                              double* __restrict__ eval_part) {
-  __shared__ double feat[kIterTile][8];  // px py pz | (Md)0..2 | d^T M d | 1
-  __shared__ double part[16][kEvalSums];
-  const uint32_t p = blockIdx.y;
-  const PairState& ps = pairs[p];
-  if (ps.phase != kPhaseEval) return;
-  const SlotInfo& sb = slots[2 * p];
-  const SlotInfo& sa = slots[2 * p + 1];
-  const uint32_t first = blockIdx.x * kIterTile;
-  if (first >= sa.n_pts) return;
-  const uint32_t r = first + threadIdx.x;
+// trial pass of one tile: 13 residual sums per pending back-tracking trial, residual formed exactly as PCL forms it
+__device__ __forceinline__ void eval_tile(const GicpArgs& a, const PairState& ps, const SlotInfo& sb, const SlotInfo& sa, uint32_t p, uint32_t tile,
+                                          unsigned char* smem) {
+  double (*feat)[8] = reinterpret_cast<double (*)[8]>(smem);                                   // px py pz | (Md)0..2 | d^T M d | 1
+  double (*part)[kEvalSums] = reinterpret_cast<double (*)[kEvalSums]>(smem + size_t(kIterTile) * 8 * 8);
+  const uint32_t r = tile * kIterTile + threadIdx.x;
   bool valid = false;
   float4 mv = make_float4(0.f, 0.f, 0.f, 0.f), qb = mv;
   double M[6] = {0, 0, 0, 0, 0, 0};
   if (r < sa.n_pts) {
-    const uint32_t c = corr[ps.pt_off + r];
+    const uint32_t c = __ldcg(a.corr + ps.pt_off + r);  // written by the search pass, possibly on another SM
     if (c != kNoIndex) {
       valid = true;
-      mv = moved[ps.pt_off + r];
+      mv = a.moved[ps.pt_off + r];
       qb = sb.gpts[c];
-      const double* Mp = mahal + 6 * (size_t)(ps.pt_off + r);
+      const double* Mp = a.mahal + 6 * (size_t)(ps.pt_off + r);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) M[i] = Mp[i];
+      for (int i = 0; i < 6; ++i) M[i] = __ldcg(Mp + i);
     }
   }
-  const size_t tile = (size_t)p * gridDim.x + blockIdx.x;
-  for (int j = ps.trial_first; j < ps.trial_first + ps.trial_count; ++j) {
+  const size_t t = (size_t)p * a.tiles_per_pair + tile;
+  const int j0 = ps.trial_first, j1 = ps.trial_first + ps.trial_count;
+  for (int j = j0; j < j1; ++j) {
     double f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (valid) {
       const float3 pp = transform_mv(ps.T_trial[j], mv.x, mv.y, mv.z);
@@ -285,13 +291,46 @@ __global__ void __launch_bounds__(kIterTile) gicp_eval_kernel(const SlotInfo* __
     if (threadIdx.x < kEvalSums) {
       double acc = 0.0;
       for (int sub = 0; sub < 16; ++sub) acc += part[sub][threadIdx.x];
-      eval_part[(tile * kLineSearchTrials + j) * kEvalSums + threadIdx.x] = acc;
+      a.eval_part[(t * kLineSearchTrials + j) * kEvalSums + threadIdx.x] = acc;
     }
   }
 }
 
+// fitness pass of one tile — getFitnessScore(max_range): transformPointCloud(input, final), 1-NN, d2 <= max_range (sic), mean of d2 (A.6)
+__device__ __forceinline__ void fitness_tile(const GicpArgs& a, const PairState& ps, const SlotInfo& sb, const SlotInfo& sa, uint32_t p, uint32_t tile,
+                                             unsigned char* smem) {
+  double* ssum = reinterpret_cast<double*>(smem);
+  uint32_t* scnt = reinterpret_cast<uint32_t*>(smem + size_t(kIterTile) * 8);
+  uint2* s_cells = reinterpret_cast<uint2*>(smem + kSmCells);
+  const uint32_t r = tile * kIterTile + threadIdx.x;
+  double s = 0.0; uint32_t c = 0;
+  if (r < sa.n_pts) {
+    const GridView g = make_grid_view(sb);
+    const float4 v = sa.gpts[r];
+    const float3 q = transform_se3(ps.final_T, v.x, v.y, v.z);
+    const float4 mv = a.moved[ps.pt_off + r];
+    const uint32_t hint = __ldcg(a.prev_nn + ps.pt_off + r);
+    NNResult nn;
+    float lb_new;
+    if (!certified_same_nn(g, q, transform_mv(ps.T_search, mv.x, mv.y, mv.z), hint, __ldcg(a.sec_lb + ps.pt_off + r), nn, lb_new))
+      nn = nn_search<true>(g, q.x, q.y, q.z, __double2float_ru(ps.fit_range), hint, kNoIndex, s_cells + threadIdx.x);
+    if (nn.pos != kNoIndex && (double)nn.d2 <= ps.fit_range) { s = (double)nn.d2; c = 1; }
+  }
+  ssum[threadIdx.x] = s; scnt[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = kIterTile / 2; o > 0; o >>= 1) {  // fixed tree
+    if (threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; scnt[threadIdx.x] += scnt[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const size_t t = (size_t)p * a.tiles_per_pair + tile;
+    a.fit_partial[2 * t] = ssum[0];
+    a.fit_partial[2 * t + 1] = (double)scnt[0];
+  }
+}
+
 // End of an outer iteration (computeTransformation): convergence test, counters, next iteration or final transform.
-__device__ void finish_outer(PairState& ps, bool optimiser_failed, int32_t* flags) {
+__device__ void finish_outer(PairState& ps, bool optimiser_failed) {
   bool stop = false;
   if (optimiser_failed) {
     ps.failed = 1; ps.converged = 0; stop = true;  // optimiser exception: loop breaks, converged_ stays false, final = previous * guess
@@ -315,9 +354,7 @@ __device__ void finish_outer(PairState& ps, bool optimiser_failed, int32_t* flag
   }
   if (stop) {
     mat4f_mul(ps.prev, ps.guess, ps.final_T);  // final_transformation_ = previous_transformation_ * guess
-    ps.active = 0;
-    ps.phase = kPhaseFinished;
-    atomicSub(&flags[1], 1);
+    ps.phase = kPhaseFitness;                  // the pair stays active until its fitness pass has been summed
   } else {
     begin_outer(ps);
   }
@@ -348,26 +385,36 @@ __device__ void euler_derivs_cta(const double* x, Euler& E, double (*fac)[3][3][
   __syncthreads();
 }
 
-// one CTA per pair: ordered reduction of the tile partials of the pass that just ran, then the optimiser advances
-__global__ void __launch_bounds__(256) gicp_ctrl_kernel(const SlotInfo* __restrict__ slots, PairState* __restrict__ pairs,
-                                                        const double* __restrict__ moments, const double* __restrict__ eval_part,
-                                                        uint32_t tiles_per_pair, int after_eval, int32_t* __restrict__ flags) {
-  __shared__ double part[3][kLineSearchTrials * kEvalSums];
-  __shared__ double red[kLineSearchTrials * kEvalSums];
-  __shared__ Euler E;
-  __shared__ double fac[3][3][3][3];
-  __shared__ double gH[42];
-  __shared__ int mode;      // 0: nothing to assemble, 1: assemble the objective at ps.nst.xc from ps.sums
-  __shared__ int newstep;   // a new Newton step started: its trial matrices are needed
-  const uint32_t p = blockIdx.x;
-  PairState& ps = pairs[p];
-  // the first ctrl launch of a round serves pairs that just searched, the later ones pairs that were just evaluated
-  if (ps.phase != (after_eval ? kPhaseEval : kPhaseNeedNN)) return;
-  const uint32_t n_tiles = (slots[2 * p + 1].n_pts + kIterTile - 1) / kIterTile;
+// Control step of pair p, run by the CTA that delivered the last tile of a search or trial pass: ordered reduction of the tile
+// partials, then the optimiser advances.  The pair state is staged in shared memory (the serial part is one thread's dependent
+// chain; on global memory every step of it was an L2 round trip: 29 us per control launch in round 1).
+struct CtrlShared {
+  PairState ps;
+  double part[3][kLineSearchTrials * kEvalSums];
+  double red[kLineSearchTrials * kEvalSums];
+  Euler E;
+  double fac[3][3][3][3];
+  double gH[42];
+  int mode;      // 0: nothing to assemble, 1: assemble the objective at ps.nst.xc from ps.sums
+  int newstep;   // a new Newton step started: its trial matrices are needed
+};
+static_assert(sizeof(CtrlShared) <= kSmTile, "control step must fit into the tile scratch");
+
+__device__ __noinline__ void ctrl_step(const GicpArgs& a, uint32_t p, int after_eval, unsigned char* smem) {
+  CtrlShared& sh = *reinterpret_cast<CtrlShared*>(smem);
+  PairState& ps = sh.ps;
+  PairState* psg = a.pairs + p;
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(psg);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sh.ps);
+    for (uint32_t i = threadIdx.x; i < sizeof(PairState) / 8; i += blockDim.x) dst[i] = __ldcg(src + i);
+  }
+  __syncthreads();
+  const uint32_t n_tiles = (a.slots[2 * p + 1].n_pts + kIterTile - 1) / kIterTile;
   const int n_sums = after_eval ? ps.trial_count * kEvalSums : kNumMoments;
   const int stride = after_eval ? kLineSearchTrials * kEvalSums : kNumMoments;
-  const double* src0 = after_eval ? eval_part + (size_t)p * tiles_per_pair * stride + ps.trial_first * kEvalSums
-                                  : moments + (size_t)p * tiles_per_pair * stride;
+  const double* src0 = after_eval ? a.eval_part + (size_t)p * a.tiles_per_pair * stride + ps.trial_first * kEvalSums
+                                  : a.moments + (size_t)p * a.tiles_per_pair * stride;
   const int subs = n_sums * 3 <= 256 ? 3 : (n_sums * 2 <= 256 ? 2 : 1);
   if ((int)threadIdx.x < subs * n_sums) {
     const int m = threadIdx.x % n_sums, sub = threadIdx.x / n_sums;
@@ -375,119 +422,202 @@ __global__ void __launch_bounds__(256) gicp_ctrl_kernel(const SlotInfo* __restri
     const uint32_t lo = sub * per, hi = min(n_tiles, lo + per);
     const double* src = src0 + m;
     double s = 0.0;
-#pragma unroll 4
-    for (uint32_t t = lo; t < hi; ++t) s += src[(size_t)t * stride];
-    part[sub][m] = s;
+#pragma unroll 8
+    for (uint32_t t = lo; t < hi; ++t) s += __ldcg(src + (size_t)t * stride);  // written by other CTAs: read from L2
+    sh.part[sub][m] = s;
   }
   __syncthreads();
   if ((int)threadIdx.x < n_sums) {
-    double s = part[0][threadIdx.x];
-    for (int sub = 1; sub < subs; ++sub) s += part[sub][threadIdx.x];
-    red[threadIdx.x] = s;
+    double s = sh.part[0][threadIdx.x];
+    for (int sub = 1; sub < subs; ++sub) s += sh.part[sub][threadIdx.x];
+    sh.red[threadIdx.x] = s;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    mode = 1; newstep = 0;
+    sh.mode = 1; sh.newstep = 0;
+    ps.ticket = 0;
     if (!after_eval) {
-      for (int i = 0; i < kNumMoments; ++i) ps.sums[i] = red[i];
+      for (int i = 0; i < kNumMoments; ++i) ps.sums[i] = sh.red[i];
       ps.n_corr = (uint32_t)ps.sums[73];
       for (int i = 0; i < 16; ++i) { ps.prev[i] = ps.T[i]; ps.T_search[i] = ps.T[i]; }  // previous_transformation_ = transformation_
-      if (ps.sums[73] < 4.0) { finish_outer(ps, true, flags); mode = 0; }  // min_number_correspondences_: PCL throws
+      if (ps.sums[73] < 4.0) { finish_outer(ps, true); sh.mode = 0; }  // min_number_correspondences_: PCL throws
     } else {
       double f_trial[kLineSearchTrials];
-      for (int j = 0; j < ps.trial_count; ++j) f_trial[ps.trial_first + j] = red[j * kEvalSums + 12] / ps.sums[73];
+      for (int j = 0; j < ps.trial_count; ++j) f_trial[ps.trial_first + j] = sh.red[j * kEvalSums + 12] / ps.sums[73];
       const int j = newton_pick_trial(ps.nst, f_trial, ps.trial_first, ps.trial_count);
       if (j >= 0) {
         newton_select_trial(ps.nst, j);
-        for (int i = 0; i < kEvalSums; ++i) ps.sums[60 + i] = red[(j - ps.trial_first) * kEvalSums + i];
+        for (int i = 0; i < kEvalSums; ++i) ps.sums[60 + i] = sh.red[(j - ps.trial_first) * kEvalSums + i];
       } else if (ps.trial_first == 0 && kLineSearchTrials > 1) {
         ps.trial_first = 1; ps.trial_count = kLineSearchTrials - 1;  // trial 0 did not improve: evaluate all remaining trials in one pass
-        mode = 0;
+        sh.mode = 0;
       } else {
         ps.nst.phase = 2;  // no improvement found
-        finish_outer(ps, false, flags);
-        mode = 0;
+        finish_outer(ps, false);
+        sh.mode = 0;
       }
     }
   }
   __syncthreads();
-  if (!mode) return;
-  euler_derivs_cta(ps.nst.xc, E, fac);
-  // objective at the evaluated state: 42 threads contract one gradient / Hessian entry each
-  if (threadIdx.x < 42) gH[threadIdx.x] = objective_entry(ps.sums, E, threadIdx.x);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double g[6], H[6][6];
-    for (int i = 0; i < 6; ++i) { g[i] = gH[i]; for (int j = 0; j < 6; ++j) H[i][j] = gH[6 + 6 * i + j]; }
-    if (newton_advance_pre(ps.nst, ps.sums[72] / ps.sums[73], g, H, ps.max_inner)) {
-      ps.trial_first = 0; ps.trial_count = 1;
-      ps.phase = kPhaseEval;
-      newstep = 1;
-    } else {
-      finish_outer(ps, false, flags);
+  if (sh.mode) {
+    euler_derivs_cta(ps.nst.xc, sh.E, sh.fac);
+    // objective at the evaluated state: 42 threads contract one gradient / Hessian entry each
+    if (threadIdx.x < 42) sh.gH[threadIdx.x] = objective_entry(ps.sums, sh.E, threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double g[6], H[6][6];
+      for (int i = 0; i < 6; ++i) { g[i] = sh.gH[i]; for (int j = 0; j < 6; ++j) H[i][j] = sh.gH[6 + 6 * i + j]; }
+      if (newton_advance_pre(ps.nst, ps.sums[72] / ps.sums[73], g, H, ps.max_inner)) {
+        ps.trial_first = 0; ps.trial_count = 1;
+        ps.phase = kPhaseEval;
+        sh.newstep = 1;
+      } else {
+        finish_outer(ps, false);
+      }
+    }
+    __syncthreads();
+    if (sh.newstep && threadIdx.x < kLineSearchTrials) {  // float matrices of all back-tracking trials of the new step
+      double xc[6];
+      newton_trial_state(ps.nst, threadIdx.x, xc);
+      matrix_from_state(xc, ps.T_trial[threadIdx.x]);
     }
   }
   __syncthreads();
-  if (newstep && threadIdx.x < kLineSearchTrials) {  // float matrices of all back-tracking trials of the new step
-    double xc[6];
-    newton_trial_state(ps.nst, threadIdx.x, xc);
-    matrix_from_state(xc, ps.T_trial[threadIdx.x]);
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&sh.ps);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(psg);
+    for (uint32_t i = threadIdx.x; i < sizeof(PairState) / 8; i += blockDim.x) dst[i] = src[i];
   }
 }
 
-// getFitnessScore(max_range): transformPointCloud(input, final), 1-NN, d2 <= max_range (sic), mean of d2   (A.6)
-__global__ void __launch_bounds__(kIterTile) gicp_fitness_kernel(const SlotInfo* __restrict__ slots, const PairState* __restrict__ pairs,
-                                                                 const float4* __restrict__ moved, const uint32_t* __restrict__ prev_nn,
-                                                                 const float* __restrict__ sec_lb, double* __restrict__ fit_partial) {
-  __shared__ double ssum[kIterTile];
-  __shared__ uint32_t scnt[kIterTile];
-  const uint32_t p = blockIdx.y;
-  const PairState& ps = pairs[p];
-  const SlotInfo& sb = slots[2 * p];
-  const SlotInfo& sa = slots[2 * p + 1];
-  if (sa.n_pts < 100 || sb.n_pts < 100) return;
-  const uint32_t first = blockIdx.x * kIterTile;
-  if (first >= sa.n_pts) return;
-  const uint32_t r = first + threadIdx.x;
-  double s = 0.0; uint32_t c = 0;
-  if (r < sa.n_pts) {
-    const GridView g = make_grid_view(sb);
-    const float4 v = sa.gpts[r];
-    const float3 q = transform_se3(ps.final_T, v.x, v.y, v.z);
-    const float4 mv = moved[ps.pt_off + r];
-    const uint32_t hint = prev_nn[ps.pt_off + r];
-    NNResult nn;
-    float lb_new;
-    if (!certified_same_nn(g, q, transform_mv(ps.T_search, mv.x, mv.y, mv.z), hint, sec_lb[ps.pt_off + r], nn, lb_new))
-      nn = nn_search(g, q.x, q.y, q.z, __double2float_ru(ps.fit_range), hint);
-    if (nn.pos != kNoIndex && (double)nn.d2 <= ps.fit_range) { s = (double)nn.d2; c = 1; }
-  }
-  ssum[threadIdx.x] = s; scnt[threadIdx.x] = c;
-  __syncthreads();
-  for (int o = kIterTile / 2; o > 0; o >>= 1) {  // fixed tree
-    if (threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; scnt[threadIdx.x] += scnt[threadIdx.x + o]; }
+// last tile of the fitness pass: ordered sum of the tile partials (same order as a sequential loop over the tiles); closes the pair
+__device__ void fitness_finish(const GicpArgs& a, uint32_t p, unsigned char* smem) {
+  double* part = reinterpret_cast<double*>(smem);
+  const uint32_t n_tiles = (a.slots[2 * p + 1].n_pts + kIterTile - 1) / kIterTile;
+  const double* src = a.fit_partial + 2 * (size_t)p * a.tiles_per_pair;
+  double s = 0.0, c = 0.0;
+  for (uint32_t base = 0; base < n_tiles; base += kIterTile) {  // 256 tiles at a time through shared memory
+    const uint32_t t = base + threadIdx.x;
+    if (t < n_tiles) { part[2 * threadIdx.x] = __ldcg(src + 2 * t); part[2 * threadIdx.x + 1] = __ldcg(src + 2 * t + 1); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t m = min((uint32_t)kIterTile, n_tiles - base);
+      for (uint32_t i = 0; i < m; ++i) { s += part[2 * i]; c += part[2 * i + 1]; }
+    }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const size_t tile = (size_t)p * gridDim.x + blockIdx.x;
-    fit_partial[2 * tile] = ssum[0];
-    fit_partial[2 * tile + 1] = (double)scnt[0];
+    PairState* psg = a.pairs + p;
+    psg->fit_sum = s; psg->fit_n = (uint32_t)c;
+    psg->ticket = 0;
+    psg->phase = kPhaseFinished;
+    psg->active = 0;
   }
 }
 
-__global__ void gicp_fitness_reduce_kernel(const SlotInfo* __restrict__ slots, PairState* __restrict__ pairs, const double* __restrict__ fit_partial,
-                                           uint32_t tiles_per_pair, uint32_t n_pairs) {
-  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pairs) return;
-  PairState& ps = pairs[p];
-  const SlotInfo& sb = slots[2 * p];
-  const SlotInfo& sa = slots[2 * p + 1];
-  ps.fit_sum = 0.0; ps.fit_n = 0;
-  if (sa.n_pts < 100 || sb.n_pts < 100) return;
-  const uint32_t n_tiles = (sa.n_pts + kIterTile - 1) / kIterTile;
-  double s = 0.0, c = 0.0;
-  for (uint32_t t = 0; t < n_tiles; ++t) { s += fit_partial[2 * ((size_t)p * tiles_per_pair + t)]; c += fit_partial[2 * ((size_t)p * tiles_per_pair + t) + 1]; }
-  ps.fit_sum = s; ps.fit_n = (uint32_t)c;
+// ---- scheduler ------------------------------------------------------------------------------------------------------------------
+// PairSched.desc  = epoch << 32 | tiles of the pass that is open for claims (0: nothing to claim — control step running, or closed)
+// PairSched.claim = epoch << 32 | next unclaimed tile.  A pass is published by writing desc first and claim second, so whoever
+// draws (epoch, t) from `claim` finds the descriptor of that epoch; claims past the end of a pass are harmless.
+__device__ __forceinline__ bool claim_tile(const GicpArgs& a, uint32_t& rot, uint32_t& p_out, uint32_t& t_out) {
+  for (uint32_t i = 0; i < a.n_pairs; ++i) {
+    uint32_t p = rot + i;
+    if (p >= a.n_pairs) p -= a.n_pairs;
+    PairSched* s = a.psched + p;
+    unsigned long long d = ld_volatile_u64(&s->desc);
+    if ((uint32_t)d == 0u) continue;
+    unsigned long long c = ld_volatile_u64(&s->claim);
+    if ((c >> 32) != (d >> 32) || (uint32_t)c >= (uint32_t)d) continue;  // fully claimed, or between two passes
+    c = atomicAdd(&s->claim, 1ull);
+    d = ld_volatile_u64(&s->desc);
+    if ((c >> 32) == (d >> 32) && (uint32_t)c < (uint32_t)d) { rot = p; p_out = p; t_out = (uint32_t)c; return true; }
+  }
+  return false;
+}
+
+__device__ __forceinline__ void publish_pass(const GicpArgs& a, uint32_t p, uint32_t n_tiles) {
+  PairSched* s = a.psched + p;
+  const unsigned long long epoch = (ld_volatile_u64(&s->desc) >> 32) + 1ull;
+  exch_release(&s->desc, (epoch << 32) | n_tiles);   // release: the pair state written by this CTA (ordered by the barrier before) comes first
+  if (n_tiles) exch_release(&s->claim, epoch << 32);  // release: the descriptor comes before the claims it validates
+}
+
+// mode 0 (latency, one launch): a CTA that finds nothing to claim waits for the next pass to be published.
+// mode 1 (throughput, inside the WHILE node of a CUDA graph): a CTA that finds nothing to claim leaves, and so does every CTA once
+//   half of the grid has left, so that the SM resources go to the kernels of the other chunks of the batch (other streams) instead
+//   of to waiting CTAs; the last CTA to leave keeps the graph's loop going while a pair is active.  Passes that are published
+//   while enough CTAs are still around are picked up by the same launch.
+__global__ void __launch_bounds__(kIterTile, 4) gicp_loop_kernel(const GicpArgs* __restrict__ ap, cudaGraphConditionalHandle cond, int mode) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ uint32_t s_p, s_tile;
+  __shared__ int s_found, s_last;
+  PairState& tps = *reinterpret_cast<PairState*>(smem + kSmTile);
+  const GicpArgs a = *ap;
+  uint32_t rot = sm_id() % a.n_pairs;  // the CTAs of one SM start on the same pair: its grid and points share that SM's L1
+  const long long t_start = clock64();
+  for (;;) {
+    if (threadIdx.x == 0) {
+      int found = 0;
+      for (uint32_t spin = 0;; ++spin) {
+        if (mode == 1 && *reinterpret_cast<volatile uint32_t*>(&a.ctl[2]) * 2u > gridDim.x) break;  // the launch is draining
+        if (claim_tile(a, rot, s_p, s_tile)) { found = 1; break; }
+        if (ld_volatile_i32(&a.flags[1]) <= 0 || (ld_volatile_i32(&a.flags[0]) & kErrWatchdog)) break;  // no pair is active: done
+        if (mode == 1 && spin >= a.linger) break;
+        __nanosleep(spin < 8 ? 100 : 400);
+        if ((spin & 255u) == 255u && clock64() - t_start > (long long)a.watchdog_cycles) { atomicOr(&a.flags[0], kErrWatchdog); break; }
+      }
+      s_found = found;
+    }
+    __syncthreads();
+    if (!s_found) break;
+    const uint32_t p = s_p, tile = s_tile;
+    {  // the pair state and pass data were released before this claim became possible; read them from L2
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.pairs + p);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&tps);
+      for (uint32_t i = threadIdx.x; i < sizeof(PairState) / 8; i += blockDim.x) dst[i] = __ldcg(src + i);
+    }
+    __syncthreads();
+    const int phase = tps.phase;
+    const SlotInfo& sb = a.slots[2 * p];
+    const SlotInfo& sa = a.slots[2 * p + 1];
+    if (phase == kPhaseNeedNN) iter_tile(a, tps, sb, sa, p, tile, smem);
+    else if (phase == kPhaseEval) eval_tile(a, tps, sb, sa, p, tile, smem);
+    else fitness_tile(a, tps, sb, sa, p, tile, smem);
+    __syncthreads();
+    if (threadIdx.x == 0) {  // release: this tile's partial sums, correspondences, matrices and hints come before its ticket
+      const uint32_t n_live = (sa.n_pts + kIterTile - 1) / kIterTile;
+      s_last = atom_add_release(&a.pairs[p].ticket, 1u) == n_live - 1;
+      atomicAdd(&a.ctl[0], 1u);
+    }
+    __syncthreads();
+    if (s_last) {  // this CTA delivered the last tile of the pass: control step, then publish what comes next
+      uint32_t next_tiles = 0;
+      if (phase == kPhaseFitness) {
+        fitness_finish(a, p, smem);
+      } else {
+        ctrl_step(a, p, phase == kPhaseEval, smem);
+        next_tiles = (sa.n_pts + kIterTile - 1) / kIterTile;  // search, trial and fitness passes all cover the moving cloud
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        atomicAdd(&a.ctl[1], 1u);
+        publish_pass(a, p, next_tiles);
+        if (next_tiles == 0) red_add_release(&a.flags[1], -1);  // the pair is closed: its results come before the count
+      }
+    }
+    __syncthreads();
+  }
+  if (mode == 1 && threadIdx.x == 0) {
+    // the last CTA to leave re-arms the counters and decides whether the graph's WHILE loop runs the kernel again
+    if (atomicAdd(&a.ctl[2], 1u) == gridDim.x - 1) {
+      a.ctl[2] = 0;
+      const uint32_t launches = ++a.ctl[3];
+      const bool stuck = launches >= a.max_launches;
+      if (stuck) atomicOr(&a.flags[0], kErrWatchdog);
+      const bool again = ld_volatile_i32(&a.flags[1]) > 0 && !(ld_volatile_i32(&a.flags[0]) & kErrWatchdog) && !stuck;
+      cudaGraphSetConditional(cond, again ? 1u : 0u);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -528,17 +658,48 @@ void check_arena(Workspace& ws, const int32_t* h_flags) {
   if (h_flags[0] & kErrHashArena) throw ArenaOverflow{(size_t)h_flags[3] + (size_t)h_flags[3] / 8 + 64};
 }
 
+static int loop_grid(int device) {
+  int sms = 0;
+  S3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  static const int per_sm = [] { const char* e = getenv("S3D_LOOP_CTAS_PER_SM"); return e ? std::max(1, atoi(e)) : 4; }();  // A/B measurements
+  return std::max(1, sms) * per_sm;  // 4 resident CTAs per SM (64 registers, 49 KB shared memory)
+}
+
+// Throughput mode: WHILE (a pair is active) { gicp_loop_kernel(mode 1) } as a CUDA graph with a conditional node, built once per
+// workspace — the kernel reads everything from the GicpArgs block at a fixed device address — and replayed for every batch.
+static void build_loop_graph(Workspace& ws) {
+  S3D_CUDA(cudaGraphCreate(&ws.loop_graph, 0));
+  cudaGraphConditionalHandle handle;
+  S3D_CUDA(cudaGraphConditionalHandleCreate(&handle, ws.loop_graph, 1, cudaGraphCondAssignDefault));  // every replay starts with "true"
+  cudaGraphNodeParams cp = {};
+  cp.type = cudaGraphNodeTypeConditional;
+  cp.conditional.handle = handle;
+  cp.conditional.type = cudaGraphCondTypeWhile;
+  cp.conditional.size = 1;
+  cudaGraphNode_t cond_node;
+  S3D_CUDA(cudaGraphAddNode(&cond_node, ws.loop_graph, nullptr, 0, &cp));
+  cudaGraph_t body = cp.conditional.phGraph_out[0];
+  const GicpArgs* ap = ws.gicp_args.as<GicpArgs>();
+  int mode = 1;
+  void* kargs[] = {&ap, &handle, &mode};
+  cudaKernelNodeParams kp = {};
+  kp.func = reinterpret_cast<void*>(gicp_loop_kernel);
+  kp.gridDim = dim3(loop_grid(ws.device));
+  kp.blockDim = dim3(kIterTile);
+  kp.sharedMemBytes = (unsigned)kSmLoop;
+  kp.kernelParams = kargs;
+  cudaGraphNode_t kernel_node;
+  S3D_CUDA(cudaGraphAddKernelNode(&kernel_node, body, nullptr, 0, &kp));
+  S3D_CUDA(cudaGraphInstantiate(&ws.loop_exec, ws.loop_graph, 0));
+}
+
 // Runs the GICP loop + fitness for every pair of the batch (grids and covariances must be ready) and fills `out`
-// with the decisions of doICP (:74-77) and align() (:134-135, :167-172).
+// with the decisions of doICP (:74-77) and align() (:134-135, :167-172).  Latency mode (single calls): set-up kernel + ONE
+// persistent loop kernel.  Throughput mode (the chunks of a batch call, several streams per device): set-up kernel + a graph
+// replay whose WHILE node relaunches the loop kernel until no pair is active.
 void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& params, const double* guesses, s3d_result* out) {
-  static bool spec_ready[64] = {false};
-  if (!spec_ready[ws.device]) {
-    MomentSpec spec[kNumMoments];
-    build_moment_spec(spec);
-    S3D_CUDA(cudaMemcpyToSymbol(c_spec, spec, sizeof spec));
-    spec_ready[ws.device] = true;
-  }
   const uint32_t np = ws.n_pairs;
+  if (np == 0) return;
   cudaStream_t st = ws.stream;
   const uint32_t max_na = ws.max_na;
   const uint32_t tiles_per_pair = std::max<uint32_t>(1, (max_na + kIterTile - 1) / kIterTile);
@@ -552,8 +713,9 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   ws.corr.reserve(4 * std::max<size_t>(ws.total, 4));
   ws.mahal.reserve(48 * std::max<size_t>(ws.total, 4));
   ws.fit_partial.reserve(sizeof(double) * 2 * size_t(tiles_per_pair) * np);
+  if (!ws.gicp_args.p) ws.gicp_args.reserve(sizeof(GicpArgs));  // allocated once: the loop graph holds this address
+  ws.gicp_sched.reserve(sizeof(PairSched) * np + 64);
   PairState* hp = ws.h_pairs.as<PairState>();
-  int max_iter = 0;
   for (uint32_t p = 0; p < np; ++p) {
     const s3d_registration_parameters& cfg = params[p];
     PairState& ps = hp[p];
@@ -567,73 +729,60 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
     ps.fit_range = cfg.max_correspondence_distance;
     ps.pt_off = ws.pair_off[p];
     ps.max_iter = cfg.maximum_iterations; ps.max_inner = cfg.maximum_optimizer_iterations; ps.k = cfg.correspondence_randomness;
-    max_iter = std::max(max_iter, cfg.maximum_iterations);
   }
   S3D_CUDA(cudaMemcpyAsync(ws.pairs.p, hp, sizeof(PairState) * np, cudaMemcpyHostToDevice, st));
   const SlotInfo* slots = ws.slots.as<SlotInfo>();
   PairState* pairs = ws.pairs.as<PairState>();
   int32_t* flags = ws.flags.as<int32_t>();
   int32_t* h_flags = ws.h_small.as<int32_t>();
+  uint32_t* h_ctl = ws.h_small.as<uint32_t>() + 8;
+  uint32_t* ctl = ws.gicp_sched.as<uint32_t>();                                       // 16 words of counters ...
+  PairSched* psched = reinterpret_cast<PairSched*>(ws.gicp_sched.as<char>() + 64);    // ... then one scheduler entry per pair
+  static const unsigned long long watchdog = [] {  // cycles without finding work after which the loop kernel gives up (~3 s; a loop takes milliseconds)
+    const char* e = getenv("S3D_WATCHDOG_MCYCLES");
+    return (e ? (unsigned long long)atoll(e) : 6000ull) * 1000000ull;
+  }();
+  // S3D_LOOP_MODE: 0 = by call type (default), 1 = always the persistent launch, 2 = always the graph replay;  S3D_LOOP_LINGER: polls
+  static const int loop_mode = [] { const char* e = getenv("S3D_LOOP_MODE"); return e ? atoi(e) : 0; }();
+  static const uint32_t linger = [] { const char* e = getenv("S3D_LOOP_LINGER"); return e ? (uint32_t)atoi(e) : 8u; }();
+  const bool throughput = loop_mode == 2 || (loop_mode == 0 && ws.blocking_sync);
+  GicpArgs* ha = reinterpret_cast<GicpArgs*>(ws.h_small.as<char>() + 256);
+  *ha = GicpArgs{slots, pairs, ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), ws.corr.as<uint32_t>(), ws.mahal.as<double>(),
+                 ws.moments.as<double>(), ws.eval_part.as<double>(), ws.fit_partial.as<double>(), flags, psched, ctl, tiles_per_pair, np,
+                 linger, 1u << 20, watchdog};
+  S3D_CUDA(cudaMemcpyAsync(ws.gicp_args.p, ha, sizeof(GicpArgs), cudaMemcpyHostToDevice, st));
+  S3D_CUDA(cudaMemsetAsync(ctl, 0, 64, st));
   dim3 grid(tiles_per_pair, np);
-  gicp_prepare_kernel<<<grid, 256, 0, st>>>(slots, pairs, ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), flags);
-  ++ws.launches;
-  // Rounds: [search + first evaluation] -> ctrl -> [trial evaluation] -> ctrl.  A pair needs one round per outer iteration
-  // plus one per extra objective evaluation; PCL's loop is a do-while, so maximum_iterations <= 0 still runs one iteration.
-  const bool trace = getenv("S3D_TRACE") != nullptr;
-  const long max_rounds = (long)std::max(max_iter, 1) * 64 + 64;
-  auto t_round = std::chrono::steady_clock::now();
-  for (long round = 0; round < max_rounds; ++round) {
-    {
-      StageTimer timer(ws, kStageIter);
-      gicp_iter_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), ws.corr.as<uint32_t>(),
-                                                   ws.mahal.as<double>(), ws.moments.as<double>());
-      ++ws.launches;
-    }
-    {
-      StageTimer timer(ws, kStageSolve);
-      gicp_ctrl_kernel<<<np, 256, 0, st>>>(slots, pairs, ws.moments.as<double>(), ws.eval_part.as<double>(), tiles_per_pair, 0, flags);
-      ++ws.launches;
-      for (int e = 0; e < 2; ++e) {  // two evaluate/advance passes per round: most outer iterations finish without another host poll
-        gicp_eval_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.moved.as<float4>(), ws.corr.as<uint32_t>(),
-                                                     ws.mahal.as<double>(), ws.eval_part.as<double>());
-        gicp_ctrl_kernel<<<np, 256, 0, st>>>(slots, pairs, ws.moments.as<double>(), ws.eval_part.as<double>(), tiles_per_pair, 1, flags);
-        ws.launches += 2;
-      }
-    }
-    S3D_CUDA(cudaMemcpyAsync(h_flags, flags, 16, cudaMemcpyDeviceToHost, st));
-    S3D_CUDA(cudaStreamSynchronize(st));
-    ws.d2h += 16;
-    if (trace) {
-      S3D_CUDA(cudaMemcpy(hp, pairs, sizeof(PairState) * np, cudaMemcpyDeviceToHost));
-      int n_nn = 0, n_ev = 0, n_fin = 0;
-      for (uint32_t p = 0; p < np; ++p) { n_nn += hp[p].phase == kPhaseNeedNN; n_ev += hp[p].phase == kPhaseEval; n_fin += hp[p].phase == kPhaseFinished; }
-      const auto now = std::chrono::steady_clock::now();
-      fprintf(stderr, "[s3d trace] round=%ld dt=%.1f us  after round: need_nn=%d eval=%d finished=%d\n", round,
-              std::chrono::duration<double, std::micro>(now - t_round).count(), n_nn, n_ev, n_fin);
-      t_round = std::chrono::steady_clock::now();
-      if (np <= 4)
-      for (uint32_t p = 0; p < np; ++p)
-        fprintf(stderr, "[s3d trace] round=%ld pair=%u phase=%d outer=%d inner=%d ncorr=%u t=(%.9g %.9g %.9g) r10=%.9g r20=%.9g r21=%.9g\n", round, p,
-                hp[p].phase, hp[p].outer_iterations, hp[p].inner_iterations, hp[p].n_corr, hp[p].T[12], hp[p].T[13], hp[p].T[14], hp[p].T[1],
-                hp[p].T[2], hp[p].T[6]);
-    }
-    if (h_flags[1] <= 0) break;
+  {
+    StageTimer timer(ws, kStageSolve);
+    gicp_prepare_kernel<<<grid, 256, 0, st>>>(slots, pairs, ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), psched, flags);
+    ++ws.launches;
   }
   {
-    StageTimer timer(ws, kStageFitness);
-    gicp_fitness_kernel<<<grid, kIterTile, 0, st>>>(slots, pairs, ws.moved.as<float4>(),
-                                                    ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), ws.fit_partial.as<double>());
-    gicp_fitness_reduce_kernel<<<(np + 63) / 64, 64, 0, st>>>(slots, pairs, ws.fit_partial.as<double>(), tiles_per_pair, np);
-    ws.launches += 2;
+    StageTimer timer(ws, kStageIter);
+    S3D_CUDA(cudaFuncSetAttribute(gicp_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmLoop));
+    if (throughput) {
+      if (!ws.loop_exec) build_loop_graph(ws);
+      S3D_CUDA(cudaGraphLaunch(ws.loop_exec, st));
+    } else {
+      gicp_loop_kernel<<<loop_grid(ws.device), kIterTile, kSmLoop, st>>>(ws.gicp_args.as<GicpArgs>(), cudaGraphConditionalHandle{}, 0);
+      ++ws.launches;
+    }
+    S3D_CUDA(cudaGetLastError());
   }
+  S3D_CUDA(cudaMemcpyAsync(h_ctl, ctl, 16, cudaMemcpyDeviceToHost, st));
   S3D_CUDA(cudaMemcpyAsync(hp, pairs, sizeof(PairState) * np, cudaMemcpyDeviceToHost, st));
   SlotInfo* hs = ws.h_slots.as<SlotInfo>();
   S3D_CUDA(cudaMemcpyAsync(hs, slots, sizeof(SlotInfo) * ws.n_slots, cudaMemcpyDeviceToHost, st));
   S3D_CUDA(cudaMemcpyAsync(h_flags, flags, 16, cudaMemcpyDeviceToHost, st));
-  S3D_CUDA(cudaStreamSynchronize(st));
-  ws.d2h += sizeof(PairState) * np + sizeof(SlotInfo) * ws.n_slots + 16;
+  ws.sync();
+  ws.d2h += sizeof(PairState) * np + sizeof(SlotInfo) * ws.n_slots + 32;
+  ws.passes += h_ctl[0]; ws.ctrl_steps += h_ctl[1];
+  ws.launches += h_ctl[3];  // launches of the loop kernel inside the graph's WHILE node (throughput mode)
+  for (auto& sp : ws.spans) if (sp.stage == kStageIter && h_ctl[3]) sp.n_launch = h_ctl[3];
   ws.collect_spans();
   check_arena(ws, h_flags);
+  if (h_flags[0] & kErrWatchdog) throw CudaError{"GICP loop kernel: watchdog expired (scheduler fault)"};
   for (uint32_t p = 0; p < np; ++p) {
     const s3d_registration_parameters& cfg = params[p];
     const PairState& ps = hp[p];
@@ -642,6 +791,11 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
     for (int i = 0; i < 16; ++i) r.T[i] = (i % 5 == 0) ? 1.0 : 0.0;
     r.n_source = hs[2 * p].n_pts; r.n_target = hs[2 * p + 1].n_pts;
     if (r.n_target < 100 || r.n_source < 100) { r.status = S3D_TOO_FEW_POINTS; continue; }  // :134-135
+    if (ps.active) {  // the loop kernel left the pair unfinished: a scheduler / optimiser fault, not a NoMatch
+      r.status = S3D_INTERNAL_ERROR;
+      set_error("GICP loop ended with an active pair");
+      continue;
+    }
     for (int i = 0; i < 16; ++i) r.T[i] = (double)ps.final_T[i];  // Transform(Eigen::Isometry3f(final))  :80
     r.fitness = ps.fit_n > 0 ? ps.fit_sum / (double)ps.fit_n : 1.7976931348623157e308;
     r.converged = ps.converged; r.outer_iterations = ps.outer_iterations; r.inner_iterations = ps.inner_iterations;

@@ -74,14 +74,34 @@ struct PairState {
   float  T_trial[kLineSearchTrials][16];  // float matrices of the back-tracking trials x - 2^-j delta of the current Newton step
   int32_t trial_first, trial_count;       // trials the next evaluation pass has to cover (0,1 first; 1,9 if trial 0 failed)
   double sums[kNumMoments];// reduced sums of the current correspondence set (static part) + last evaluation (residual part)
-  int32_t phase;           // kPhaseNeedNN / kPhaseEval / kPhaseFinished
+  int32_t phase;           // kPhaseNeedNN / kPhaseEval / kPhaseFitness / kPhaseFinished
   int32_t active;          // 1 while the outer loop runs
   int32_t converged;
   int32_t failed;          // optimiser exception (<4 correspondences)
   int32_t outer_iterations, inner_iterations;
   uint32_t n_corr;
   uint32_t pt_off;         // first index of this pair in the per-pair arrays (moved, prev_nn, sec_lb, corr, mahal)
-  uint32_t reserved;
+  uint32_t ticket;         // tiles of the running pass that have delivered their partial sums (the last one runs the control step)
+};
+static_assert(sizeof(PairState) % 8 == 0, "PairState is staged through shared memory in 8-byte words");
+
+// Scheduler entry of one pair in the persistent GICP loop kernel (gicp.cu): both words are epoch << 32 | count.
+struct PairSched {
+  unsigned long long claim;  // next unclaimed tile of the open pass
+  unsigned long long desc;   // tiles of the open pass (0: nothing to claim)
+};
+
+// Arguments of the GICP loop kernel (device resident).
+struct GicpArgs {
+  const SlotInfo* slots; PairState* pairs;
+  const float4* moved; uint32_t* prev_nn; float* sec_lb; uint32_t* corr; double* mahal; double* moments; double* eval_part; double* fit_partial;
+  int32_t* flags;          // [0] error bits, [1] active pairs
+  PairSched* psched;
+  uint32_t* ctl;           // [0] tiles processed, [1] control steps (statistics); [2] CTAs that have left the launch, [3] launches (throughput mode)
+  uint32_t tiles_per_pair, n_pairs;
+  uint32_t linger;         // throughput mode: polls (~0.4 us each) an idle CTA waits for a pass to be published before it leaves
+  uint32_t max_launches;   // throughput mode: launches after which the loop gives up (scheduler fault)
+  unsigned long long watchdog_cycles;
 };
 
 constexpr int kIterTile = 256;   // source points per CTA in the fused correspondence kernel
@@ -90,6 +110,10 @@ constexpr int kIterTile = 256;   // source points per CTA in the fused correspon
 struct Workspace {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaEvent_t sync_event = nullptr;           // cudaEventBlockingSync: a worker of a batch call sleeps in sync() instead of spinning on the stream
+  bool blocking_sync = false;                 // set for the chunks of multi-threaded batch calls (many host threads per device, several ranks per box)
+  cudaEvent_t input_event = nullptr;          // orders this workspace's stream after the caller's stream (s3d_set_input_stream)
+  cudaStream_t input_stream = nullptr; bool wait_input = false;
   std::mutex* upload_gate = nullptr;          // when set, setup_batch holds it from its first host-to-device copy until the copies have landed
   // sizes of the current batch
   uint32_t n_slots = 0, n_pairs = 0, total = 0, n_tiles = 0;
@@ -120,6 +144,10 @@ struct Workspace {
   DevBuf fit_partial;                         // double[iter_tiles*2]
   DevBuf accu, accu2, map_aux;                // map building: accumulated cloud, filtered cloud, poses / keep flags
   DevBuf ndt_pairs, ndt_leaves, ndt_hash, ndt_part;  // NDT: NdtPair[n_pairs], NdtLeaf[], uint2 hash arena, double[tiles * 44]
+  DevBuf gicp_args, gicp_sched;               // GicpArgs; 16 counter words + PairSched[n_pairs] of the loop kernel
+  uint64_t passes = 0, ctrl_steps = 0;        // tiles processed / control steps run by the loop kernel (statistics)
+  cudaGraph_t loop_graph = nullptr;           // throughput mode: WHILE (a pair is active) { gicp_loop_kernel }, built on first use
+  cudaGraphExec_t loop_exec = nullptr;
   DevBuf flags;                               // int32[16]: [0] error bits, [1] active pairs, [2] hash entries used, [3] entries needed, [8] long voxel runs, [9] kept points
   PinnedBuf h_slots, h_pairs, h_small, h_tiles;  // pinned host mirrors
   uint64_t launches = 0, h2d = 0, d2h = 0;
@@ -135,10 +163,12 @@ struct Workspace {
 
   void init(int dev);
   void destroy();
+  void sync();  // wait for everything enqueued on `stream`
+  void order_after_input();  // s3d_set_input_stream: enqueue a wait for what the caller's stream holds now
 };
 
-enum ErrorBits { kErrHashArena = 1 };
-enum PairPhase { kPhaseNeedNN = 0, kPhaseEval = 1, kPhaseFinished = 2 };
+enum ErrorBits { kErrHashArena = 1, kErrWatchdog = 2 };
+enum PairPhase { kPhaseNeedNN = 0, kPhaseEval = 1, kPhaseFinished = 2, kPhaseFitness = 3 };
 constexpr int kEvalSums = 13;  // sums 60..72 of gicp_math.h: the residual-dependent part of an evaluation (per trial)
 enum Stage { kStageVoxel = 0, kStageGrid = 1, kStageKnn = 2, kStageIter = 3, kStageSolve = 4, kStageFitness = 5 };
 

@@ -19,33 +19,70 @@
 
 namespace s3d {
 
-// heapsort (ascending (d2, idx) = FLANN's sorted result order), moments exactly as PCL (float products accumulated in
-// double, in neighbour order; A.3 step 2), smallest eigenvector; optional neighbour lists for the stage API
+// Moments exactly as PCL (float products accumulated in double, in neighbour order = FLANN's ascending (d2, idx) order; A.3
+// step 2), smallest eigenvector; optional neighbour lists for the stage API.
+//
+// The neighbour ORDER only matters where a double sum rounds.  Every term is a float (24-bit significand) widened to double,
+// so a sum of k of them is exact — hence the same in any order — whenever the binary exponents of its non-zero terms span
+// few enough bits: with e in [lo, hi] per axis and L = ceil(log2 k), all partial sums of x_i are multiples of 2^(lo-23) below
+// 2^(hi+1+L), and those of the products x_i*y_i multiples of 2^(lox+loy-23) below 2^(hix+hiy+2+L); both fit 53 bits if every
+// axis has hi - lo <= (28 - L) / 2 (11 for k = 20).  The align() path therefore sums the heap in storage order while tracking
+// the exponent range (a few integer min/max per neighbour) and only falls back to heapsort + ordered sums when that exactness
+// certificate fails (a neighbourhood that straddles a coordinate plane within ~1e-4 of its extent) or when the caller wants the
+// sorted lists.  The result is bit-identical to the ordered sums either way; the heapsort was 18 % of this kernel.
 __device__ __forceinline__ void knn_finish(const SlotInfo& si, const float4* __restrict__ cloud, uint64_t* h, int cnt, int k, uint32_t r, uint32_t q_orig,
                                            double4* __restrict__ normals, uint32_t* __restrict__ knn_index, float* __restrict__ knn_dist2) {
-  for (int m = cnt - 1; m > 0; --m) {
-    const uint64_t last = h[m * kKnnThreads];
-    h[m * kKnnThreads] = h[0];
-    heap_sift_down(h, m, last);
-  }
   double mean[3] = {0, 0, 0}, cov[6] = {0, 0, 0, 0, 0, 0};  // cov: 00,10,11,20,21,22
-  for (int j = 0; j < cnt; ++j) {
-    const uint64_t key = h[j * kKnnThreads];
-    const uint32_t id = (uint32_t)key;
-    const float4 pt = __ldg(cloud + id);
-    mean[0] += (double)pt.x; mean[1] += (double)pt.y; mean[2] += (double)pt.z;
-    cov[0] += (double)__fmul_rn(pt.x, pt.x);
-    cov[1] += (double)__fmul_rn(pt.y, pt.x);
-    cov[2] += (double)__fmul_rn(pt.y, pt.y);
-    cov[3] += (double)__fmul_rn(pt.z, pt.x);
-    cov[4] += (double)__fmul_rn(pt.z, pt.y);
-    cov[5] += (double)__fmul_rn(pt.z, pt.z);
-    if (knn_index) knn_index[((size_t)si.off + q_orig) * k + j] = id;
-    if (knn_dist2) knn_dist2[((size_t)si.off + q_orig) * k + j] = __uint_as_float((uint32_t)(key >> 32));
+  bool ordered = knn_index != nullptr || knn_dist2 != nullptr;
+  if (!ordered) {
+    uint32_t elo[3] = {255u, 255u, 255u}, ehi[3] = {0u, 0u, 0u};
+    for (int j = 0; j < cnt; ++j) {
+      const float4 pt = __ldg(cloud + (uint32_t)h[j * kKnnThreads]);
+      const float c3v[3] = {pt.x, pt.y, pt.z};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const uint32_t e = (__float_as_uint(c3v[a]) >> 23) & 255u;
+        if (c3v[a] != 0.f) { elo[a] = min(elo[a], e); ehi[a] = max(ehi[a], e); }  // exact zeros add nothing; denormals (e = 0) fail the test below
+      }
+      mean[0] += (double)pt.x; mean[1] += (double)pt.y; mean[2] += (double)pt.z;
+      cov[0] += (double)__fmul_rn(pt.x, pt.x);
+      cov[1] += (double)__fmul_rn(pt.y, pt.x);
+      cov[2] += (double)__fmul_rn(pt.y, pt.y);
+      cov[3] += (double)__fmul_rn(pt.z, pt.x);
+      cov[4] += (double)__fmul_rn(pt.z, pt.y);
+      cov[5] += (double)__fmul_rn(pt.z, pt.z);
+    }
+    const int L = 32 - __clz(max(cnt, 2) - 1);  // ceil(log2 cnt)
+    const uint32_t span = (uint32_t)max(0, (28 - L) / 2);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      if (ehi[a] >= elo[a] && (ehi[a] - elo[a] > span || elo[a] < 64u || ehi[a] > 190u)) ordered = true;  // products must stay normal floats
+    if (ordered) { for (int a = 0; a < 3; ++a) mean[a] = 0.0; for (int a = 0; a < 6; ++a) cov[a] = 0.0; }
   }
-  for (int j = cnt; j < k; ++j) {
-    if (knn_index) knn_index[((size_t)si.off + q_orig) * k + j] = kNoIndex;
-    if (knn_dist2) knn_dist2[((size_t)si.off + q_orig) * k + j] = INFINITY;
+  if (ordered) {
+    for (int m = cnt - 1; m > 0; --m) {  // heapsort: ascending (d2, idx)
+      const uint64_t last = h[m * kKnnThreads];
+      h[m * kKnnThreads] = h[0];
+      heap_sift_down(h, m, last);
+    }
+    for (int j = 0; j < cnt; ++j) {
+      const uint64_t key = h[j * kKnnThreads];
+      const uint32_t id = (uint32_t)key;
+      const float4 pt = __ldg(cloud + id);
+      mean[0] += (double)pt.x; mean[1] += (double)pt.y; mean[2] += (double)pt.z;
+      cov[0] += (double)__fmul_rn(pt.x, pt.x);
+      cov[1] += (double)__fmul_rn(pt.y, pt.x);
+      cov[2] += (double)__fmul_rn(pt.y, pt.y);
+      cov[3] += (double)__fmul_rn(pt.z, pt.x);
+      cov[4] += (double)__fmul_rn(pt.z, pt.y);
+      cov[5] += (double)__fmul_rn(pt.z, pt.z);
+      if (knn_index) knn_index[((size_t)si.off + q_orig) * k + j] = id;
+      if (knn_dist2) knn_dist2[((size_t)si.off + q_orig) * k + j] = __uint_as_float((uint32_t)(key >> 32));
+    }
+    for (int j = cnt; j < k; ++j) {
+      if (knn_index) knn_index[((size_t)si.off + q_orig) * k + j] = kNoIndex;
+      if (knn_dist2) knn_dist2[((size_t)si.off + q_orig) * k + j] = INFINITY;
+    }
   }
   const double dk = (double)k;  // PCL divides by k_correspondences_
   mean[0] /= dk; mean[1] /= dk; mean[2] /= dk;

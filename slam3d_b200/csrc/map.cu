@@ -143,7 +143,7 @@ uint32_t run_accumulate(Workspace& ws, const std::vector<const float*>& clouds, 
   transform_concat_kernel<<<ws.n_tiles, kSortThreads, 0, ws.stream>>>(ws.slots.as<SlotInfo>(), tm, d_pose, d_off, ws.accu.as<float4>());
   ++ws.launches;
   S3D_CUDA(cudaGetLastError());
-  S3D_CUDA(cudaStreamSynchronize(ws.stream));  // `off` and the pageable `poses` must outlive the copies
+  ws.sync();  // `off` and the pageable `poses` must outlive the copies
   return (uint32_t)total;
 }
 
@@ -166,7 +166,7 @@ uint32_t run_radius_filter(Workspace& ws, const float4* dev_in, uint32_t n, doub
   S3D_CUDA(cudaGetLastError());
   int32_t* hf = ws.h_small.as<int32_t>();
   S3D_CUDA(cudaMemcpyAsync(hf, ws.flags.p, 64, cudaMemcpyDeviceToHost, ws.stream));
-  S3D_CUDA(cudaStreamSynchronize(ws.stream));
+  ws.sync();
   ws.d2h += 64;
   check_arena(ws, hf);
   return (uint32_t)hf[9];

@@ -557,7 +557,7 @@ void run_ndt(Workspace& ws, const std::vector<s3d_registration_parameters>& para
       }
     }
     S3D_CUDA(cudaMemcpyAsync(h_flags, flags, 16, cudaMemcpyDeviceToHost, st));
-    S3D_CUDA(cudaStreamSynchronize(st));
+    ws.sync();
     ws.d2h += 16;
     if (trace && np <= 4) {
       S3D_CUDA(cudaMemcpy(hp, pairs, sizeof(NdtPair) * np, cudaMemcpyDeviceToHost));
@@ -578,7 +578,7 @@ void run_ndt(Workspace& ws, const std::vector<s3d_registration_parameters>& para
   SlotInfo* hs = ws.h_slots.as<SlotInfo>();
   S3D_CUDA(cudaMemcpyAsync(hs, slots, sizeof(SlotInfo) * ws.n_slots, cudaMemcpyDeviceToHost, st));
   S3D_CUDA(cudaMemcpyAsync(h_flags, flags, 16, cudaMemcpyDeviceToHost, st));
-  S3D_CUDA(cudaStreamSynchronize(st));
+  ws.sync();
   ws.d2h += sizeof(NdtPair) * np + sizeof(SlotInfo) * ws.n_slots + 16;
   ws.collect_spans();
   check_arena(ws, h_flags);

@@ -19,8 +19,29 @@ void Workspace::init(int dev) {
   device = dev;
   S3D_CUDA(cudaSetDevice(dev));
   S3D_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  S3D_CUDA(cudaEventCreateWithFlags(&sync_event, cudaEventBlockingSync | cudaEventDisableTiming));
+  S3D_CUDA(cudaEventCreateWithFlags(&input_event, cudaEventDisableTiming));
   flags.reserve(64);
   h_small.reserve(4096);
+}
+
+// Single calls spin on the stream (lowest latency).  The chunks of a batch call run on several host threads per device — and
+// under torchrun on several ranks per box — so they sleep on a blocking event instead: 8 ranks x 6 spinning threads on a
+// 32-core host was the 8-GPU scaling loss of round 1.
+void Workspace::sync() {
+  if (blocking_sync && sync_event) {
+    S3D_CUDA(cudaEventRecord(sync_event, stream));
+    S3D_CUDA(cudaEventSynchronize(sync_event));
+  } else {
+    S3D_CUDA(cudaStreamSynchronize(stream));
+  }
+}
+
+// device inputs produced on the caller's stream (s3d_set_input_stream): order this workspace's stream after it
+void Workspace::order_after_input() {
+  if (!wait_input) return;
+  S3D_CUDA(cudaEventRecord(input_event, input_stream));
+  S3D_CUDA(cudaStreamWaitEvent(stream, input_event, 0));
 }
 
 cudaEvent_t Workspace::get_event() {
@@ -46,9 +67,16 @@ void Workspace::destroy() {
   collect_spans();
   for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
   event_pool.clear();
+  if (sync_event) cudaEventDestroy(sync_event);
+  if (input_event) cudaEventDestroy(input_event);
+  sync_event = input_event = nullptr;
+  if (loop_exec) cudaGraphExecDestroy(loop_exec);
+  if (loop_graph) cudaGraphDestroy(loop_graph);
+  loop_exec = nullptr; loop_graph = nullptr;
+
   DevBuf* bufs[] = {&slots, &pairs, &raw_stage, &work, &gpts, &keys0, &keys1, &vals0, &vals1, &hist, &sort_totals, &long_runs, &tile_slot, &tile_first,
                     &slot_tile_begin, &tile_heads, &hash, &normals, &moved, &prev_nn, &sec_lb, &moments, &eval_part, &corr, &mahal, &iter_tile_pair, &iter_tile_first,
-                    &fit_partial, &flags, &accu, &accu2, &map_aux, &ndt_pairs, &ndt_leaves, &ndt_hash, &ndt_part};
+                    &fit_partial, &flags, &accu, &accu2, &map_aux, &ndt_pairs, &ndt_leaves, &ndt_hash, &ndt_part, &gicp_args, &gicp_sched};
   for (DevBuf* b : bufs) b->release();
   h_slots.release(); h_pairs.release(); h_small.release(); h_tiles.release();
   if (stream) cudaStreamDestroy(stream);
@@ -108,6 +136,7 @@ void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const s
   }
   if (need_stage) ws.raw_stage.reserve(16 * tot);
 
+  ws.order_after_input();
   std::unique_lock<std::mutex> gate;  // uploads of concurrent chunks take turns (api.cu, t_gate_uploads)
   if (need_stage && ws.upload_gate) gate = std::unique_lock<std::mutex>(*ws.upload_gate);
   SlotInfo* hs = ws.h_slots.as<SlotInfo>();
@@ -134,7 +163,7 @@ void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const s
     for (uint64_t f = 0; f < sizes[s]; f += kSortTile) { h_tile_slot[t] = s; h_tile_first[t] = static_cast<uint32_t>(f); ++t; }
   }
   h_begin[ns] = t;
-  if (gate.owns_lock()) { S3D_CUDA(cudaStreamSynchronize(ws.stream)); gate.unlock(); }
+  if (gate.owns_lock()) { ws.sync(); gate.unlock(); }
   S3D_CUDA(cudaMemcpyAsync(ws.slots.p, hs, sizeof(SlotInfo) * ns, cudaMemcpyHostToDevice, ws.stream));
   if (n_tiles) {
     S3D_CUDA(cudaMemcpyAsync(ws.tile_slot.p, h_tile_slot, 4 * size_t(n_tiles), cudaMemcpyHostToDevice, ws.stream));

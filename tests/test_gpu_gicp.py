@@ -84,9 +84,14 @@ def test_gates_match_oracle(ctx, oracle_mod, kitti):
         check(ctx.gicp_align(src, tgt, None, p), oracle_mod.gicp_align(src, tgt, None, p))
     r = ctx.gicp_align(src[:500], tgt[:500], None, RegistrationParameters.defaults(point_cloud_density=20.0))
     assert r.status == _abi.S3D_TOO_FEW_POINTS
-    for alg in (_abi.ALG_ICP, _abi.ALG_GICP_OMP, _abi.ALG_NDT_OMP, 17):  # ALG_NDT runs: tests/test_gpu_ndt.py
+    for alg in (_abi.ALG_ICP, 17):  # ALG_NDT runs: tests/test_gpu_ndt.py
         r = ctx.gicp_align(src, tgt, None, RegistrationParameters.defaults(point_cloud_density=0.5, registration_algorithm=alg))
         assert r.status == _abi.S3D_UNKNOWN_ALGORITHM
+    # GICP_OMP (PointCloudSensor.cpp:149-152, pclomp's multi-threaded GICP) selects the GICP branch of the GPU path
+    p_omp = RegistrationParameters.defaults(point_cloud_density=0.5, registration_algorithm=_abi.ALG_GICP_OMP)
+    p_gicp = RegistrationParameters.defaults(point_cloud_density=0.5)
+    r_omp, r_gicp = ctx.gicp_align(src, tgt, None, p_omp), ctx.gicp_align(src, tgt, None, p_gicp)
+    assert r_omp.status == _abi.S3D_OK and np.array_equal(r_omp.pose(), r_gicp.pose()) and r_omp.fitness == r_gicp.fitness
     # too few points wins over the algorithm switch (:134 before :139)
     r = ctx.gicp_align(src[:500], tgt[:500], None, RegistrationParameters.defaults(point_cloud_density=20.0, registration_algorithm=_abi.ALG_NDT))
     assert r.status == _abi.S3D_TOO_FEW_POINTS

@@ -80,8 +80,10 @@ def test_gates_match_oracle(ctx, oracle_mod, kitti):
     import slam3d_b200
     with pytest.raises(slam3d_b200.S3DError, match="resolution must be positive"):
         ctx.gicp_align(src, tgt, None, ndt_params(resolution=0.0))
-    r = ctx.gicp_align(src, tgt, None, RegistrationParameters.defaults(registration_algorithm=_abi.ALG_NDT_OMP))
-    assert r.status == _abi.S3D_UNKNOWN_ALGORITHM
+    # NDT_OMP (PointCloudSensor.cpp:153-157, pclomp's multi-threaded NDT) selects the NDT branch of the GPU path
+    r_omp = ctx.gicp_align(src, tgt, None, RegistrationParameters.defaults(point_cloud_density=0.2, registration_algorithm=_abi.ALG_NDT_OMP))
+    r_ndt = ctx.gicp_align(src, tgt, None, ndt_params())
+    assert r_omp.status == r_ndt.status and np.array_equal(r_omp.pose(), r_ndt.pose()) and r_omp.outer_iterations == r_ndt.outer_iterations
 
 
 def test_batch_equals_single_and_is_deterministic(ctx, kitti):
