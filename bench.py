@@ -305,6 +305,7 @@ def main():
     # per-kernel durations for the roofline: same workload, same process, right after the timed region, but on ONE stream
     # (with several concurrent streams an event pair also spans other streams' kernels, so a kernel's own duration is undefined)
     os.environ["S3D_STREAMS_PER_DEVICE"] = "1"
+    os.environ["S3D_LOOP_MODE"] = "2"  # the per-pass kernels of the batch path (a single-stream call would otherwise take the persistent kernel)
     ctx_serial = slam3d_b200.Context([devices[0]])
     ser_src, ser_tgt = dev_src[:args.pairs], dev_tgt[:args.pairs]
     ctx_serial.gicp_align_batch(ser_src, ser_tgt, None, p)
@@ -318,6 +319,7 @@ def main():
     loop_stats = ctx_serial.loop_stats(reset=True)
     ctx_serial.close()
     del os.environ["S3D_STREAMS_PER_DEVICE"]
+    del os.environ["S3D_LOOP_MODE"]
 
     # ---- end to end: host buffers in, results out, same call ---------------------------------------------------------------------
     for _ in range(2):
@@ -410,15 +412,15 @@ def main():
     eval_total = max(passes_total - outer_total - n_ser, 0.0)                            # trial passes
     # algorithmic bytes (SURVEY 8d with 24-byte normals instead of 48-byte covariances):
     bytes_by_stage = {
-        # search pass 16+24 moving point/normal + 16+24 gathered fixed point/normal; trial pass 16 + 16 + 48; fitness pass 32
-        "gicp_iter": m_tgt * (80.0 * outer_total + 80.0 * eval_total + 32.0 * n_ser),
+        "gicp_iter": 80.0 * m_tgt * outer_total,                        # search pass: 16+24 moving point/normal + 16+24 gathered fixed point/normal
         "knn_cov": 40.0 * (m_tgt + m_src) * n_ser,                      # 16 read + 24 written per point
         "voxel": (16.0 * 2 * N_POINTS + 16.0 * (m_tgt + m_src)) * n_ser,
         "grid": 36.0 * (m_tgt + m_src) * n_ser,
         "fitness": 32.0 * m_tgt * n_ser,
-        "gicp_solve": 32.0 * m_tgt * n_ser,
+        "gicp_solve": 80.0 * m_tgt * eval_total,                        # trial pass: 16 + 16 + 48 (control kernels: a few KB)
     }
-    kernel_of = {"gicp_iter": "gicp_loop_kernel", "knn_cov": "knn_cov_kernel", "voxel": "voxel_*", "grid": "grid_*", "fitness": "ndt_fitness", "gicp_solve": "gicp_prepare_kernel"}
+    kernel_of = {"gicp_iter": "gicp_search_kernel", "knn_cov": "knn_cov_kernel", "voxel": "voxel_*", "grid": "grid_*", "fitness": "gicp_fitness_kernel",
+                 "gicp_solve": "gicp_trial_kernel + gicp_ctrl_kernel"}
     dom_ms = stages[dom]["ms"]
     dom_launches = max(stages[dom]["launches"], 1)
     achieved = bytes_by_stage[dom] / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
@@ -430,7 +432,7 @@ def main():
         tj = json.load(open(os.path.join(ROOT, "profiles", tpaths[-1])))
         ent = tj.get(kernel_of[dom])
         if ent:
-            units = {"gicp_iter": m_tgt * passes_total, "knn_cov": (m_tgt + m_src) * n_ser}.get(dom)
+            units = {"gicp_iter": m_tgt * outer_total, "knn_cov": (m_tgt + m_src) * n_ser}.get(dom)
             if units:
                 traffic = ent["dram_bytes_per_unit"] * units / dom_launches
                 traffic_src = f"profiles/{tpaths[-1]}: {ent['dram_bytes_per_unit']:.1f} B per {ent['unit']} ({ent.get('capture', '')})"

@@ -207,6 +207,15 @@ int s3d_remove_outliers(s3d_context* ctx, s3d_cloud in, double radius, unsigned 
 int s3d_build_map(s3d_context* ctx, const s3d_cloud* clouds, const double* poses, int n, double outlier_radius,
                   unsigned outlier_neighbors, double resolution, float* out_xyzw, uint64_t* n_out);
 
+/* PointCloudSensor::createCombinedMeasurement (:258-266) on explicit lists — the patch of scans a loop closure is matched
+ * with (ScanSensor::buildPatch, core/ScanSensor.cpp:215-270): getAccumulatedCloud (transform(cloud_i, pose_i) appended in list
+ * order, pose_i = vertex.correctedPose * measurement.sensorPose), then pcl::transformPointCloud with patch_pose.inverse().
+ * Both transforms run on the device in one pass over the points (two float roundings per coordinate, like the two PCL calls).
+ * poses = n x 16 doubles, patch_pose = 16 doubles; out_xyzw (host or device) holds sum(clouds[i].n) points.
+ * patch_pose == NULL stops after the accumulation: PointCloudSensor::getAccumulatedCloud (:235-256). */
+int s3d_create_combined_measurement(s3d_context* ctx, const s3d_cloud* clouds, const double* poses, int n, const double patch_pose[16],
+                                    float* out_xyzw, uint64_t* n_out);
+
 /* Optional per-stage device timing (CUDA events on the launching stream, read back at the call's final
  * synchronisation).  Stage ids: 0 voxel filter, 1 NN grid build, 2 kNN+covariances (NDT: the target's Gaussian voxel
  * grid), 3 the GICP loop kernel — search, trial and fitness passes and the control steps of all outer iterations (NDT:

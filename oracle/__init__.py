@@ -166,6 +166,31 @@ def transform_cloud(cloud, T):
     return out
 
 
+def combined_measurement(clouds, poses, patch_pose):
+    """createCombinedMeasurement (PointCloudSensor.cpp:258-266) on explicit lists; poses[i] = correctedPose_i * sensorPose_i."""
+    n = len(clouds)
+    keep = []
+    cc = (Cloud * max(n, 1))()
+    total = 0
+    for i in range(n):
+        a, c = _cloud(clouds[i]); keep.append(a); cc[i] = c; total += a.shape[0]
+    P = np.ascontiguousarray(np.stack([np.asarray(p, np.float64).T for p in poses])) if n else np.zeros((1, 4, 4))
+    inv = np.ascontiguousarray(isometry_inverse(patch_pose).T)
+    out = np.empty((max(total, 1), 4), np.float32)
+    m = C.c_uint64(0)
+    lib().s3d_oracle_combined_measurement(cc, P.ctypes.data_as(C.c_void_p), n, inv.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.byref(m))
+    return out[: m.value].copy()
+
+
+def isometry_inverse(T):
+    """Eigen::Isometry3d::inverse(): [R^T | -R^T t], in double."""
+    T = np.asarray(T, np.float64)
+    out = np.eye(4)
+    out[:3, :3] = T[:3, :3].T
+    out[:3, 3] = -(T[:3, :3].T @ T[:3, 3])
+    return out
+
+
 def remove_outliers(cloud, radius, min_neighbors):
     a, c = _cloud(cloud)
     out = np.empty((max(a.shape[0], 1), 4), np.float32)
@@ -189,6 +214,14 @@ def build_map(clouds, poses, outlier_radius, outlier_neighbors, resolution):
     lib().s3d_oracle_build_map(cc, P.ctypes.data_as(C.c_void_p), n, C.c_double(outlier_radius), C.c_uint(outlier_neighbors),
                                C.c_double(resolution), out.ctypes.data_as(C.c_void_p), C.byref(m))
     return out[: m.value].copy()
+
+
+def fnv1a(array):
+    """FNV-1a over the raw bytes of a numpy array, as baseline/doicp_driver.cpp hashes PCL's outputs."""
+    a = np.ascontiguousarray(array)
+    lib().s3d_oracle_fnv1a.restype = C.c_uint64
+    lib().s3d_oracle_fnv1a.argtypes = [C.c_void_p, C.c_uint64]
+    return "%016x" % lib().s3d_oracle_fnv1a(a.ctypes.data, a.nbytes)
 
 
 def max_threads():

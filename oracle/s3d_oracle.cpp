@@ -993,6 +993,29 @@ int s3d_oracle_remove_outliers(s3d_cloud cloud, double radius, unsigned min_neig
   return S3D_OK;
 }
 
+// FNV-1a over raw bytes: the array hash baseline/doicp_driver.cpp writes into tests/golden/pcl_<version>.json
+uint64_t s3d_oracle_fnv1a(const void* p, uint64_t n) {
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  uint64_t h = 1469598103934665603ull;
+  for (uint64_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+// PointCloudSensor::createCombinedMeasurement :258-266 with explicit (cloud, pose) lists: getAccumulatedCloud (:235-256,
+// transform(cloud_i, pose_i) appended in list order — the order of a build without OpenMP), then pcl::transformPointCloud with
+// pose.inverse().matrix(); `inv_patch_pose` is that inverse (the caller forms it, as Eigen::Isometry3d::inverse() does).
+int s3d_oracle_combined_measurement(const s3d_cloud* clouds, const double* poses, int n, const double inv_patch_pose[16], float* out_xyzw,
+                                    uint64_t* n_out) {
+  P4* o = reinterpret_cast<P4*>(out_xyzw);
+  size_t m = 0;
+  for (int i = 0; i < n; ++i) {
+    const P4* p = reinterpret_cast<const P4*>(clouds[i].xyzw);
+    for (size_t j = 0; j < clouds[i].n; ++j) o[m++] = transform_se3_d(inv_patch_pose, transform_se3_d(poses + 16 * i, p[j]));
+  }
+  *n_out = m;
+  return S3D_OK;
+}
+
 // PointCloudSensor::buildMap :301-318 with explicit (cloud, pose) lists: accumulate in list order, removeOutliers, downsample.
 // poses: n x 16 doubles (column-major) = vertex.correctedPose * measurement.sensorPose  (:248)
 int s3d_oracle_build_map(const s3d_cloud* clouds, const double* poses, int n, double outlier_radius, unsigned outlier_neighbors,

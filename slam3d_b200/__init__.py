@@ -51,6 +51,7 @@ def lib():
         L.s3d_remove_outliers.argtypes = [C.c_void_p, Cloud, C.c_double, C.c_uint, C.c_void_p, C.POINTER(C.c_uint64)]
         L.s3d_build_map.argtypes = [C.c_void_p, C.POINTER(Cloud), C.c_void_p, C.c_int, C.c_double, C.c_uint, C.c_double, C.c_void_p,
                                     C.POINTER(C.c_uint64)]
+        L.s3d_create_combined_measurement.argtypes = [C.c_void_p, C.POINTER(Cloud), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.s3d_prepare_cloud.argtypes = [C.c_void_p, C.c_int, Cloud, C.c_double, C.c_int, C.POINTER(C.c_void_p)]
         L.s3d_prepare_clouds.argtypes = [C.c_void_p, C.c_int, C.POINTER(Cloud), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_void_p)]
         L.s3d_release_cloud.argtypes = [C.c_void_p, C.c_void_p]
@@ -323,6 +324,24 @@ def _build_map(self, clouds, poses, outlier_radius=0.2, outlier_neighbors=3, res
     return out[: m.value].copy()
 
 
+def _combined_measurement(self, clouds, poses, patch_pose):
+    """createCombinedMeasurement (PointCloudSensor.cpp:258-266) on explicit (cloud, pose) lists."""
+    n = len(clouds)
+    keep = []
+    cc = (Cloud * max(n, 1))()
+    total = 0
+    for i in range(n):
+        a, c = _cloud(self, clouds[i]); keep.append(a); cc[i] = c; total += a.shape[0]
+    P = np.ascontiguousarray(np.stack([_colmajor(p) for p in poses])) if n else np.zeros((1, 4, 4))
+    pp = _colmajor(patch_pose)
+    out = np.empty((max(total, 1), 4), np.float32)
+    m = C.c_uint64(0)
+    self._check(lib().s3d_create_combined_measurement(self._h, cc, P.ctypes.data, n, pp.ctypes.data, out.ctypes.data, C.byref(m)),
+                "s3d_create_combined_measurement")
+    return out[: m.value].copy()
+
+
+Context.combined_measurement = _combined_measurement
 Context.transform_cloud = _transform_cloud
 Context.remove_outliers = _remove_outliers
 Context.build_map = _build_map

@@ -781,6 +781,33 @@ int s3d_transform_cloud(s3d_context* ctx, s3d_cloud in, const double T[16], floa
   });
 }
 
+int s3d_create_combined_measurement(s3d_context* ctx, const s3d_cloud* clouds, const double* poses, int n, const double patch_pose[16],
+                                    float* out_xyzw, uint64_t* n_out) {
+  if (!ctx || !n_out || n < 0 || (n > 0 && (!clouds || !poses))) return S3D_INVALID_ARGUMENT;
+  *n_out = 0;
+  if (n == 0) return S3D_OK;
+  return guarded([&]() -> int {
+    WsLease lease(ctx, 0);
+    Workspace& ws = *lease;
+    std::vector<const float*> ptrs(n);
+    std::vector<uint64_t> sizes(n);
+    for (int i = 0; i < n; ++i) { ptrs[i] = clouds[i].xyzw; sizes[i] = clouds[i].n; }
+    // pose.inverse() of an Eigen::Isometry3d: [R^T | -R^T t]
+    double inv[16];
+    if (patch_pose) {
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) inv[c * 4 + r] = patch_pose[r * 4 + c];
+      for (int r = 0; r < 3; ++r) { double s = 0; for (int c = 0; c < 3; ++c) s += inv[c * 4 + r] * patch_pose[12 + c]; inv[12 + r] = -s; }
+      inv[3] = inv[7] = inv[11] = 0; inv[15] = 1;
+    }
+    const uint32_t m = run_accumulate(ws, ptrs, sizes, poses, patch_pose ? inv : nullptr);
+    if (m && !out_xyzw) return S3D_INVALID_ARGUMENT;
+    copy_out(ws, out_xyzw, ws.accu.p, 16 * (size_t)m);
+    ws.sync();
+    *n_out = m;
+    return S3D_OK;
+  });
+}
+
 int s3d_remove_outliers(s3d_context* ctx, s3d_cloud in, double radius, unsigned min_neighbors, float* out_xyzw, uint64_t* n_out) {
   if (!ctx || !n_out || (in.n && !out_xyzw)) return S3D_INVALID_ARGUMENT;
   *n_out = 0;

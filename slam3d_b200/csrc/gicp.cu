@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) gicp_prepare_kernel(const SlotInfo* __res
     ps.ticket = 0;
     if (enough) { begin_outer(ps); atomicAdd(&flags[1], 1); }
     // first pass (epoch 1): the search pass of outer iteration 1, or nothing for a pair that fails the <100-point gate
-    psched[p].desc = (1ull << 32) | (enough ? (sa.n_pts + kIterTile - 1) / kIterTile : 0u);
+    psched[p].desc = (1ull << 32) | (enough ? (1u << 24) | ((sa.n_pts + kIterTile - 1) / kIterTile) : 0u);
     psched[p].claim = 1ull << 32;
   }
   if (!enough) return;
@@ -144,13 +144,20 @@ __device__ __forceinline__ bool certified_same_nn(const GridView& g, float3 q, f
 }
 
 // ---- shared-memory plan of gicp_loop_kernel ---------------------------------------------------------------------------------
-// [0, kSmTile)            tile scratch: search pass = feat[256][14] | part[3][74] | noted cells; the other passes and the control
-//                         step (CtrlShared) reuse the front of it
-// [kSmTile, kSmLoop)      read-only copy of the pair state of the tile being processed (fetched from L2)
+// [0, kSmTile)  tile scratch.  search pass: feat[256][14] | part[3][74] | noted cells;  trial pass: feat[256][8] | part[16][13];
+//                fitness pass: sums[256] | counts[256] | ... | noted cells;  control step: CtrlShared from 0.
+// The read-only copy of the pair state of the tile being processed (fetched from L2) sits in a part of the scratch that its
+// pass does not touch while the state is read: at kSmStateA (inside the feat area, which the search and fitness passes only
+// write after their searches — behind a barrier) or at kSmStateB (the noted-cells area, unused by the trial pass).
+// 46 832 B per CTA keeps four CTAs per SM inside the 196 KB shared-memory carve-out, i.e. 60 KB of L1 for the searches; a
+// separate 2.5 KB slot for the pair state pushed the carve-out to 228 KB and halved L1 (measured: profiles/r02_summary.md).
 constexpr size_t kSmPart = size_t(kIterTile) * kFeat * 8;                  // after feat[256][14]
 constexpr size_t kSmCells = kSmPart + 3 * kNumMoments * 8;                  // after part[3][74]
 constexpr size_t kSmTile = kSmCells + size_t(kNNGatherCap) * kIterTile * 8; // 46 832 B
-constexpr size_t kSmLoop = kSmTile + ((sizeof(PairState) + 15) & ~size_t(15));
+constexpr size_t kSmLoop = kSmTile;
+constexpr size_t kSmStateA = 4096, kSmStateB = kSmCells;
+static_assert(kSmStateA >= size_t(kIterTile) * 12 && kSmStateA + sizeof(PairState) <= kSmPart, "pair state vs fitness sums / feat area");
+static_assert(kSmStateB >= size_t(kIterTile) * 64 + 16 * kEvalSums * 8 && kSmStateB + sizeof(PairState) <= kSmTile, "pair state vs trial-pass scratch");
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
 __device__ __forceinline__ int32_t ld_volatile_i32(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
@@ -170,7 +177,14 @@ __device__ __forceinline__ void exch_release(unsigned long long* p, unsigned lon
 }
 __device__ __forceinline__ void red_add_release(int32_t* p, int32_t v) { asm volatile("red.add.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-// search pass of one tile; ps = shared-memory copy of the pair state
+// kShared = true: called from the persistent kernel — the pair state is a copy inside the scratch, and data written by other CTAs
+// of the same launch is read from L2.  kShared = false: called from a per-pass kernel — the pair state is read in place and
+// everything written before the launch is visible through L1.
+template <bool kShared, typename T>
+__device__ __forceinline__ T ld_pass(const T* p) { return kShared ? __ldcg(p) : *p; }
+
+// search pass of one tile
+template <bool kShared>
 __device__ __forceinline__ void iter_tile(const GicpArgs& a, const PairState& ps, const SlotInfo& sb, const SlotInfo& sa, uint32_t p, uint32_t tile,
                                           unsigned char* smem) {
   double (*feat)[kFeat] = reinterpret_cast<double (*)[kFeat]>(smem);
@@ -186,10 +200,10 @@ __device__ __forceinline__ void iter_tile(const GicpArgs& a, const PairState& ps
     const float3 q = transform_mv(ps.T, mv.x, mv.y, mv.z);
     const double thr = ps.max_corr2;
     const float cutoff = __double2float_ru(thr);
-    const uint32_t hint = __ldcg(a.prev_nn + ps.pt_off + r);  // written by the previous search pass, possibly on another SM
+    const uint32_t hint = ld_pass<kShared>(a.prev_nn + ps.pt_off + r);  // written by the previous search pass, possibly on another SM
     NNResult nn;
     float lb_new;
-    if (!certified_same_nn(g, q, transform_mv(ps.T_search, mv.x, mv.y, mv.z), hint, __ldcg(a.sec_lb + ps.pt_off + r), nn, lb_new)) {
+    if (!certified_same_nn(g, q, transform_mv(ps.T_search, mv.x, mv.y, mv.z), hint, ld_pass<kShared>(a.sec_lb + ps.pt_off + r), nn, lb_new)) {
       nn = nn_search<true>(g, q.x, q.y, q.z, cutoff, hint, kNoIndex, s_cells + threadIdx.x);
       a.prev_nn[ps.pt_off + r] = nn.pos;
       lb_new = sqrtf(nn.lb2) * 0.99999f;
@@ -223,6 +237,7 @@ __device__ __forceinline__ void iter_tile(const GicpArgs& a, const PairState& ps
     }
     a.corr[ps.pt_off + r] = c;
   }
+  if (kShared) __syncthreads();  // every thread is done with the pair state, which lives inside the feat area
 #pragma unroll
   for (int i = 0; i < kFeat; ++i) feat[threadIdx.x][i] = f[i];
   __syncthreads();
@@ -243,6 +258,7 @@ __device__ __forceinline__ void iter_tile(const GicpArgs& a, const PairState& ps
 }
 
 // trial pass of one tile: 13 residual sums per pending back-tracking trial, residual formed exactly as PCL forms it
+template <bool kShared>
 __device__ __forceinline__ void eval_tile(const GicpArgs& a, const PairState& ps, const SlotInfo& sb, const SlotInfo& sa, uint32_t p, uint32_t tile,
                                           unsigned char* smem) {
   double (*feat)[8] = reinterpret_cast<double (*)[8]>(smem);                                   // px py pz | (Md)0..2 | d^T M d | 1
@@ -252,14 +268,14 @@ __device__ __forceinline__ void eval_tile(const GicpArgs& a, const PairState& ps
   float4 mv = make_float4(0.f, 0.f, 0.f, 0.f), qb = mv;
   double M[6] = {0, 0, 0, 0, 0, 0};
   if (r < sa.n_pts) {
-    const uint32_t c = __ldcg(a.corr + ps.pt_off + r);  // written by the search pass, possibly on another SM
+    const uint32_t c = ld_pass<kShared>(a.corr + ps.pt_off + r);  // written by the search pass, possibly on another SM
     if (c != kNoIndex) {
       valid = true;
       mv = a.moved[ps.pt_off + r];
       qb = sb.gpts[c];
       const double* Mp = a.mahal + 6 * (size_t)(ps.pt_off + r);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) M[i] = __ldcg(Mp + i);
+      for (int i = 0; i < 6; ++i) M[i] = ld_pass<kShared>(Mp + i);
     }
   }
   const size_t t = (size_t)p * a.tiles_per_pair + tile;
@@ -297,6 +313,7 @@ __device__ __forceinline__ void eval_tile(const GicpArgs& a, const PairState& ps
 }
 
 // fitness pass of one tile — getFitnessScore(max_range): transformPointCloud(input, final), 1-NN, d2 <= max_range (sic), mean of d2 (A.6)
+template <bool kShared>
 __device__ __forceinline__ void fitness_tile(const GicpArgs& a, const PairState& ps, const SlotInfo& sb, const SlotInfo& sa, uint32_t p, uint32_t tile,
                                              unsigned char* smem) {
   double* ssum = reinterpret_cast<double*>(smem);
@@ -309,14 +326,14 @@ __device__ __forceinline__ void fitness_tile(const GicpArgs& a, const PairState&
     const float4 v = sa.gpts[r];
     const float3 q = transform_se3(ps.final_T, v.x, v.y, v.z);
     const float4 mv = a.moved[ps.pt_off + r];
-    const uint32_t hint = __ldcg(a.prev_nn + ps.pt_off + r);
+    const uint32_t hint = ld_pass<kShared>(a.prev_nn + ps.pt_off + r);
     NNResult nn;
     float lb_new;
-    if (!certified_same_nn(g, q, transform_mv(ps.T_search, mv.x, mv.y, mv.z), hint, __ldcg(a.sec_lb + ps.pt_off + r), nn, lb_new))
+    if (!certified_same_nn(g, q, transform_mv(ps.T_search, mv.x, mv.y, mv.z), hint, ld_pass<kShared>(a.sec_lb + ps.pt_off + r), nn, lb_new))
       nn = nn_search<true>(g, q.x, q.y, q.z, __double2float_ru(ps.fit_range), hint, kNoIndex, s_cells + threadIdx.x);
     if (nn.pos != kNoIndex && (double)nn.d2 <= ps.fit_range) { s = (double)nn.d2; c = 1; }
   }
-  ssum[threadIdx.x] = s; scnt[threadIdx.x] = c;
+  ssum[threadIdx.x] = s; scnt[threadIdx.x] = c;  // [0, 3072): below the pair state at kSmStateA
   __syncthreads();
   for (int o = kIterTile / 2; o > 0; o >>= 1) {  // fixed tree
     if (threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; scnt[threadIdx.x] += scnt[threadIdx.x + o]; }
@@ -400,7 +417,7 @@ struct CtrlShared {
 };
 static_assert(sizeof(CtrlShared) <= kSmTile, "control step must fit into the tile scratch");
 
-__device__ __noinline__ void ctrl_step(const GicpArgs& a, uint32_t p, int after_eval, unsigned char* smem) {
+__device__ __forceinline__ void ctrl_step_body(const GicpArgs& a, uint32_t p, int after_eval, unsigned char* smem) {
   CtrlShared& sh = *reinterpret_cast<CtrlShared*>(smem);
   PairState& ps = sh.ps;
   PairState* psg = a.pairs + p;
@@ -516,78 +533,102 @@ __device__ void fitness_finish(const GicpArgs& a, uint32_t p, unsigned char* sme
 }
 
 // ---- scheduler ------------------------------------------------------------------------------------------------------------------
-// PairSched.desc  = epoch << 32 | tiles of the pass that is open for claims (0: nothing to claim — control step running, or closed)
+// PairSched.desc  = epoch << 32 | tiles per claim << 24 | tiles of the pass that is open for claims (0 tiles: nothing to claim —
+//                   control step running, or the pair is closed)
 // PairSched.claim = epoch << 32 | next unclaimed tile.  A pass is published by writing desc first and claim second, so whoever
 // draws (epoch, t) from `claim` finds the descriptor of that epoch; claims past the end of a pass are harmless.
-__device__ __forceinline__ bool claim_tile(const GicpArgs& a, uint32_t& rot, uint32_t& p_out, uint32_t& t_out) {
-  for (uint32_t i = 0; i < a.n_pairs; ++i) {
-    uint32_t p = rot + i;
+// The first warp of a CTA claims: its lanes look at 32 pairs at once (two loads per lane, one L2 round trip for the warp), the
+// candidate nearest to the pair the CTA worked on last draws with one atomic — n tiles at a time (1 for the search and fitness
+// passes, kTrialTilesPerClaim for the cheap trial passes, whose fixed cost per claim — state fetch, ticket, barriers — would
+// otherwise match their work).
+constexpr uint32_t kTrialTilesPerClaim = 4;
+constexpr uint32_t kAvailMask = 0x00FFFFFFu;
+
+__device__ __forceinline__ bool claim_tiles_warp(const GicpArgs& a, uint32_t& rot, uint32_t& p_out, uint32_t& t_out, uint32_t& n_out) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t base = 0; base < a.n_pairs; base += 32) {
+    const bool in = base + lane < a.n_pairs;
+    uint32_t p = rot + base + lane;
     if (p >= a.n_pairs) p -= a.n_pairs;
-    PairSched* s = a.psched + p;
-    unsigned long long d = ld_volatile_u64(&s->desc);
-    if ((uint32_t)d == 0u) continue;
-    unsigned long long c = ld_volatile_u64(&s->claim);
-    if ((c >> 32) != (d >> 32) || (uint32_t)c >= (uint32_t)d) continue;  // fully claimed, or between two passes
-    c = atomicAdd(&s->claim, 1ull);
-    d = ld_volatile_u64(&s->desc);
-    if ((c >> 32) == (d >> 32) && (uint32_t)c < (uint32_t)d) { rot = p; p_out = p; t_out = (uint32_t)c; return true; }
+    unsigned long long d = 0, c = 0;
+    if (in) { d = ld_volatile_u64(&a.psched[p].desc); c = ld_volatile_u64(&a.psched[p].claim); }
+    const uint32_t per = max(1u, (uint32_t)d >> 24);
+    const bool cand = in && ((uint32_t)d & kAvailMask) != 0u && (c >> 32) == (d >> 32) && (uint32_t)c < ((uint32_t)d & kAvailMask);
+    uint32_t m = __ballot_sync(FULL, cand);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      unsigned long long cc = 0, dd = d;
+      if ((int)lane == src) {
+        cc = atomicAdd(&a.psched[p].claim, (unsigned long long)per);
+        if ((cc >> 32) != (d >> 32)) dd = ld_volatile_u64(&a.psched[p].desc);  // drawn from a newer pass: its descriptor is already published
+      }
+      cc = __shfl_sync(FULL, cc, src); dd = __shfl_sync(FULL, dd, src);
+      const uint32_t pp = __shfl_sync(FULL, p, src), added = __shfl_sync(FULL, per, src);
+      const uint32_t avail = (uint32_t)dd & kAvailMask, t0 = (uint32_t)cc;
+      if ((cc >> 32) == (dd >> 32) && t0 < avail) { rot = pp; p_out = pp; t_out = t0; n_out = min(added, avail - t0); return true; }
+    }
   }
   return false;
 }
 
-__device__ __forceinline__ void publish_pass(const GicpArgs& a, uint32_t p, uint32_t n_tiles) {
+__device__ __forceinline__ void publish_pass(const GicpArgs& a, uint32_t p, uint32_t n_tiles, uint32_t per_claim) {
   PairSched* s = a.psched + p;
   const unsigned long long epoch = (ld_volatile_u64(&s->desc) >> 32) + 1ull;
-  exch_release(&s->desc, (epoch << 32) | n_tiles);   // release: the pair state written by this CTA (ordered by the barrier before) comes first
-  if (n_tiles) exch_release(&s->claim, epoch << 32);  // release: the descriptor comes before the claims it validates
+  exch_release(&s->desc, (epoch << 32) | (n_tiles ? (per_claim << 24) | n_tiles : 0u));  // release: the pair state written by this CTA comes first
+  if (n_tiles) exch_release(&s->claim, epoch << 32);                                      // release: the descriptor comes before its claims
 }
 
-// mode 0 (latency, one launch): a CTA that finds nothing to claim waits for the next pass to be published.
-// mode 1 (throughput, inside the WHILE node of a CUDA graph): a CTA that finds nothing to claim leaves, and so does every CTA once
-//   half of the grid has left, so that the SM resources go to the kernels of the other chunks of the batch (other streams) instead
-//   of to waiting CTAs; the last CTA to leave keeps the graph's loop going while a pair is active.  Passes that are published
-//   while enough CTAs are still around are picked up by the same launch.
-__global__ void __launch_bounds__(kIterTile, 4) gicp_loop_kernel(const GicpArgs* __restrict__ ap, cudaGraphConditionalHandle cond, int mode) {
+// LATENCY mode — single registrations and small batches, one call at a time: the whole loop in ONE launch.  A CTA that finds
+// nothing to claim waits (nanosleep) for the next pass to be published.  Two CTAs per SM (128 registers): a single pair has 185
+// tiles per pass for 148 SMs, so occupancy is not what limits it — the serial control step is, and with 128 registers it runs
+// without the spills a 64-register budget forces on its FP64 chain.
+__global__ void __launch_bounds__(kIterTile, 2) gicp_loop_kernel(const GicpArgs* __restrict__ ap) {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ uint32_t s_p, s_tile;
+  __shared__ uint32_t s_p, s_tile, s_n;
   __shared__ int s_found, s_last;
-  PairState& tps = *reinterpret_cast<PairState*>(smem + kSmTile);
   const GicpArgs a = *ap;
   uint32_t rot = sm_id() % a.n_pairs;  // the CTAs of one SM start on the same pair: its grid and points share that SM's L1
   const long long t_start = clock64();
   for (;;) {
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {  // the first warp looks for work; the others wait at the barrier
       int found = 0;
+      uint32_t cp = 0, ct = 0, cn = 0;
       for (uint32_t spin = 0;; ++spin) {
-        if (mode == 1 && *reinterpret_cast<volatile uint32_t*>(&a.ctl[2]) * 2u > gridDim.x) break;  // the launch is draining
-        if (claim_tile(a, rot, s_p, s_tile)) { found = 1; break; }
+        if (claim_tiles_warp(a, rot, cp, ct, cn)) { found = 1; break; }
         if (ld_volatile_i32(&a.flags[1]) <= 0 || (ld_volatile_i32(&a.flags[0]) & kErrWatchdog)) break;  // no pair is active: done
-        if (mode == 1 && spin >= a.linger) break;
         __nanosleep(spin < 8 ? 100 : 400);
         if ((spin & 255u) == 255u && clock64() - t_start > (long long)a.watchdog_cycles) { atomicOr(&a.flags[0], kErrWatchdog); break; }
       }
-      s_found = found;
+      if (threadIdx.x == 0) { s_found = found; s_p = cp; s_tile = ct; s_n = cn; }
     }
     __syncthreads();
     if (!s_found) break;
-    const uint32_t p = s_p, tile = s_tile;
-    {  // the pair state and pass data were released before this claim became possible; read them from L2
+    const uint32_t p = s_p, tile0 = s_tile, n_claimed = s_n;
+    // the pair state and pass data were released before this claim became possible; read them from L2
+    const int phase = __ldcg(&a.pairs[p].phase);
+    const PairState& tps = *reinterpret_cast<const PairState*>(smem + (phase == kPhaseEval ? kSmStateB : kSmStateA));
+    {
       const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.pairs + p);
-      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&tps);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(smem + (phase == kPhaseEval ? kSmStateB : kSmStateA));
       for (uint32_t i = threadIdx.x; i < sizeof(PairState) / 8; i += blockDim.x) dst[i] = __ldcg(src + i);
     }
     __syncthreads();
-    const int phase = tps.phase;
     const SlotInfo& sb = a.slots[2 * p];
     const SlotInfo& sa = a.slots[2 * p + 1];
-    if (phase == kPhaseNeedNN) iter_tile(a, tps, sb, sa, p, tile, smem);
-    else if (phase == kPhaseEval) eval_tile(a, tps, sb, sa, p, tile, smem);
-    else fitness_tile(a, tps, sb, sa, p, tile, smem);
+    if (phase == kPhaseNeedNN) iter_tile<true>(a, tps, sb, sa, p, tile0, smem);            // one tile per claim
+    else if (phase == kPhaseFitness) fitness_tile<true>(a, tps, sb, sa, p, tile0, smem);   // one tile per claim
+    else
+      for (uint32_t k = 0; k < n_claimed; ++k) {
+        if (k) __syncthreads();  // the previous tile's partial sums have left the scratch
+        eval_tile<true>(a, tps, sb, sa, p, tile0 + k, smem);
+      }
     __syncthreads();
-    if (threadIdx.x == 0) {  // release: this tile's partial sums, correspondences, matrices and hints come before its ticket
+    if (threadIdx.x == 0) {  // release: these tiles' partial sums, correspondences, matrices and hints come before their tickets
       const uint32_t n_live = (sa.n_pts + kIterTile - 1) / kIterTile;
-      s_last = atom_add_release(&a.pairs[p].ticket, 1u) == n_live - 1;
-      atomicAdd(&a.ctl[0], 1u);
+      s_last = atom_add_release(&a.pairs[p].ticket, n_claimed) + n_claimed == n_live;
+      atomicAdd(&a.ctl[0], n_claimed);
     }
     __syncthreads();
     if (s_last) {  // this CTA delivered the last tile of the pass: control step, then publish what comes next
@@ -595,29 +636,91 @@ __global__ void __launch_bounds__(kIterTile, 4) gicp_loop_kernel(const GicpArgs*
       if (phase == kPhaseFitness) {
         fitness_finish(a, p, smem);
       } else {
-        ctrl_step(a, p, phase == kPhaseEval, smem);
+        ctrl_step_body(a, p, phase == kPhaseEval, smem);
         next_tiles = (sa.n_pts + kIterTile - 1) / kIterTile;  // search, trial and fitness passes all cover the moving cloud
       }
       __syncthreads();
       if (threadIdx.x == 0) {
         atomicAdd(&a.ctl[1], 1u);
-        publish_pass(a, p, next_tiles);
+        const int next_phase = next_tiles ? reinterpret_cast<const CtrlShared*>(smem)->ps.phase : kPhaseFinished;
+        publish_pass(a, p, next_tiles, next_phase == kPhaseEval ? kTrialTilesPerClaim : 1u);
         if (next_tiles == 0) red_add_release(&a.flags[1], -1);  // the pair is closed: its results come before the count
       }
     }
     __syncthreads();
   }
-  if (mode == 1 && threadIdx.x == 0) {
-    // the last CTA to leave re-arms the counters and decides whether the graph's WHILE loop runs the kernel again
-    if (atomicAdd(&a.ctl[2], 1u) == gridDim.x - 1) {
-      a.ctl[2] = 0;
-      const uint32_t launches = ++a.ctl[3];
-      const bool stuck = launches >= a.max_launches;
-      if (stuck) atomicOr(&a.flags[0], kErrWatchdog);
-      const bool again = ld_volatile_i32(&a.flags[1]) > 0 && !(ld_volatile_i32(&a.flags[0]) & kErrWatchdog) && !stuck;
-      cudaGraphSetConditional(cond, again ? 1u : 0u);
-    }
+}
+
+// THROUGHPUT mode — the chunks of a batch call, several streams per device.  The same tile and control functions, but one
+// kernel per pass and a separate (tiny) control kernel, replayed by the WHILE node of a CUDA graph until no pair iterates:
+//     search -> control -> trial -> control -> trial -> control -> condition
+// No host poll either, but nothing waits on the device: while one chunk sits in a control kernel (one CTA per pair) the SMs run
+// the search kernels of the other chunks, and the trial and control kernels have a light footprint.  Measured on B200 (64
+// pairs, 16 scenes, loop only): persistent kernel 11.2 ms on one stream but 13.7-16.3 ms on six (its resident CTAs hold the
+// registers of every SM, so the chunks serialise and each drags its own tail); per-pass kernels 14.9 ms on one stream and
+// 10.3 ms on six (profiles/r02_summary.md).  Results are bit-identical in both modes (same tile partials, same control step).
+__global__ void __launch_bounds__(kIterTile, 4) gicp_search_kernel(const GicpArgs* __restrict__ ap) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const GicpArgs a = *ap;
+  const uint32_t p = blockIdx.y, tile = blockIdx.x;
+  const PairState& ps = a.pairs[p];
+  if (ps.phase != kPhaseNeedNN) return;
+  const SlotInfo& sa = a.slots[2 * p + 1];
+  if (tile * kIterTile >= sa.n_pts) return;
+  iter_tile<false>(a, ps, a.slots[2 * p], sa, p, tile, smem);
+}
+
+__global__ void __launch_bounds__(kIterTile) gicp_trial_kernel(const GicpArgs* __restrict__ ap) {
+  __shared__ __align__(16) unsigned char smem[size_t(kIterTile) * 64 + 16 * kEvalSums * 8];
+  const GicpArgs a = *ap;
+  const uint32_t p = blockIdx.y, tile = blockIdx.x;
+  const PairState& ps = a.pairs[p];
+  if (ps.phase != kPhaseEval) return;
+  const SlotInfo& sa = a.slots[2 * p + 1];
+  if (tile * kIterTile >= sa.n_pts) return;
+  eval_tile<false>(a, ps, a.slots[2 * p], sa, p, tile, smem);
+}
+
+// one CTA per pair; the first control launch of a round serves pairs that just searched, the later ones pairs that were just evaluated
+__global__ void __launch_bounds__(256) gicp_ctrl_kernel(const GicpArgs* __restrict__ ap, int after_eval) {
+  __shared__ __align__(16) unsigned char smem[sizeof(CtrlShared)];
+  const GicpArgs a = *ap;
+  const uint32_t p = blockIdx.x;
+  if (a.pairs[p].phase != (after_eval ? kPhaseEval : kPhaseNeedNN)) return;
+  ctrl_step_body(a, p, after_eval, smem);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&a.ctl[0], (a.slots[2 * p + 1].n_pts + kIterTile - 1) / kIterTile);  // statistics: tiles of the pass just summed
+    atomicAdd(&a.ctl[1], 1u);
+    if (reinterpret_cast<const CtrlShared*>(smem)->ps.phase == kPhaseFitness) atomicSub(&a.flags[1], 1);  // the outer loop of this pair has ended
   }
+}
+
+__global__ void gicp_cond_kernel(const GicpArgs* __restrict__ ap, cudaGraphConditionalHandle cond) {
+  const GicpArgs a = *ap;
+  const uint32_t rounds = ++a.ctl[3];
+  const bool stuck = rounds >= a.max_launches;
+  if (stuck) atomicOr(&a.flags[0], kErrWatchdog);
+  cudaGraphSetConditional(cond, (a.flags[1] > 0 && !stuck) ? 1u : 0u);
+}
+
+__global__ void __launch_bounds__(kIterTile, 4) gicp_fitness_kernel(const GicpArgs* __restrict__ ap) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const GicpArgs a = *ap;
+  const uint32_t p = blockIdx.y, tile = blockIdx.x;
+  const PairState& ps = a.pairs[p];
+  if (ps.phase != kPhaseFitness) return;
+  const SlotInfo& sa = a.slots[2 * p + 1];
+  if (tile * kIterTile >= sa.n_pts) return;
+  fitness_tile<false>(a, ps, a.slots[2 * p], sa, p, tile, smem);
+}
+
+__global__ void __launch_bounds__(kIterTile) gicp_fitness_finish_kernel(const GicpArgs* __restrict__ ap) {
+  __shared__ __align__(16) unsigned char smem[size_t(kIterTile) * 16];
+  const GicpArgs a = *ap;
+  if (a.pairs[blockIdx.x].phase != kPhaseFitness) return;
+  fitness_finish(a, blockIdx.x, smem);
+  if (threadIdx.x == 0) atomicAdd(&a.ctl[0], (a.slots[2 * blockIdx.x + 1].n_pts + kIterTile - 1) / kIterTile);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -661,42 +764,63 @@ void check_arena(Workspace& ws, const int32_t* h_flags) {
 static int loop_grid(int device) {
   int sms = 0;
   S3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  static const int per_sm = [] { const char* e = getenv("S3D_LOOP_CTAS_PER_SM"); return e ? std::max(1, atoi(e)) : 4; }();  // A/B measurements
-  return std::max(1, sms) * per_sm;  // 4 resident CTAs per SM (64 registers, 49 KB shared memory)
+  static const int per_sm = [] { const char* e = getenv("S3D_LOOP_CTAS_PER_SM"); return e ? std::max(1, atoi(e)) : 2; }();  // A/B measurements
+  return std::max(1, sms) * per_sm;  // 2 resident CTAs per SM (128 registers, 46 KB shared memory)
 }
 
-// Throughput mode: WHILE (a pair is active) { gicp_loop_kernel(mode 1) } as a CUDA graph with a conditional node, built once per
-// workspace — the kernel reads everything from the GicpArgs block at a fixed device address — and replayed for every batch.
-static void build_loop_graph(Workspace& ws) {
-  S3D_CUDA(cudaGraphCreate(&ws.loop_graph, 0));
+// Throughput mode: WHILE (a pair iterates) { search, control, trial, control, trial, control, condition } as a CUDA graph with a
+// conditional node.  The kernels read everything from the GicpArgs block at a fixed device address; only the grid dimensions
+// depend on the batch, so executable graphs are cached per workspace by (tiles per pair, pairs).
+static cudaGraphExec_t loop_graph_for(Workspace& ws, uint32_t tiles_per_pair, uint32_t np) {
+  const uint64_t key = (uint64_t)tiles_per_pair << 32 | np;
+  auto it = ws.loop_graphs.find(key);
+  if (it != ws.loop_graphs.end()) return it->second;
+  cudaGraph_t graph;
+  S3D_CUDA(cudaGraphCreate(&graph, 0));
   cudaGraphConditionalHandle handle;
-  S3D_CUDA(cudaGraphConditionalHandleCreate(&handle, ws.loop_graph, 1, cudaGraphCondAssignDefault));  // every replay starts with "true"
+  S3D_CUDA(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));  // every replay starts with "true"
   cudaGraphNodeParams cp = {};
   cp.type = cudaGraphNodeTypeConditional;
   cp.conditional.handle = handle;
   cp.conditional.type = cudaGraphCondTypeWhile;
   cp.conditional.size = 1;
   cudaGraphNode_t cond_node;
-  S3D_CUDA(cudaGraphAddNode(&cond_node, ws.loop_graph, nullptr, 0, &cp));
+  S3D_CUDA(cudaGraphAddNode(&cond_node, graph, nullptr, 0, &cp));
   cudaGraph_t body = cp.conditional.phGraph_out[0];
   const GicpArgs* ap = ws.gicp_args.as<GicpArgs>();
-  int mode = 1;
-  void* kargs[] = {&ap, &handle, &mode};
-  cudaKernelNodeParams kp = {};
-  kp.func = reinterpret_cast<void*>(gicp_loop_kernel);
-  kp.gridDim = dim3(loop_grid(ws.device));
-  kp.blockDim = dim3(kIterTile);
-  kp.sharedMemBytes = (unsigned)kSmLoop;
-  kp.kernelParams = kargs;
-  cudaGraphNode_t kernel_node;
-  S3D_CUDA(cudaGraphAddKernelNode(&kernel_node, body, nullptr, 0, &kp));
-  S3D_CUDA(cudaGraphInstantiate(&ws.loop_exec, ws.loop_graph, 0));
+  int zero = 0, one = 1;
+  cudaGraphNode_t prev = nullptr;
+  auto add = [&](void* fn, dim3 grid, unsigned block, unsigned smem, void** args) {
+    cudaKernelNodeParams kp = {};
+    kp.func = fn; kp.gridDim = grid; kp.blockDim = dim3(block); kp.sharedMemBytes = smem; kp.kernelParams = args;
+    cudaGraphNode_t node;
+    S3D_CUDA(cudaGraphAddKernelNode(&node, body, prev ? &prev : nullptr, prev ? 1 : 0, &kp));
+    prev = node;
+  };
+  void* a1[] = {&ap};
+  void* a_ctrl0[] = {&ap, &zero};
+  void* a_ctrl1[] = {&ap, &one};
+  void* a_cond[] = {&ap, &handle};
+  const dim3 tiles(tiles_per_pair, np);
+  add(reinterpret_cast<void*>(gicp_search_kernel), tiles, kIterTile, (unsigned)kSmTile, a1);
+  add(reinterpret_cast<void*>(gicp_ctrl_kernel), dim3(np), 256, 0, a_ctrl0);
+  for (int e = 0; e < 2; ++e) {  // two trial/advance passes per round: most outer iterations finish within one round
+    add(reinterpret_cast<void*>(gicp_trial_kernel), tiles, kIterTile, 0, a1);
+    add(reinterpret_cast<void*>(gicp_ctrl_kernel), dim3(np), 256, 0, a_ctrl1);
+  }
+  add(reinterpret_cast<void*>(gicp_cond_kernel), dim3(1), 1, 0, a_cond);
+  cudaGraphExec_t exec;
+  S3D_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  ws.loop_graphs[key] = exec;
+  ws.loop_graph_defs.push_back(graph);
+  return exec;
 }
 
 // Runs the GICP loop + fitness for every pair of the batch (grids and covariances must be ready) and fills `out`
 // with the decisions of doICP (:74-77) and align() (:134-135, :167-172).  Latency mode (single calls): set-up kernel + ONE
-// persistent loop kernel.  Throughput mode (the chunks of a batch call, several streams per device): set-up kernel + a graph
-// replay whose WHILE node relaunches the loop kernel until no pair is active.
+// persistent loop kernel.  Throughput mode (the chunks of a batch call, several streams per device): set-up kernel + one graph
+// replay (per-pass kernels inside a WHILE node) + the fitness kernels.  With stage profiling on, the throughput kernels are
+// launched from the host instead, round by round with one poll each, so that every kernel can be bracketed by events.
 void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& params, const double* guesses, s3d_result* out) {
   const uint32_t np = ws.n_pairs;
   if (np == 0) return;
@@ -742,10 +866,12 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
     const char* e = getenv("S3D_WATCHDOG_MCYCLES");
     return (e ? (unsigned long long)atoll(e) : 6000ull) * 1000000ull;
   }();
-  // S3D_LOOP_MODE: 0 = by call type (default), 1 = always the persistent launch, 2 = always the graph replay;  S3D_LOOP_LINGER: polls
-  static const int loop_mode = [] { const char* e = getenv("S3D_LOOP_MODE"); return e ? atoi(e) : 0; }();
-  static const uint32_t linger = [] { const char* e = getenv("S3D_LOOP_LINGER"); return e ? (uint32_t)atoi(e) : 8u; }();
-  const bool throughput = loop_mode == 2 || (loop_mode == 0 && ws.blocking_sync);
+  // S3D_LOOP_MODE (measurement aid): 0 = by call type (default), 1 = always the persistent launch, 2 = always the per-pass kernels (graph replay),
+  // 3 = the per-pass kernels launched from the host with one poll per round (what stage profiling uses)
+  const char* loop_env = getenv("S3D_LOOP_MODE");
+  const int loop_mode = loop_env ? atoi(loop_env) : 0;
+  const uint32_t linger = 0;
+  const bool throughput = loop_mode == 2 || loop_mode == 3 || (loop_mode == 0 && ws.blocking_sync);
   GicpArgs* ha = reinterpret_cast<GicpArgs*>(ws.h_small.as<char>() + 256);
   *ha = GicpArgs{slots, pairs, ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), ws.corr.as<uint32_t>(), ws.mahal.as<double>(),
                  ws.moments.as<double>(), ws.eval_part.as<double>(), ws.fit_partial.as<double>(), flags, psched, ctl, tiles_per_pair, np,
@@ -758,15 +884,44 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
     gicp_prepare_kernel<<<grid, 256, 0, st>>>(slots, pairs, ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), psched, flags);
     ++ws.launches;
   }
-  {
+  const GicpArgs* dargs = ws.gicp_args.as<GicpArgs>();
+  if (!throughput) {
     StageTimer timer(ws, kStageIter);
-    S3D_CUDA(cudaFuncSetAttribute(gicp_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmLoop));
-    if (throughput) {
-      if (!ws.loop_exec) build_loop_graph(ws);
-      S3D_CUDA(cudaGraphLaunch(ws.loop_exec, st));
+    gicp_loop_kernel<<<loop_grid(ws.device), kIterTile, kSmLoop, st>>>(dargs);
+    ++ws.launches;
+    S3D_CUDA(cudaGetLastError());
+  } else {
+    if (!ws.profiling && loop_mode != 3) {
+      StageTimer timer(ws, kStageIter);
+      S3D_CUDA(cudaGraphLaunch(loop_graph_for(ws, tiles_per_pair, np), st));
     } else {
-      gicp_loop_kernel<<<loop_grid(ws.device), kIterTile, kSmLoop, st>>>(ws.gicp_args.as<GicpArgs>(), cudaGraphConditionalHandle{}, 0);
-      ++ws.launches;
+      // the same kernels from the host, one poll per round, so that each can be timed
+      for (uint32_t round = 0; round < (1u << 20); ++round) {
+        {
+          StageTimer timer(ws, kStageIter);
+          gicp_search_kernel<<<grid, kIterTile, kSmTile, st>>>(dargs);
+          ++ws.launches;
+        }
+        {
+          StageTimer timer(ws, kStageSolve);
+          gicp_ctrl_kernel<<<np, 256, 0, st>>>(dargs, 0);
+          for (int e = 0; e < 2; ++e) {
+            gicp_trial_kernel<<<grid, kIterTile, 0, st>>>(dargs);
+            gicp_ctrl_kernel<<<np, 256, 0, st>>>(dargs, 1);
+          }
+          ws.launches += 5;
+        }
+        S3D_CUDA(cudaMemcpyAsync(h_flags, flags, 16, cudaMemcpyDeviceToHost, st));
+        ws.sync();
+        ws.d2h += 16;
+        if (h_flags[1] <= 0) break;
+      }
+    }
+    {
+      StageTimer timer(ws, kStageFitness);
+      gicp_fitness_kernel<<<grid, kIterTile, kSmTile, st>>>(dargs);
+      gicp_fitness_finish_kernel<<<np, kIterTile, 0, st>>>(dargs);
+      ws.launches += 2;
     }
     S3D_CUDA(cudaGetLastError());
   }
@@ -778,8 +933,8 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   ws.sync();
   ws.d2h += sizeof(PairState) * np + sizeof(SlotInfo) * ws.n_slots + 32;
   ws.passes += h_ctl[0]; ws.ctrl_steps += h_ctl[1];
-  ws.launches += h_ctl[3];  // launches of the loop kernel inside the graph's WHILE node (throughput mode)
-  for (auto& sp : ws.spans) if (sp.stage == kStageIter && h_ctl[3]) sp.n_launch = h_ctl[3];
+  ws.launches += 7ull * h_ctl[3];  // rounds replayed by the graph's WHILE node (throughput mode): 7 kernels each
+  for (auto& sp : ws.spans) if (sp.stage == kStageIter && h_ctl[3]) sp.n_launch = 7 * h_ctl[3];
   ws.collect_spans();
   check_arena(ws, h_flags);
   if (h_flags[0] & kErrWatchdog) throw CudaError{"GICP loop kernel: watchdog expired (scheduler fault)"};

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -97,10 +98,10 @@ struct GicpArgs {
   const float4* moved; uint32_t* prev_nn; float* sec_lb; uint32_t* corr; double* mahal; double* moments; double* eval_part; double* fit_partial;
   int32_t* flags;          // [0] error bits, [1] active pairs
   PairSched* psched;
-  uint32_t* ctl;           // [0] tiles processed, [1] control steps (statistics); [2] CTAs that have left the launch, [3] launches (throughput mode)
+  uint32_t* ctl;           // [0] tiles processed, [1] control steps (statistics); [3] rounds (throughput mode)
   uint32_t tiles_per_pair, n_pairs;
-  uint32_t linger;         // throughput mode: polls (~0.4 us each) an idle CTA waits for a pass to be published before it leaves
-  uint32_t max_launches;   // throughput mode: launches after which the loop gives up (scheduler fault)
+  uint32_t reserved;
+  uint32_t max_launches;   // throughput mode: rounds after which the loop gives up (scheduler fault)
   unsigned long long watchdog_cycles;
 };
 
@@ -146,10 +147,11 @@ struct Workspace {
   DevBuf ndt_pairs, ndt_leaves, ndt_hash, ndt_part;  // NDT: NdtPair[n_pairs], NdtLeaf[], uint2 hash arena, double[tiles * 44]
   DevBuf gicp_args, gicp_sched;               // GicpArgs; 16 counter words + PairSched[n_pairs] of the loop kernel
   uint64_t passes = 0, ctrl_steps = 0;        // tiles processed / control steps run by the loop kernel (statistics)
-  cudaGraph_t loop_graph = nullptr;           // throughput mode: WHILE (a pair is active) { gicp_loop_kernel }, built on first use
-  cudaGraphExec_t loop_exec = nullptr;
+  std::map<uint64_t, cudaGraphExec_t> loop_graphs;  // throughput mode: WHILE (a pair iterates) { per-pass kernels }, by (tiles per pair, pairs)
+  std::vector<cudaGraph_t> loop_graph_defs;
   DevBuf flags;                               // int32[16]: [0] error bits, [1] active pairs, [2] hash entries used, [3] entries needed, [8] long voxel runs, [9] kept points
   PinnedBuf h_slots, h_pairs, h_small, h_tiles;  // pinned host mirrors
+  PinnedBuf h_bounce;                            // pinned landing zone for pageable host clouds (setup_batch)
   uint64_t launches = 0, h2d = 0, d2h = 0;
   // optional stage timing (s3d_set_profiling)
   bool profiling = false;
@@ -191,7 +193,8 @@ void run_grid(Workspace& ws, float leaf_hint);      // NN grid on the working cl
 void run_knn_covariances(Workspace& ws, int k, uint32_t* knn_index, float* knn_dist2);  // outputs optional (device, slot-concatenated)
 void run_expand_cov(Workspace& ws, double* cov_out);  // full 3x3 covariances per original index (stage API)
 void run_nn_stage(Workspace& ws, uint32_t ref_slot, uint32_t qry_slot, const float* T16_dev, uint32_t* nn_index, float* nn_dist2);
-uint32_t run_accumulate(Workspace& ws, const std::vector<const float*>& clouds, const std::vector<uint64_t>& sizes, const double* poses);  // -> ws.accu
+uint32_t run_accumulate(Workspace& ws, const std::vector<const float*>& clouds, const std::vector<uint64_t>& sizes, const double* poses,
+                        const double* second = nullptr);  // -> ws.accu; second: one more 4x4 applied to every (float-rounded) point
 uint32_t run_radius_filter(Workspace& ws, const float4* dev_in, uint32_t n, double radius, unsigned min_pts, float4* dev_out);
 void check_arena(Workspace& ws, const int32_t* h_flags);  // throws ArenaOverflow when the grid build flagged it (h_flags: synchronised copy)
 void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& params, const double* guesses, s3d_result* out);

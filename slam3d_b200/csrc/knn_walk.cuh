@@ -127,7 +127,7 @@ __device__ __forceinline__ int thread_walk(const GridView& g, const float4 qv, f
       const float c0 = fmaxf(az * hl - g.margin, 0.f), c1 = fmaxf((1.f - az) * hl - g.margin, 0.f);
       glx = a0 * a0; gux = a1 * a1; gly = b0 * b0; guy = b1 * b1; glz = c0 * c0; guz = c1 * c1;
     }
-#pragma unroll 1
+S3D_CELL_LOOP_PRAGMA
     for (int i = 0; i < 27; ++i) {
       const int c = cell_order(i);  // own cell, faces, edges, corners
       const int dx = c % 3, dy = (c / 3) % 3, dz = c / 9;

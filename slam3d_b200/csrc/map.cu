@@ -13,8 +13,11 @@ namespace s3d {
 
 // pcl::transformPointCloud(cloud, out, Matrix4d): double se3 form  x*c0 + (y*c1 + (z*c2 + c3)), cast to float.
 // poses: n_slots x 16 doubles (column-major); out_off: first output index of every slot (clouds are concatenated unpadded).
+// second: optional 16 doubles applied to the (float-rounded) result of the first transform — createCombinedMeasurement's
+// transformPointCloud(accumulated, shifted, pose.inverse()) fused into the same pass, with both float roundings kept.
 __global__ void __launch_bounds__(kSortThreads) transform_concat_kernel(const SlotInfo* __restrict__ slots, TileMap tm, const double* __restrict__ poses,
-                                                                        const uint32_t* __restrict__ out_off, float4* __restrict__ out) {
+                                                                        const uint32_t* __restrict__ out_off, float4* __restrict__ out,
+                                                                        const double* __restrict__ second) {
   const uint32_t t = blockIdx.x;
   const uint32_t slot = tm.tile_slot[t], first = tm.tile_first[t];
   const SlotInfo& si = slots[slot];
@@ -31,6 +34,12 @@ __global__ void __launch_bounds__(kSortThreads) transform_concat_kernel(const Sl
       o.y = (float)__dadd_rn(__dmul_rn(x, t1), __dadd_rn(__dmul_rn(y, t5), __dadd_rn(__dmul_rn(z, t9), t13)));
       o.z = (float)__dadd_rn(__dmul_rn(x, t2), __dadd_rn(__dmul_rn(y, t6), __dadd_rn(__dmul_rn(z, t10), t14)));
       o.w = 1.0f;
+      if (second) {
+        const double u = o.x, v = o.y, w = o.z;
+        o.x = (float)__dadd_rn(__dmul_rn(u, second[0]), __dadd_rn(__dmul_rn(v, second[4]), __dadd_rn(__dmul_rn(w, second[8]), second[12])));
+        o.y = (float)__dadd_rn(__dmul_rn(u, second[1]), __dadd_rn(__dmul_rn(v, second[5]), __dadd_rn(__dmul_rn(w, second[9]), second[13])));
+        o.z = (float)__dadd_rn(__dmul_rn(u, second[2]), __dadd_rn(__dmul_rn(v, second[6]), __dadd_rn(__dmul_rn(w, second[10]), second[14])));
+      }
       out[out_off[slot] + e] = o;
     }
   }
@@ -125,7 +134,8 @@ __global__ void __launch_bounds__(kSortThreads) keep_scatter_kernel(const SlotIn
 }
 
 // clouds -> one concatenated, transformed cloud in ws.accu (device); returns the number of points
-uint32_t run_accumulate(Workspace& ws, const std::vector<const float*>& clouds, const std::vector<uint64_t>& sizes, const double* poses) {
+uint32_t run_accumulate(Workspace& ws, const std::vector<const float*>& clouds, const std::vector<uint64_t>& sizes, const double* poses,
+                        const double* second) {
   const uint32_t ns = (uint32_t)clouds.size();
   setup_batch(ws, clouds, sizes, 0);
   std::vector<uint32_t> off(ns);
@@ -134,13 +144,15 @@ uint32_t run_accumulate(Workspace& ws, const std::vector<const float*>& clouds, 
   if (total >= (1ull << 31)) throw CudaError{"map too large: more than 2^31 points"};
   ws.accu.reserve(16 * std::max<uint64_t>(total, 4));
   if (total == 0 || ws.n_tiles == 0) return 0;
-  ws.map_aux.reserve(128 * (size_t)ns + 4 * (size_t)ns);
+  ws.map_aux.reserve(128 * (size_t)(ns + 1) + 4 * (size_t)ns);
   double* d_pose = ws.map_aux.as<double>();
-  uint32_t* d_off = reinterpret_cast<uint32_t*>(d_pose + 16 * (size_t)ns);
+  double* d_second = d_pose + 16 * (size_t)ns;
+  uint32_t* d_off = reinterpret_cast<uint32_t*>(d_second + 16);
   S3D_CUDA(cudaMemcpyAsync(d_pose, poses, 128 * (size_t)ns, cudaMemcpyHostToDevice, ws.stream));
+  if (second) S3D_CUDA(cudaMemcpyAsync(d_second, second, 128, cudaMemcpyHostToDevice, ws.stream));
   S3D_CUDA(cudaMemcpyAsync(d_off, off.data(), 4 * (size_t)ns, cudaMemcpyHostToDevice, ws.stream));
   TileMap tm{ws.tile_slot.as<uint32_t>(), ws.tile_first.as<uint32_t>(), ws.n_tiles};
-  transform_concat_kernel<<<ws.n_tiles, kSortThreads, 0, ws.stream>>>(ws.slots.as<SlotInfo>(), tm, d_pose, d_off, ws.accu.as<float4>());
+  transform_concat_kernel<<<ws.n_tiles, kSortThreads, 0, ws.stream>>>(ws.slots.as<SlotInfo>(), tm, d_pose, d_off, ws.accu.as<float4>(), second ? d_second : nullptr);
   ++ws.launches;
   S3D_CUDA(cudaGetLastError());
   ws.sync();  // `off` and the pageable `poses` must outlive the copies

@@ -69,6 +69,14 @@ __device__ __forceinline__ int cell_order(int i) {
 // its distance (gap along each axis, shrunk by the float slack) already exceeds the best candidate — with a warm start
 // that leaves 1-4 of the 27 cells.  (ax,ay,az) = position of the query inside its cell in [0,1); prune = false at the
 // top level, where the block is anchored at cell 0 instead of the query.
+// the 27-slot loop of the walks: rolled by default (measured in round 2: see profiles/r02_summary.md); -DS3D_CELL_UNROLL=27 lets
+// the compiler fold the slot decoding and the per-axis selects of every slot into constants
+#ifndef S3D_CELL_UNROLL
+#define S3D_CELL_UNROLL 1
+#endif
+#define S3D_PRAGMA_(x) _Pragma(#x)
+#define S3D_PRAGMA(x) S3D_PRAGMA_(x)
+#define S3D_CELL_LOOP_PRAGMA S3D_PRAGMA(unroll S3D_CELL_UNROLL)
 constexpr int kNNGatherCap = 8;  // noted cells per thread in the gathering variant (8 bytes each)
 
 // host-side work statistics (tests/hostsearch.cpp defines it to record which cell slot scanned how many points); nothing on the device
@@ -113,7 +121,7 @@ __device__ __forceinline__ void scan_block(const GridView& g, int L, int cx, int
   }
   uint32_t found = 0;
   int n_list = 0;
-#pragma unroll 1
+S3D_CELL_LOOP_PRAGMA
   for (int i = 0; i < 27; ++i) {
     const int c = cell_order(i);
     const int dx = c % 3, dy = (c / 3) % 3, dz = c / 9;

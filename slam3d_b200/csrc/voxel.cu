@@ -70,15 +70,15 @@ void Workspace::destroy() {
   if (sync_event) cudaEventDestroy(sync_event);
   if (input_event) cudaEventDestroy(input_event);
   sync_event = input_event = nullptr;
-  if (loop_exec) cudaGraphExecDestroy(loop_exec);
-  if (loop_graph) cudaGraphDestroy(loop_graph);
-  loop_exec = nullptr; loop_graph = nullptr;
+  for (auto& g : loop_graphs) cudaGraphExecDestroy(g.second);
+  for (cudaGraph_t g : loop_graph_defs) cudaGraphDestroy(g);
+  loop_graphs.clear(); loop_graph_defs.clear();
 
   DevBuf* bufs[] = {&slots, &pairs, &raw_stage, &work, &gpts, &keys0, &keys1, &vals0, &vals1, &hist, &sort_totals, &long_runs, &tile_slot, &tile_first,
                     &slot_tile_begin, &tile_heads, &hash, &normals, &moved, &prev_nn, &sec_lb, &moments, &eval_part, &corr, &mahal, &iter_tile_pair, &iter_tile_first,
                     &fit_partial, &flags, &accu, &accu2, &map_aux, &ndt_pairs, &ndt_leaves, &ndt_hash, &ndt_part, &gicp_args, &gicp_sched};
   for (DevBuf* b : bufs) b->release();
-  h_slots.release(); h_pairs.release(); h_small.release(); h_tiles.release();
+  h_slots.release(); h_pairs.release(); h_small.release(); h_tiles.release(); h_bounce.release();
   if (stream) cudaStreamDestroy(stream);
   stream = nullptr;
 }
@@ -124,17 +124,31 @@ void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const s
   ws.h_tiles.reserve(4 * (2 * size_t(n_tiles) + ns + 1));
 
   // classify input pointers; host memory (pinned or pageable) and misaligned device memory go through raw_stage
-  bool need_stage = false;
-  std::vector<int> on_device(ns, 0);
+  bool need_stage = false, need_bounce = false;
+  std::vector<int> on_device(ns, 0), pageable(ns, 0);
   for (uint32_t s = 0; s < ns; ++s) {
     if (sizes[s] == 0) continue;
     cudaPointerAttributes at{};
     cudaError_t e = cudaPointerGetAttributes(&at, clouds[s]);
     if (e != cudaSuccess) { cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; }
     on_device[s] = (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) && (reinterpret_cast<uintptr_t>(clouds[s]) & 15) == 0;
+    pageable[s] = at.type == cudaMemoryTypeUnregistered;
     if (!on_device[s]) need_stage = true;
+    if (pageable[s]) need_bounce = true;
   }
   if (need_stage) ws.raw_stage.reserve(16 * tot);
+  // Pageable host clouds (a std::vector, the points of a pcl::PointCloud): cudaMemcpyAsync from pageable memory is staged by the
+  // driver through one small pinned buffer and blocks the calling thread (~10 GB/s, measured: e2e 1800 against 2430
+  // registrations/s from pinned memory).  The chunk's host thread copies them into the workspace's own pinned buffer instead —
+  // the host threads of the other chunks do the same in parallel, before they queue for the upload turn — and the DMA runs from there.
+  static const bool bounce_enabled = [] { const char* e = getenv("S3D_PINNED_BOUNCE"); return !e || atoi(e) != 0; }();  // 0: A/B measurements
+  if (need_bounce && bounce_enabled) {
+    ws.h_bounce.reserve(16 * tot);
+    for (uint32_t s = 0; s < ns; ++s)
+      if (pageable[s]) memcpy(ws.h_bounce.as<char>() + 16 * size_t(ws.h_off[s]), clouds[s], 16 * sizes[s]);
+  } else {
+    need_bounce = false;
+  }
 
   ws.order_after_input();
   std::unique_lock<std::mutex> gate;  // uploads of concurrent chunks take turns (api.cu, t_gate_uploads)
@@ -156,7 +170,8 @@ void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const s
     else if (on_device[s]) si.raw = reinterpret_cast<const float4*>(clouds[s]);
     else {
       si.raw = ws.raw_stage.as<float4>() + si.off;
-      S3D_CUDA(cudaMemcpyAsync(ws.raw_stage.as<float4>() + si.off, clouds[s], 16 * sizes[s], cudaMemcpyDefault, ws.stream));
+      const void* from = (need_bounce && pageable[s]) ? static_cast<const void*>(ws.h_bounce.as<char>() + 16 * size_t(si.off)) : static_cast<const void*>(clouds[s]);
+      S3D_CUDA(cudaMemcpyAsync(ws.raw_stage.as<float4>() + si.off, from, 16 * sizes[s], cudaMemcpyDefault, ws.stream));
       ws.h2d += 16 * sizes[s];
     }
     h_begin[s] = t;

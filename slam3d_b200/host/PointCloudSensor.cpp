@@ -163,6 +163,28 @@ PointCloud::Ptr PointCloudSensor::getAccumulatedCloud(const PosedMeasurements& v
   return accu;
 }
 
+// :258-266  one device pass: transform(cloud_i, pose_i) appended in list order, then transformPointCloud(pose.inverse())
+Measurement::Ptr PointCloudSensor::createCombinedMeasurement(const PosedMeasurements& vertices, Transform pose) const {
+  std::vector<s3d_cloud> clouds(vertices.size());
+  std::vector<double> poses(16 * vertices.size());
+  size_t total = 0;
+  for (size_t i = 0; i < vertices.size(); ++i) {
+    clouds[i] = asCloud(vertices[i].first->getPointCloud());
+    const Transform p = vertices[i].second * vertices[i].first->getSensorPose();  // :248
+    for (int j = 0; j < 16; ++j) poses[16 * i + j] = p.m[j];
+    total += clouds[i].n;
+  }
+  PointCloud::Ptr shifted(new PointCloud);
+  shifted->points.resize(total);
+  uint64_t n = 0;
+  if (s3d_create_combined_measurement(defaultContext(), clouds.data(), poses.data(), (int)vertices.size(), pose.data(),
+                                      total ? &shifted->points[0].x : nullptr, &n) != S3D_OK)
+    throw std::runtime_error(s3d_last_error());
+  shifted->points.resize(n);
+  if (mLogger) mLogger->message(DEBUG, "Patch pointcloud has " + std::to_string(n) + " points.");
+  return Measurement::Ptr(new PointCloudMeasurement(shifted, "AccumulatedPointcloud", mName, Transform::Identity()));
+}
+
 // :301-318  one device pass: accumulate -> removeOutliers -> downsample
 PointCloud::Ptr PointCloudSensor::buildMap(const PosedMeasurements& vertices) const {
   PointCloud::Ptr map(new PointCloud);
@@ -199,6 +221,58 @@ Constraint::Ptr PointCloudSensor::createConstraint(const Measurement::Ptr& sourc
   Transform tf = source->getSensorPose() * icp_result * target->getInverseSensorPose();  // :295
   Covariance<6> covariance = Covariance<6>::Identity() * mCovarianceScale;  // :296
   return Constraint::Ptr(new SE3Constraint(mName, tf, covariance.inverseDiagonal()));
+}
+
+// what align() throws for a per-pair status of a batch call (same texts as the single call, PointCloudSensor.cpp:74-77, :134-135, :167-172)
+static void failureOf(int st, const s3d_result& r, const RegistrationParameters& cfg, int& kind, std::string& msg) {
+  switch (st) {
+    case S3D_TOO_FEW_POINTS: kind = 1; msg = "Too few points after filtering, you may have to decrease 'point_cloud_density'."; break;
+    case S3D_NOT_CONVERGED:
+      kind = 1;
+      msg = std::string(cfg.registration_algorithm == NDT || cfg.registration_algorithm == NDT_OMP ? "NDT" : "ICP") + " failed with Fitness-Score " +
+            std::to_string(r.fitness) + " > " + std::to_string(cfg.max_fitness_score);
+      break;
+    case S3D_TOO_FAR_FROM_GUESS: kind = 1; msg = "ICP result is to far away from guess"; break;
+    case S3D_UNKNOWN_ALGORITHM: kind = 3; msg = "Unknown registration algorithm specified."; break;
+    default: kind = 3; msg = s3d_last_error(); break;
+  }
+}
+
+std::vector<PointCloudSensor::ConstraintResult> PointCloudSensor::createConstraints(const std::vector<ConstraintRequest>& requests, bool loop) {
+  std::vector<ConstraintResult> out(requests.size());
+  std::vector<size_t> idx;
+  std::vector<s3d_cloud> src, tgt;
+  std::vector<double> guesses;
+  for (size_t i = 0; i < requests.size(); ++i) {
+    PointCloudMeasurement::Ptr sc = std::dynamic_pointer_cast<PointCloudMeasurement>(requests[i].source);
+    PointCloudMeasurement::Ptr tc = std::dynamic_pointer_cast<PointCloudMeasurement>(requests[i].target);
+    if (!sc || !tc) {  // :279-283
+      if (mLogger) mLogger->message(ERROR, "Measurement given to createConstraint() is not a PointCloud!");
+      out[i].error = 2; out[i].message = BadMeasurementType().what();
+      continue;
+    }
+    const Transform guess = requests[i].source->getInverseSensorPose() * requests[i].odometry * requests[i].target->getSensorPose();  // :274
+    idx.push_back(i); src.push_back(asCloud(sc->getPointCloud())); tgt.push_back(asCloud(tc->getPointCloud()));
+    guesses.insert(guesses.end(), guess.m.begin(), guess.m.end());
+  }
+  const int n = (int)idx.size();
+  if (n == 0) return out;
+  std::vector<s3d_result> coarse(n), fine(n);
+  const s3d_registration_parameters cc = mCoarseConfiguration.toC(), cf = mFineConfiguration.toC();
+  const int st = loop ? s3d_gicp_align_loop_batch(defaultContext(), src.data(), tgt.data(), guesses.data(), &cc, &cf, n, coarse.data(), fine.data())  // :286-292
+                      : s3d_gicp_align_batch(defaultContext(), src.data(), tgt.data(), guesses.data(), &cf, n, fine.data());                           // :292
+  if (st != S3D_OK) throw std::runtime_error(s3d_last_error());
+  for (int k = 0; k < n; ++k) {
+    ConstraintResult& r = out[idx[k]];
+    if (loop && coarse[k].status != S3D_OK) { failureOf(coarse[k].status, coarse[k], mCoarseConfiguration, r.error, r.message); continue; }  // the coarse align threw
+    if (fine[k].status != S3D_OK) { failureOf(fine[k].status, fine[k], mFineConfiguration, r.error, r.message); continue; }
+    Transform icp_result;
+    for (int j = 0; j < 16; ++j) icp_result.m[j] = fine[k].T[j];
+    const Transform tf = requests[idx[k]].source->getSensorPose() * icp_result * requests[idx[k]].target->getInverseSensorPose();  // :295
+    Covariance<6> covariance = Covariance<6>::Identity() * mCovarianceScale;                                                      // :296
+    r.constraint.reset(new SE3Constraint(mName, tf, covariance.inverseDiagonal()));
+  }
+  return out;
 }
 
 // :320-340

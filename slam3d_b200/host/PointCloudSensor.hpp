@@ -6,10 +6,11 @@
 //   setRegistrationParameters(param, coarse)           :320-340
 //   setScanResolution / downsample / downsampleScan    :342-346, :190-209
 //   transform                                          :228-233
-// plus the free function align() (:119-174).  Everything that needs the graph (createCombinedMeasurement,
-// getAccumulatedCloud, buildMap, loadPLY) or other PCL modules (removeOutliers, fillGroundPlane) is outside the
-// hot path and not declared here.  In a real slam3d build the same bodies replace
-// PointCloudSensor.cpp's downsample()/align() — see INTEGRATION.md.
+//   removeOutliers / getAccumulatedCloud / createCombinedMeasurement / buildMap   :211-266, :301-318 (vertex lists passed explicitly)
+// plus the free function align() (:119-174) and createConstraints(), a batch form of createConstraint for callers that have
+// several candidates at hand (ScanSensor::linkToNeighbors, core/ScanSensor.cpp:179-201).  loadPLY, fillGroundPlane and the
+// serializers do no arithmetic on this path and stay with the reference (shim/PointCloudSensor.cpp passes them through).
+// In a real slam3d build the same bodies replace PointCloudSensor.cpp's downsample()/align() — see INTEGRATION.md.
 #pragma once
 
 #include <mutex>
@@ -56,6 +57,19 @@ class PointCloudSensor {
   typedef std::vector<std::pair<PointCloudMeasurement::Ptr, Transform> > PosedMeasurements;
   PointCloud::Ptr getAccumulatedCloud(const PosedMeasurements& vertices) const;
   PointCloud::Ptr buildMap(const PosedMeasurements& vertices) const;
+  // :258-266 — the patch a loop closure is matched with: accumulated cloud re-expressed in the frame `pose`, sensor pose identity
+  Measurement::Ptr createCombinedMeasurement(const PosedMeasurements& vertices, Transform pose) const;
+
+  // Batch form of createConstraint (extension): request i gives the same constraint — or fails with the same exception type and
+  // message — as createConstraint(source_i, target_i, odometry_i, loop), but all registrations run as ONE device batch
+  // (s3d_gicp_align_batch / s3d_gicp_align_loop_batch), which is what the GPU path is fastest at.
+  struct ConstraintRequest { Measurement::Ptr source, target; Transform odometry; };
+  struct ConstraintResult {
+    Constraint::Ptr constraint;  // null when the request failed
+    int error = 0;               // 0 none, 1 NoMatch, 2 BadMeasurementType, 3 std::runtime_error
+    std::string message;
+  };
+  std::vector<ConstraintResult> createConstraints(const std::vector<ConstraintRequest>& requests, bool loop);
 
  protected:
   std::string mName;

@@ -124,16 +124,18 @@ int s3dhost_run_odometry(void* s, const float* const* scans, const uint64_t* siz
 // BASELINE configs[4] (trajectory): n scans through addMeasurement(m, odom) + linkLastToNeighbors() after every new vertex.
 // edges_out: per recorded edge {source, target, loop} as 3 ints followed by nothing; T_out: 16 doubles per edge (relative pose);
 // poses_out: n x 16 doubles (corrected poses).  Returns the number of edges (<= max_edges) or -1.
-int s3dhost_run_trajectory(void* s, const float* const* scans, const uint64_t* sizes, int n, const double* odoms, double neighbor_radius,
-                           int max_links, int min_loop_length, int max_edges, int* edges_out, double* T_out, double* poses_out, int* n_warnings) {
+static int run_trajectory(void* s, const float* const* scans, const uint64_t* sizes, int n, const double* odoms, double neighbor_radius,
+                          int max_links, int min_loop_length, int patch_range, int batched, int max_edges, int* edges_out, double* T_out,
+                          double* poses_out, int* n_warnings) {
   PointCloudSensor* sensor = static_cast<PointCloudSensor*>(s);
   try {
     MiniHost host(sensor);
     host.setNeighborRadius((float)neighbor_radius, max_links);
     host.setMinLoopLength((unsigned)min_loop_length);
+    host.setPatchBuildingRange((unsigned)patch_range);
     for (int i = 0; i < n; ++i) {
       Measurement::Ptr m(new PointCloudMeasurement(makeCloud(scans[i], sizes[i]), "robot", sensor->getName(), Transform()));
-      if (host.addMeasurement(m, makeTransform(odoms + 16 * i))) host.linkLastToNeighbors();
+      if (host.addMeasurement(m, makeTransform(odoms + 16 * i))) host.linkLastToNeighbors(batched != 0);
     }
     const int ne = (int)std::min<size_t>(host.edges.size(), (size_t)max_edges);
     for (int e = 0; e < ne; ++e) {
@@ -148,6 +150,59 @@ int s3dhost_run_trajectory(void* s, const float* const* scans, const uint64_t* s
     g_msg = e.what();
     return -1;
   }
+}
+
+int s3dhost_run_trajectory(void* s, const float* const* scans, const uint64_t* sizes, int n, const double* odoms, double neighbor_radius,
+                           int max_links, int min_loop_length, int max_edges, int* edges_out, double* T_out, double* poses_out, int* n_warnings) {
+  return run_trajectory(s, scans, sizes, n, odoms, neighbor_radius, max_links, min_loop_length, 0, 0, max_edges, edges_out, T_out, poses_out, n_warnings);
+}
+
+// the same with Sensor::mPatchBuildingRange = patch_range (loop closures match patches of scans, ScanSensor.cpp:215-270) and,
+// when batched != 0, all candidates of a vertex matched in one device batch (PointCloudSensor::createConstraints)
+int s3dhost_run_trajectory2(void* s, const float* const* scans, const uint64_t* sizes, int n, const double* odoms, double neighbor_radius,
+                            int max_links, int min_loop_length, int patch_range, int batched, int max_edges, int* edges_out, double* T_out,
+                            double* poses_out, int* n_warnings) {
+  return run_trajectory(s, scans, sizes, n, odoms, neighbor_radius, max_links, min_loop_length, patch_range, batched, max_edges, edges_out, T_out, poses_out, n_warnings);
+}
+
+// ScanSensor::addMeasurement(m) without odometry (core/ScanSensor.cpp:49-79): the guess is chained from the previous result and
+// a scan becomes a vertex only after min_translation / min_rotation.  T_out: 16 doubles per recorded edge.  Returns the edges or -1.
+int s3dhost_run_no_odometry(void* s, const float* const* scans, const uint64_t* sizes, int n, double min_translation, double min_rotation,
+                            int* added_out, double* T_out, int* n_warnings) {
+  PointCloudSensor* sensor = static_cast<PointCloudSensor*>(s);
+  try {
+    MiniHost host(sensor);
+    host.setMinPoseDistance((float)min_translation, (float)min_rotation);
+    for (int i = 0; i < n; ++i) {
+      Measurement::Ptr m(new PointCloudMeasurement(makeCloud(scans[i], sizes[i]), "robot", sensor->getName(), Transform()));
+      const bool added = host.addMeasurement(m);
+      if (added_out) added_out[i] = added ? 1 : 0;
+    }
+    for (size_t e = 0; e < host.edges.size(); ++e) for (int i = 0; i < 16; ++i) T_out[16 * e + i] = host.edges[e].relative.m[i];
+    if (n_warnings) *n_warnings = (int)host.warnings.size();
+    g_msg = host.warnings.empty() ? "" : host.warnings.back();
+    return (int)host.edges.size();
+  } catch (std::exception& e) {
+    g_msg = e.what();
+    return -1;
+  }
+}
+
+// createCombinedMeasurement on n posed scans (sensor pose = identity): out must hold the sum of the sizes. Returns the size or -1.
+int64_t s3dhost_combined_measurement(void* s, const float* const* scans, const uint64_t* sizes, int n, const double* poses, const double* patch_pose, float* out) {
+  int64_t m = -1;
+  wrap([&] {
+    PointCloudSensor* sensor = static_cast<PointCloudSensor*>(s);
+    PointCloudSensor::PosedMeasurements v;
+    for (int i = 0; i < n; ++i)
+      v.emplace_back(PointCloudMeasurement::Ptr(new PointCloudMeasurement(makeCloud(scans[i], sizes[i]), "robot", sensor->getName(), Transform())),
+                     makeTransform(poses + 16 * i));
+    Measurement::Ptr c = sensor->createCombinedMeasurement(v, makeTransform(patch_pose));
+    PointCloudMeasurement::Ptr pc = std::dynamic_pointer_cast<PointCloudMeasurement>(c);
+    m = (int64_t)pc->getPointCloud()->size();
+    if (m) std::memcpy(out, &pc->getPointCloud()->points[0].x, 16 * m);
+  });
+  return m;
 }
 
 }  // extern "C"

@@ -229,3 +229,102 @@ def test_minihost_trajectory_links_to_neighbors(host):
     dt, _ = pose_delta(np.linalg.inv(truth[0]) @ truth[-1], P[-1])              # chained corrected poses follow the path
     assert dt < 0.2
     host.s3dhost_sensor_destroy(sensor)
+
+
+def _figure_eight(lap=20, radius=0.8, extra=4, seed=3):
+    from slam3d_b200 import synth
+    import slam3d_b200
+    step = 4 * np.pi * radius / lap
+    n = lap + extra
+    truth = synth.figure_eight_poses(n, radius, step)
+    scene = synth.Scene(seed)
+    rng = np.random.default_rng(seed)
+    scans = [slam3d_b200.as_xyzw(synth.scan(scene, p, rng, azimuth_stride=8)) for p in truth]
+    odoms = [np.linalg.inv(truth[0]) @ p for p in truth]
+    return n, truth, scans, odoms
+
+
+def _run_trajectory2(host, sensor, scans, odoms, n, patch_range, batched, max_links=1, radius=1.0):
+    host.s3dhost_run_trajectory2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    ptrs = (C.c_void_p * n)(*[s.ctypes.data for s in scans])
+    sizes = (C.c_uint64 * n)(*[s.shape[0] for s in scans])
+    od = np.ascontiguousarray(np.stack([o.T for o in odoms]))
+    edges = np.zeros((6 * n, 3), np.int32); T = np.zeros((6 * n, 16)); poses = np.zeros((n, 16)); nw = C.c_int(0)
+    ne = host.s3dhost_run_trajectory2(sensor, ptrs, sizes, n, od.ctypes.data, radius, max_links, 10, patch_range, int(batched), 6 * n,
+                                      edges.ctypes.data, T.ctypes.data, poses.ctypes.data, C.byref(nw))
+    assert ne >= n - 1, host.s3dhost_last_message()
+    return edges[:ne].copy(), T[:ne].reshape(ne, 4, 4).transpose(0, 2, 1).copy(), nw.value
+
+
+def test_minihost_patch_range_two_and_batched_links(host):
+    """BASELINE configs[4] with Sensor::mPatchBuildingRange = 2: a loop closure matches PATCHES — the scans within two hops of
+    each vertex, accumulated by createCombinedMeasurement (ScanSensor.cpp:215-270, PointCloudSensor.cpp:258-266) — and the
+    candidates of a vertex go through PointCloudSensor::createConstraints as ONE device batch.  The batched run must record
+    the same edges as the one-at-a-time run, bit for bit."""
+    n, truth, scans, odoms = _figure_eight()
+    sensor = host.s3dhost_sensor_create(b"velodyne")
+    fine = RegistrationParameters.defaults(point_cloud_density=0.2)
+    coarse = RegistrationParameters.defaults(point_cloud_density=0.5, max_correspondence_distance=5.0)
+    host.s3dhost_sensor_set_params(sensor, C.byref(fine), 0)
+    host.s3dhost_sensor_set_params(sensor, C.byref(coarse), 1)
+    e_seq, T_seq, w_seq = _run_trajectory2(host, sensor, scans, odoms, n, patch_range=2, batched=False)
+    e_bat, T_bat, w_bat = _run_trajectory2(host, sensor, scans, odoms, n, patch_range=2, batched=True)
+    assert np.array_equal(e_seq, e_bat) and np.array_equal(T_seq, T_bat) and w_seq == w_bat
+    loops = e_seq[e_seq[:, 2] == 1]
+    assert len(loops) >= 2
+    assert all(abs(int(t) - int(s)) >= 10 for s, t, _ in loops)   # mMinLoopLength; also > 2 * mPatchBuildingRange (:196)
+    for (s, t, _), rel in zip(e_seq, T_seq):
+        dt, dr = pose_delta(np.linalg.inv(truth[s]) @ truth[t], rel)
+        assert dt < 0.05 and dr < 0.01, (s, t, dt, dr)
+    # several links per vertex in one batch: still the edges of the sequential policy
+    e_seq3, T_seq3, _ = _run_trajectory2(host, sensor, scans, odoms, n, patch_range=0, batched=False, max_links=3, radius=1.7)
+    e_bat3, T_bat3, _ = _run_trajectory2(host, sensor, scans, odoms, n, patch_range=0, batched=True, max_links=3, radius=1.7)
+    assert np.array_equal(e_seq3, e_bat3) and np.array_equal(T_seq3, T_bat3)
+    assert len(e_seq3[e_seq3[:, 2] == 1]) >= len(loops)
+    host.s3dhost_sensor_destroy(sensor)
+
+
+def test_host_combined_measurement(host, oracle_mod, kitti):
+    import slam3d_b200
+    host.s3dhost_combined_measurement.restype = C.c_int64
+    host.s3dhost_combined_measurement.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    sensor = host.s3dhost_sensor_create(b"velodyne")
+    scans = [slam3d_b200.as_xyzw(k) for k in kitti[:3]]
+    ptrs = (C.c_void_p * 3)(*[s.ctypes.data for s in scans])
+    sizes = (C.c_uint64 * 3)(*[s.shape[0] for s in scans])
+    poses = []
+    for i in range(3):
+        P = rot_z(0.01 * i); P[0, 3] = 0.69 * i
+        poses.append(P)
+    patch = poses[1]
+    pc = np.ascontiguousarray(np.stack([p.T for p in poses]))
+    out = np.zeros((sum(s.shape[0] for s in scans), 4), np.float32)
+    m = host.s3dhost_combined_measurement(sensor, ptrs, sizes, 3, pc.ctypes.data, cm(patch).ctypes.data, out.ctypes.data)
+    want = oracle_mod.combined_measurement(kitti[:3], poses, patch)
+    assert m == want.shape[0] and np.array_equal(out[:m].view(np.uint32), want.view(np.uint32))
+    host.s3dhost_sensor_destroy(sensor)
+
+
+def test_minihost_without_odometry(host, kitti):
+    """ScanSensor::addMeasurement(m) (core/ScanSensor.cpp:49-79): no odometry — the guess of a registration is the motion since
+    the last vertex chained from the previous results, and Sensor::checkMinDistance decides when a scan becomes a vertex."""
+    import slam3d_b200
+    host.s3dhost_run_no_odometry.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    sensor = host.s3dhost_sensor_create(b"velodyne")
+    fine = RegistrationParameters.defaults(point_cloud_density=0.5)
+    host.s3dhost_sensor_set_params(sensor, C.byref(fine), 0)
+    scans = [slam3d_b200.as_xyzw(k[::2]) for k in kitti]
+    ptrs = (C.c_void_p * 4)(*[s.ctypes.data for s in scans])
+    sizes = (C.c_uint64 * 4)(*[s.shape[0] for s in scans])
+    added = np.zeros(4, np.int32); T = np.zeros((4, 16)); nw = C.c_int(0)
+    # every scan qualifies (the KITTI scans are ~0.7 m apart): three odometry edges, each ~0.7 m forward
+    ne = host.s3dhost_run_no_odometry(sensor, ptrs, sizes, 4, 0.0, 0.0, added.ctypes.data, T.ctypes.data, C.byref(nw))
+    assert ne == 3 and list(added) == [1, 1, 1, 1] and nw.value == 0, host.s3dhost_last_message()
+    steps = [np.linalg.norm(T[e].reshape(4, 4).T[:3, 3]) for e in range(3)]
+    assert all(0.4 < s < 1.0 for s in steps), steps
+    # with a 1 m threshold only every second scan becomes a vertex; the skipped motion is carried as the next guess (:62, mLastTransform)
+    ne2 = host.s3dhost_run_no_odometry(sensor, ptrs, sizes, 4, 1.0, 0.5, added.ctypes.data, T.ctypes.data, C.byref(nw))
+    assert list(added) == [1, 0, 1, 0] and ne2 == 1 and nw.value == 0
+    assert 1.0 < np.linalg.norm(T[0].reshape(4, 4).T[:3, 3]) < 2.0
+    host.s3dhost_sensor_destroy(sensor)

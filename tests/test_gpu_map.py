@@ -75,3 +75,19 @@ def test_build_map_2m_points(ctx, oracle_mod):
     got = ctx.build_map(scans, poses, 0.2, 3, 0.1)
     want = oracle_mod.build_map(scans, poses, 0.2, 3, 0.1)
     assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_combined_measurement_bit_exact(ctx, oracle_mod, kitti):
+    """createCombinedMeasurement (PointCloudSensor.cpp:258-266): accumulate in list order, then re-express in the patch frame;
+    both float roundings of the two pcl::transformPointCloud calls are kept, so the result equals the oracle's bit for bit —
+    and two separate transform calls of the product."""
+    poses = [pose(0.69 * i, 0.004 * i, 0.0035 * i) for i in range(3)]
+    patch_pose = pose(0.7, 0.01, 0.004)
+    got = ctx.combined_measurement(kitti[:3], poses, patch_pose)
+    want = oracle_mod.combined_measurement(kitti[:3], poses, patch_pose)
+    assert got.shape == want.shape == (sum(c.shape[0] for c in kitti[:3]), 4)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    inv = oracle_mod.isometry_inverse(patch_pose)
+    two_step = np.concatenate([ctx.transform_cloud(ctx.transform_cloud(c, P), inv) for c, P in zip(kitti[:3], poses)])
+    assert np.array_equal(got.view(np.uint32), two_step.view(np.uint32))
+    assert ctx.combined_measurement([], [], patch_pose).shape[0] == 0

@@ -85,3 +85,25 @@ def test_map_golden(oracle_mod, kitti, golden):
     poses = [pose(0.69 * i, 0.004 * i, 0.0035 * i) for i in range(4)]
     m = oracle_mod.build_map(kitti, poses, 0.2, 3, 0.1)
     assert m.shape[0] == g["build_map 4 clouds"]["n_out"] and sha(m) == g["build_map 4 clouds"]["sha"]
+
+
+def test_combined_measurement_is_two_rounded_transforms(oracle_mod, kitti):
+    """createCombinedMeasurement = transformPointCloud(pose_i) then transformPointCloud(patch_pose^-1), each rounding to float."""
+    def pose(tx, ty, yaw):
+        T = np.eye(4)
+        T[:2, :2] = [[np.cos(yaw), -np.sin(yaw)], [np.sin(yaw), np.cos(yaw)]]
+        T[:3, 3] = [tx, ty, 0.01]
+        return T
+    clouds = [kitti[0][:2000], kitti[1][:3000]]
+    poses = [pose(0.5, 0.1, 0.02), pose(1.2, -0.1, 0.05)]
+    patch = pose(0.6, 0.0, 0.03)
+    got = oracle_mod.combined_measurement(clouds, poses, patch)
+    inv = oracle_mod.isometry_inverse(patch)
+    assert np.allclose(inv @ patch, np.eye(4), atol=1e-12)
+    want = []
+    for c, P in zip(clouds, poses):
+        p = c[:, :3].astype(np.float64)
+        step1 = (p[:, 0:1] * P[:3, 0] + (p[:, 1:2] * P[:3, 1] + (p[:, 2:3] * P[:3, 2] + P[:3, 3]))).astype(np.float32).astype(np.float64)
+        want.append((step1[:, 0:1] * inv[:3, 0] + (step1[:, 1:2] * inv[:3, 1] + (step1[:, 2:3] * inv[:3, 2] + inv[:3, 3]))).astype(np.float32))
+    want = np.concatenate(want)
+    assert got.shape == (5000, 4) and np.array_equal(got[:, :3].view(np.uint32), want.view(np.uint32)) and np.all(got[:, 3] == 1.0)
