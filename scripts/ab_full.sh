@@ -14,10 +14,5 @@ except Exception as e:
     print("$NAME: failed", e)
 PY
 }
+for S in ${STREAMS:-3 4 5 6}; do run streams$S S3D_STREAMS_PER_DEVICE=$S; done
 run default A=1
-run spin S3D_BLOCKING_SYNC=0
-run hostloop S3D_LOOP_MODE=3
-run hostloop_spin S3D_LOOP_MODE=3 S3D_BLOCKING_SYNC=0
-run streams4 S3D_STREAMS_PER_DEVICE=4
-run streams8 S3D_STREAMS_PER_DEVICE=8
-run r01 S3D_LIB_PATH=$PWD/slam3d_b200/build/variants/libs3d_r01.so

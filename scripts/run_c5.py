@@ -27,6 +27,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scans", type=int, default=2000)
     ap.add_argument("--build-cache-only", action="store_true")
+    ap.add_argument("--patch-range", type=int, default=0, help="Sensor::mPatchBuildingRange: loop closures match patches of scans (SURVEY 8d: 0 then 2)")
+    ap.add_argument("--batched", action="store_true", help="candidates of a vertex matched as one device batch (PointCloudSensor::createConstraints)")
+    ap.add_argument("--max-links", type=int, default=1)
+    ap.add_argument("--radius", type=float, default=1.0)
     args = ap.parse_args()
     from slam3d_b200 import synth
     radius, step = 1.5, 0.7
@@ -49,8 +53,8 @@ def main():
     import test_gpu_host as th
     from slam3d_b200._abi import RegistrationParameters
     host = th.load_host()
-    host.s3dhost_run_trajectory.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int,
-                                            C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    host.s3dhost_run_trajectory2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
     n = args.scans
     rng = np.random.default_rng(7)
     truth, scans = [], []
@@ -75,7 +79,8 @@ def main():
     max_edges = 4 * n
     edges = np.zeros((max_edges, 3), np.int32); T = np.zeros((max_edges, 16)); poses = np.zeros((n, 16)); nw = C.c_int(0)
     t0 = time.perf_counter()
-    ne = host.s3dhost_run_trajectory(sensor, ptrs, sizes, n, od.ctypes.data, 1.0, 1, 10, max_edges, edges.ctypes.data, T.ctypes.data, poses.ctypes.data, C.byref(nw))
+    ne = host.s3dhost_run_trajectory2(sensor, ptrs, sizes, n, od.ctypes.data, args.radius, args.max_links, 10, args.patch_range, int(args.batched), max_edges,
+                                      edges.ctypes.data, T.ctypes.data, poses.ctypes.data, C.byref(nw))
     dt = time.perf_counter() - t0
     assert ne >= 0, host.s3dhost_last_message()
     edges = edges[:ne]; T = T[:ne].reshape(ne, 4, 4).transpose(0, 2, 1)
@@ -87,6 +92,7 @@ def main():
     drift = float(np.linalg.norm((np.linalg.inv(truth[0]) @ truth[-1])[:3, 3] - P[-1][:3, 3]))
     loops = int(edges[:, 2].sum())
     print(json.dumps({"workload": "BASELINE configs[4]: figure-eight trajectory, addMeasurement(m, odom) + linkLastToNeighbors()", "scans": n,
+                      "patch_building_range": args.patch_range, "batched_links": bool(args.batched), "max_neighbor_links": args.max_links, "neighbor_radius": args.radius,
                       "seconds": dt, "scans_per_s": n / dt, "edges": int(ne), "odometry_edges": int(ne - loops), "loop_edges": loops,
                       "aligns": int((ne - loops) + 2 * loops), "warnings": int(nw.value), "last_warning": host.s3dhost_last_message().decode(),
                       "edge_translation_error_m": {"median": float(np.median(err_t)), "max": float(np.max(err_t))},

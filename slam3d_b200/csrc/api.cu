@@ -99,10 +99,11 @@ struct s3d_context {
   double stage_ms[S3D_N_STAGES] = {0, 0, 0, 0, 0, 0};
   uint64_t stage_launches[S3D_N_STAGES] = {0, 0, 0, 0, 0, 0};
   int max_pairs_per_launch = 32;
-  // Host threads / streams per device, swept 3..16 on B200 (profiles/r01h_summary.md): GICP on raw host scans is fastest with
-  // 6 (smaller chunks: the first kernels start after 1/6 of the upload); the prepare + prepared-align path and the NDT branch
-  // (252-register kernels) are fastest with 3.
-  int streams_per_device = 6;
+  // Host threads / streams per device.  Round 1 (host-driven rounds, one poll each) was fastest with 6; with the loop replayed by a
+  // graph there is no host latency left to hide and 3-4 chunks are best (B200, 64 pairs: 3300 / 3294 / 3008 registrations/s with
+  // 3 / 4 / 6 streams, e2e 2820 / 2831 / 2746; profiles/r02_summary.md).  The prepare + prepared-align path and the NDT branch
+  // (252-register kernels) use 3.
+  int streams_per_device = 4;
   int streams_small = 3;
   cudaStream_t input_stream = nullptr;  // s3d_set_input_stream: device-pointer inputs are produced on this stream
   bool have_input_stream = false;
@@ -298,7 +299,7 @@ static void align_chunk_body(Workspace& ws, const std::vector<const float*>& clo
       if (out[i].n_source < 100 || out[i].n_target < 100) out[i].status = S3D_TOO_FEW_POINTS;
       else out[i].status = (gicp || ndt) ? S3D_INVALID_ARGUMENT : S3D_UNKNOWN_ALGORITHM;
     }
-    if (gicp) set_error("correspondence_randomness must be in [1, 200] on the GPU path");
+    if (gicp) set_error("correspondence_randomness must be in [1, 4096]");
     else if (ndt) set_error("NDT resolution must be positive");
     else if (cfg.registration_algorithm == S3D_ALG_GICP_OMP || cfg.registration_algorithm == S3D_ALG_NDT_OMP)
       set_error("OMP is not available, you need to rebuild SLAM3D with OMP or use another matching algorithm.");
@@ -470,7 +471,7 @@ int s3d_voxel_downsample(s3d_context* ctx, s3d_cloud in, float leaf, float* out_
 
 int s3d_knn_covariances(s3d_context* ctx, s3d_cloud cloud, int k, uint32_t* knn_index, float* knn_dist2, double* covariances) {
   if (!ctx) return S3D_INVALID_ARGUMENT;
-  if (k < 1 || k > kMaxK || (uint64_t)k > cloud.n) { set_error("k must be in [1, 200] and not larger than the cloud"); return S3D_INVALID_ARGUMENT; }
+  if (k < 1 || k > kMaxK || (uint64_t)k > cloud.n) { set_error("k must be in [1, 4096] and not larger than the cloud"); return S3D_INVALID_ARGUMENT; }
   return guarded([&]() -> int {
     WsLease lease(ctx, 0);
     Workspace& ws = *lease;
@@ -613,7 +614,7 @@ static void prepare_chunk(s3d_context* ctx, int device_slot, const s3d_cloud* cl
 int s3d_prepare_clouds(s3d_context* ctx, int device_slot, const s3d_cloud* clouds, int n, double density, int k, s3d_prepared_cloud** out) {
   if (!ctx || !out || n < 0 || (n > 0 && !clouds) || device_slot < 0 || device_slot >= (int)ctx->devs.size()) return S3D_INVALID_ARGUMENT;
   for (int i = 0; i < n; ++i) out[i] = nullptr;
-  if (k < 1 || k > kMaxK) { set_error("correspondence_randomness must be in [1, 200] on the GPU path"); return S3D_INVALID_ARGUMENT; }
+  if (k < 1 || k > kMaxK) { set_error("correspondence_randomness must be in [1, 4096]"); return S3D_INVALID_ARGUMENT; }
   if (n == 0) return S3D_OK;
   const int W = std::max(1, ctx->streams_small);
   const int chunk = balanced_chunk(n, W, 2 * ctx->max_pairs_per_launch);

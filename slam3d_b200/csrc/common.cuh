@@ -19,7 +19,8 @@ constexpr int kSortThreads = 256;
 constexpr int kMaxLevels = 10;       // Morton bits per axis (30-bit keys)
 constexpr uint32_t kInvalidKey = 0xFFFFFFFFu;
 constexpr uint32_t kNoIndex = 0xFFFFFFFFu;
-constexpr int kMaxK = 200;           // correspondence_randomness limit: the per-thread heap of the kNN kernel lives in shared memory (k KB per CTA)
+constexpr int kMaxKShared = 200;     // up to here the per-thread heap of the kNN kernel lives in shared memory (k KB per CTA); beyond: global memory
+constexpr int kMaxK = 4096;          // sanity limit of correspondence_randomness (heap arena: 8 k bytes per point)
 
 struct HashEntry;
 

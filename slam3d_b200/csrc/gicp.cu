@@ -161,6 +161,7 @@ static_assert(kSmStateB >= size_t(kIterTile) * 64 + 16 * kEvalSums * 8 && kSmSta
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
 __device__ __forceinline__ int32_t ld_volatile_i32(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ uint32_t sm_id() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 // Release-only operations (MEMBAR.ALL.GPU + the atomic).  __threadfence() and every acquire form additionally emit CCTL.IVALL,
 // which drops the SM's whole L1 — the cache the searches of all resident CTAs live on — so the consumer side of every hand-over
@@ -183,6 +184,11 @@ __device__ __forceinline__ void red_add_release(int32_t* p, int32_t v) { asm vol
 template <bool kShared, typename T>
 __device__ __forceinline__ T ld_pass(const T* p) { return kShared ? __ldcg(p) : *p; }
 
+__device__ __forceinline__ double4 ldg_normal(const double4* p) {  // unit normal (x, y, z) through the read-only path; .w is padding
+  const double2 xy = __ldg(reinterpret_cast<const double2*>(p));
+  return make_double4(xy.x, xy.y, __ldg(reinterpret_cast<const double*>(p) + 2), 0.0);
+}
+
 // search pass of one tile
 template <bool kShared>
 __device__ __forceinline__ void iter_tile(const GicpArgs& a, const PairState& ps, const SlotInfo& sb, const SlotInfo& sa, uint32_t p, uint32_t tile,
@@ -196,7 +202,7 @@ __device__ __forceinline__ void iter_tile(const GicpArgs& a, const PairState& ps
   for (int i = 0; i < kFeat; ++i) f[i] = 0.0;
   if (r < sa.n_pts) {
     const GridView g = make_grid_view(sb);
-    const float4 mv = a.moved[ps.pt_off + r];
+    const float4 mv = __ldg(a.moved + ps.pt_off + r);  // moved[], the normals and the sorted points never change during the loop: read-only path
     const float3 q = transform_mv(ps.T, mv.x, mv.y, mv.z);
     const double thr = ps.max_corr2;
     const float cutoff = __double2float_ru(thr);
@@ -212,8 +218,8 @@ __device__ __forceinline__ void iter_tile(const GicpArgs& a, const PairState& ps
     uint32_t c = kNoIndex;
     if (nn.pos != kNoIndex && (double)nn.d2 < thr) {
       c = nn.pos;
-      const double4 n1 = sa.normals[r];
-      const double4 n2 = sb.normals[nn.pos];
+      const double4 n1 = ldg_normal(sa.normals + r);
+      const double4 n2 = ldg_normal(sb.normals + nn.pos);
       double av[3], bv[3] = {n2.x, n2.y, n2.z};
       for (int i = 0; i < 3; ++i) av[i] = ps.R[i][0] * n1.x + ps.R[i][1] * n1.y + ps.R[i][2] * n1.z;
       double M[6];
@@ -222,7 +228,7 @@ __device__ __forceinline__ void iter_tile(const GicpArgs& a, const PairState& ps
 #pragma unroll
       for (int i = 0; i < 6; ++i) mo[i] = M[i];
       // PCL's first objective evaluation of this outer iteration: d = float(T(x0) * p) - q, float subtraction, then double
-      const float4 qb = g.pts[nn.pos];
+      const float4 qb = __ldg(g.pts + nn.pos);
       const float3 pp = transform_mv(ps.T_eval, mv.x, mv.y, mv.z);
       const double d0 = (double)__fsub_rn(pp.x, qb.x), d1 = (double)__fsub_rn(pp.y, qb.y), d2 = (double)__fsub_rn(pp.z, qb.z);
       const double Md0 = M[0] * d0 + M[1] * d1 + M[2] * d2;
@@ -271,8 +277,8 @@ __device__ __forceinline__ void eval_tile(const GicpArgs& a, const PairState& ps
     const uint32_t c = ld_pass<kShared>(a.corr + ps.pt_off + r);  // written by the search pass, possibly on another SM
     if (c != kNoIndex) {
       valid = true;
-      mv = a.moved[ps.pt_off + r];
-      qb = sb.gpts[c];
+      mv = __ldg(a.moved + ps.pt_off + r);
+      qb = __ldg(sb.gpts + c);
       const double* Mp = a.mahal + 6 * (size_t)(ps.pt_off + r);
 #pragma unroll
       for (int i = 0; i < 6; ++i) M[i] = ld_pass<kShared>(Mp + i);
@@ -323,9 +329,9 @@ __device__ __forceinline__ void fitness_tile(const GicpArgs& a, const PairState&
   double s = 0.0; uint32_t c = 0;
   if (r < sa.n_pts) {
     const GridView g = make_grid_view(sb);
-    const float4 v = sa.gpts[r];
+    const float4 v = __ldg(sa.gpts + r);
     const float3 q = transform_se3(ps.final_T, v.x, v.y, v.z);
-    const float4 mv = a.moved[ps.pt_off + r];
+    const float4 mv = __ldg(a.moved + ps.pt_off + r);
     const uint32_t hint = ld_pass<kShared>(a.prev_nn + ps.pt_off + r);
     NNResult nn;
     float lb_new;
@@ -432,7 +438,11 @@ __device__ __forceinline__ void ctrl_step_body(const GicpArgs& a, uint32_t p, in
   const int stride = after_eval ? kLineSearchTrials * kEvalSums : kNumMoments;
   const double* src0 = after_eval ? a.eval_part + (size_t)p * a.tiles_per_pair * stride + ps.trial_first * kEvalSums
                                   : a.moments + (size_t)p * a.tiles_per_pair * stride;
-  const int subs = n_sums * 3 <= 256 ? 3 : (n_sums * 2 <= 256 ? 2 : 1);
+  // fixed order: `subs` contiguous tile ranges per sum, each summed front to back, then the ranges front to back.  As many ranges
+  // as the CTA has threads for (3 for the 74 sums of a search pass, 16 for the 13 of a single trial): the chain of dependent L2
+  // loads per thread is what this step waits for.
+  const int subs = min(16, 256 / n_sums);
+  double* part = &sh.part[0][0];  // [subs][n_sums], at most 3 * 130 entries
   if ((int)threadIdx.x < subs * n_sums) {
     const int m = threadIdx.x % n_sums, sub = threadIdx.x / n_sums;
     const uint32_t per = (n_tiles + subs - 1) / subs;
@@ -441,12 +451,12 @@ __device__ __forceinline__ void ctrl_step_body(const GicpArgs& a, uint32_t p, in
     double s = 0.0;
 #pragma unroll 8
     for (uint32_t t = lo; t < hi; ++t) s += __ldcg(src + (size_t)t * stride);  // written by other CTAs: read from L2
-    sh.part[sub][m] = s;
+    part[sub * n_sums + m] = s;
   }
   __syncthreads();
   if ((int)threadIdx.x < n_sums) {
-    double s = sh.part[0][threadIdx.x];
-    for (int sub = 1; sub < subs; ++sub) s += sh.part[sub][threadIdx.x];
+    double s = part[threadIdx.x];
+    for (int sub = 1; sub < subs; ++sub) s += part[sub * n_sums + threadIdx.x];
     sh.red[threadIdx.x] = s;
   }
   __syncthreads();
@@ -532,6 +542,16 @@ __device__ void fitness_finish(const GicpArgs& a, uint32_t p, unsigned char* sme
   }
 }
 
+// cooperative copy of the pair state from L2 into shared memory (explicitly global loads: every field a tile reads afterwards is
+// an LDS broadcast instead of a generic load per thread)
+__device__ __forceinline__ const PairState& stage_state(const GicpArgs& a, uint32_t p, unsigned char* dst) {
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.pairs + p);
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(dst);
+  for (uint32_t i = threadIdx.x; i < sizeof(PairState) / 8; i += blockDim.x) d[i] = __ldcg(src + i);
+  __syncthreads();
+  return *reinterpret_cast<const PairState*>(dst);
+}
+
 // ---- scheduler ------------------------------------------------------------------------------------------------------------------
 // PairSched.desc  = epoch << 32 | tiles per claim << 24 | tiles of the pass that is open for claims (0 tiles: nothing to claim —
 //                   control step running, or the pair is closed)
@@ -584,11 +604,10 @@ __device__ __forceinline__ void publish_pass(const GicpArgs& a, uint32_t p, uint
 // nothing to claim waits (nanosleep) for the next pass to be published.  Two CTAs per SM (128 registers): a single pair has 185
 // tiles per pass for 148 SMs, so occupancy is not what limits it — the serial control step is, and with 128 registers it runs
 // without the spills a 64-register budget forces on its FP64 chain.
-__global__ void __launch_bounds__(kIterTile, 2) gicp_loop_kernel(const GicpArgs* __restrict__ ap) {
+__global__ void __launch_bounds__(kIterTile, 2) gicp_loop_kernel(const __grid_constant__ GicpArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ uint32_t s_p, s_tile, s_n;
   __shared__ int s_found, s_last;
-  const GicpArgs a = *ap;
   uint32_t rot = sm_id() % a.n_pairs;  // the CTAs of one SM start on the same pair: its grid and points share that SM's L1
   const long long t_start = clock64();
   for (;;) {
@@ -606,15 +625,10 @@ __global__ void __launch_bounds__(kIterTile, 2) gicp_loop_kernel(const GicpArgs*
     __syncthreads();
     if (!s_found) break;
     const uint32_t p = s_p, tile0 = s_tile, n_claimed = s_n;
+    const unsigned long long t_tile = threadIdx.x == 0 ? global_ns() : 0ull;
     // the pair state and pass data were released before this claim became possible; read them from L2
     const int phase = __ldcg(&a.pairs[p].phase);
-    const PairState& tps = *reinterpret_cast<const PairState*>(smem + (phase == kPhaseEval ? kSmStateB : kSmStateA));
-    {
-      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.pairs + p);
-      unsigned long long* dst = reinterpret_cast<unsigned long long*>(smem + (phase == kPhaseEval ? kSmStateB : kSmStateA));
-      for (uint32_t i = threadIdx.x; i < sizeof(PairState) / 8; i += blockDim.x) dst[i] = __ldcg(src + i);
-    }
-    __syncthreads();
+    const PairState& tps = stage_state(a, p, smem + (phase == kPhaseEval ? kSmStateB : kSmStateA));
     const SlotInfo& sb = a.slots[2 * p];
     const SlotInfo& sa = a.slots[2 * p + 1];
     if (phase == kPhaseNeedNN) iter_tile<true>(a, tps, sb, sa, p, tile0, smem);            // one tile per claim
@@ -629,9 +643,11 @@ __global__ void __launch_bounds__(kIterTile, 2) gicp_loop_kernel(const GicpArgs*
       const uint32_t n_live = (sa.n_pts + kIterTile - 1) / kIterTile;
       s_last = atom_add_release(&a.pairs[p].ticket, n_claimed) + n_claimed == n_live;
       atomicAdd(&a.ctl[0], n_claimed);
+      atomicAdd(&a.ctl[phase == kPhaseNeedNN ? 4 : (phase == kPhaseEval ? 5 : 6)], (uint32_t)(global_ns() - t_tile));  // statistics: ns in tiles by pass type
     }
     __syncthreads();
     if (s_last) {  // this CTA delivered the last tile of the pass: control step, then publish what comes next
+      const unsigned long long t_ctrl = threadIdx.x == 0 ? global_ns() : 0ull;
       uint32_t next_tiles = 0;
       if (phase == kPhaseFitness) {
         fitness_finish(a, p, smem);
@@ -643,7 +659,10 @@ __global__ void __launch_bounds__(kIterTile, 2) gicp_loop_kernel(const GicpArgs*
       if (threadIdx.x == 0) {
         atomicAdd(&a.ctl[1], 1u);
         const int next_phase = next_tiles ? reinterpret_cast<const CtrlShared*>(smem)->ps.phase : kPhaseFinished;
-        publish_pass(a, p, next_tiles, next_phase == kPhaseEval ? kTrialTilesPerClaim : 1u);
+        // several trial tiles per claim only when there are more tiles in flight than CTAs (a single pair has fewer: one tile per CTA)
+        const bool crowded = (unsigned long long)a.n_pairs * next_tiles > 2ull * gridDim.x;
+        publish_pass(a, p, next_tiles, next_phase == kPhaseEval && crowded ? kTrialTilesPerClaim : 1u);
+        atomicAdd(&a.ctl[7], (uint32_t)(global_ns() - t_ctrl));  // statistics: ns in control steps (incl. publishing)
         if (next_tiles == 0) red_add_release(&a.flags[1], -1);  // the pair is closed: its results come before the count
       }
     }
@@ -659,34 +678,33 @@ __global__ void __launch_bounds__(kIterTile, 2) gicp_loop_kernel(const GicpArgs*
 // pairs, 16 scenes, loop only): persistent kernel 11.2 ms on one stream but 13.7-16.3 ms on six (its resident CTAs hold the
 // registers of every SM, so the chunks serialise and each drags its own tail); per-pass kernels 14.9 ms on one stream and
 // 10.3 ms on six (profiles/r02_summary.md).  Results are bit-identical in both modes (same tile partials, same control step).
-__global__ void __launch_bounds__(kIterTile, 4) gicp_search_kernel(const GicpArgs* __restrict__ ap) {
+__global__ void __launch_bounds__(kIterTile, 4) gicp_search_kernel(const __grid_constant__ GicpArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const GicpArgs a = *ap;
   const uint32_t p = blockIdx.y, tile = blockIdx.x;
-  const PairState& ps = a.pairs[p];
-  if (ps.phase != kPhaseNeedNN) return;
+  if (__ldcg(&a.pairs[p].phase) != kPhaseNeedNN) return;
   const SlotInfo& sa = a.slots[2 * p + 1];
   if (tile * kIterTile >= sa.n_pts) return;
-  iter_tile<false>(a, ps, a.slots[2 * p], sa, p, tile, smem);
+  iter_tile<true>(a, stage_state(a, p, smem + kSmStateA), a.slots[2 * p], sa, p, tile, smem);
 }
 
-__global__ void __launch_bounds__(kIterTile) gicp_trial_kernel(const GicpArgs* __restrict__ ap) {
-  __shared__ __align__(16) unsigned char smem[size_t(kIterTile) * 64 + 16 * kEvalSums * 8];
-  const GicpArgs a = *ap;
+// (Tried: the control step fused into this kernel by the ticket scheme — one launch less per trial pass, but the inlined FP64
+// chain raises the kernel from 56 to 80+ registers and the light trial tiles lose a resident CTA per SM: 3262-3283 against
+// 3294-3300 registrations/s, profiles/r02_summary.md.)
+__global__ void __launch_bounds__(kIterTile) gicp_trial_kernel(const __grid_constant__ GicpArgs a) {
+  constexpr size_t kScratch = size_t(kIterTile) * 64 + 16 * kEvalSums * 8;
+  __shared__ __align__(16) unsigned char smem[kScratch + sizeof(PairState)];
   const uint32_t p = blockIdx.y, tile = blockIdx.x;
-  const PairState& ps = a.pairs[p];
-  if (ps.phase != kPhaseEval) return;
+  if (__ldcg(&a.pairs[p].phase) != kPhaseEval) return;
   const SlotInfo& sa = a.slots[2 * p + 1];
   if (tile * kIterTile >= sa.n_pts) return;
-  eval_tile<false>(a, ps, a.slots[2 * p], sa, p, tile, smem);
+  eval_tile<true>(a, stage_state(a, p, smem + kScratch), a.slots[2 * p], sa, p, tile, smem);
 }
 
 // one CTA per pair; the first control launch of a round serves pairs that just searched, the later ones pairs that were just evaluated
-__global__ void __launch_bounds__(256) gicp_ctrl_kernel(const GicpArgs* __restrict__ ap, int after_eval) {
+__global__ void __launch_bounds__(256) gicp_ctrl_kernel(const __grid_constant__ GicpArgs a, int after_eval) {
   __shared__ __align__(16) unsigned char smem[sizeof(CtrlShared)];
-  const GicpArgs a = *ap;
   const uint32_t p = blockIdx.x;
-  if (a.pairs[p].phase != (after_eval ? kPhaseEval : kPhaseNeedNN)) return;
+  if (__ldcg(&a.pairs[p].phase) != (after_eval ? kPhaseEval : kPhaseNeedNN)) return;
   ctrl_step_body(a, p, after_eval, smem);
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -696,29 +714,25 @@ __global__ void __launch_bounds__(256) gicp_ctrl_kernel(const GicpArgs* __restri
   }
 }
 
-__global__ void gicp_cond_kernel(const GicpArgs* __restrict__ ap, cudaGraphConditionalHandle cond) {
-  const GicpArgs a = *ap;
+__global__ void gicp_cond_kernel(const __grid_constant__ GicpArgs a, cudaGraphConditionalHandle cond) {
   const uint32_t rounds = ++a.ctl[3];
   const bool stuck = rounds >= a.max_launches;
   if (stuck) atomicOr(&a.flags[0], kErrWatchdog);
   cudaGraphSetConditional(cond, (a.flags[1] > 0 && !stuck) ? 1u : 0u);
 }
 
-__global__ void __launch_bounds__(kIterTile, 4) gicp_fitness_kernel(const GicpArgs* __restrict__ ap) {
+__global__ void __launch_bounds__(kIterTile, 4) gicp_fitness_kernel(const __grid_constant__ GicpArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const GicpArgs a = *ap;
   const uint32_t p = blockIdx.y, tile = blockIdx.x;
-  const PairState& ps = a.pairs[p];
-  if (ps.phase != kPhaseFitness) return;
+  if (__ldcg(&a.pairs[p].phase) != kPhaseFitness) return;
   const SlotInfo& sa = a.slots[2 * p + 1];
   if (tile * kIterTile >= sa.n_pts) return;
-  fitness_tile<false>(a, ps, a.slots[2 * p], sa, p, tile, smem);
+  fitness_tile<true>(a, stage_state(a, p, smem + kSmStateA), a.slots[2 * p], sa, p, tile, smem);
 }
 
-__global__ void __launch_bounds__(kIterTile) gicp_fitness_finish_kernel(const GicpArgs* __restrict__ ap) {
+__global__ void __launch_bounds__(kIterTile) gicp_fitness_finish_kernel(const __grid_constant__ GicpArgs a) {
   __shared__ __align__(16) unsigned char smem[size_t(kIterTile) * 16];
-  const GicpArgs a = *ap;
-  if (a.pairs[blockIdx.x].phase != kPhaseFitness) return;
+  if (__ldcg(&a.pairs[blockIdx.x].phase) != kPhaseFitness) return;
   fitness_finish(a, blockIdx.x, smem);
   if (threadIdx.x == 0) atomicAdd(&a.ctl[0], (a.slots[2 * blockIdx.x + 1].n_pts + kIterTile - 1) / kIterTile);
 }
@@ -771,7 +785,21 @@ static int loop_grid(int device) {
 // Throughput mode: WHILE (a pair iterates) { search, control, trial, control, trial, control, condition } as a CUDA graph with a
 // conditional node.  The kernels read everything from the GicpArgs block at a fixed device address; only the grid dimensions
 // depend on the batch, so executable graphs are cached per workspace by (tiles per pair, pairs).
-static cudaGraphExec_t loop_graph_for(Workspace& ws, uint32_t tiles_per_pair, uint32_t np) {
+static cudaGraphExec_t loop_graph_for(Workspace& ws, const GicpArgs& args, uint32_t tiles_per_pair, uint32_t np) {
+  // the graphs hold the argument block by value: when a buffer has moved (the batch grew), the cached graphs are stale
+  uint64_t sig = 1469598103934665603ull;
+  {
+    GicpArgs key_args = args;
+    key_args.tiles_per_pair = 0; key_args.n_pairs = 0;
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(&key_args);
+    for (size_t i = 0; i < sizeof key_args; ++i) { sig ^= b[i]; sig *= 1099511628211ull; }
+  }
+  if (sig != ws.loop_graph_sig) {
+    for (auto& g : ws.loop_graphs) cudaGraphExecDestroy(g.second);
+    for (cudaGraph_t g : ws.loop_graph_defs) cudaGraphDestroy(g);
+    ws.loop_graphs.clear(); ws.loop_graph_defs.clear();
+    ws.loop_graph_sig = sig;
+  }
   const uint64_t key = (uint64_t)tiles_per_pair << 32 | np;
   auto it = ws.loop_graphs.find(key);
   if (it != ws.loop_graphs.end()) return it->second;
@@ -787,7 +815,7 @@ static cudaGraphExec_t loop_graph_for(Workspace& ws, uint32_t tiles_per_pair, ui
   cudaGraphNode_t cond_node;
   S3D_CUDA(cudaGraphAddNode(&cond_node, graph, nullptr, 0, &cp));
   cudaGraph_t body = cp.conditional.phGraph_out[0];
-  const GicpArgs* ap = ws.gicp_args.as<GicpArgs>();
+  GicpArgs ap = args;
   int zero = 0, one = 1;
   cudaGraphNode_t prev = nullptr;
   auto add = [&](void* fn, dim3 grid, unsigned block, unsigned smem, void** args) {
@@ -837,7 +865,6 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   ws.corr.reserve(4 * std::max<size_t>(ws.total, 4));
   ws.mahal.reserve(48 * std::max<size_t>(ws.total, 4));
   ws.fit_partial.reserve(sizeof(double) * 2 * size_t(tiles_per_pair) * np);
-  if (!ws.gicp_args.p) ws.gicp_args.reserve(sizeof(GicpArgs));  // allocated once: the loop graph holds this address
   ws.gicp_sched.reserve(sizeof(PairSched) * np + 64);
   PairState* hp = ws.h_pairs.as<PairState>();
   for (uint32_t p = 0; p < np; ++p) {
@@ -872,11 +899,11 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   const int loop_mode = loop_env ? atoi(loop_env) : 0;
   const uint32_t linger = 0;
   const bool throughput = loop_mode == 2 || loop_mode == 3 || (loop_mode == 0 && ws.blocking_sync);
-  GicpArgs* ha = reinterpret_cast<GicpArgs*>(ws.h_small.as<char>() + 256);
+  GicpArgs args_value;
+  GicpArgs* ha = &args_value;
   *ha = GicpArgs{slots, pairs, ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), ws.corr.as<uint32_t>(), ws.mahal.as<double>(),
                  ws.moments.as<double>(), ws.eval_part.as<double>(), ws.fit_partial.as<double>(), flags, psched, ctl, tiles_per_pair, np,
                  linger, 1u << 20, watchdog};
-  S3D_CUDA(cudaMemcpyAsync(ws.gicp_args.p, ha, sizeof(GicpArgs), cudaMemcpyHostToDevice, st));
   S3D_CUDA(cudaMemsetAsync(ctl, 0, 64, st));
   dim3 grid(tiles_per_pair, np);
   {
@@ -884,7 +911,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
     gicp_prepare_kernel<<<grid, 256, 0, st>>>(slots, pairs, ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), psched, flags);
     ++ws.launches;
   }
-  const GicpArgs* dargs = ws.gicp_args.as<GicpArgs>();
+  const GicpArgs dargs = *ha;
   if (!throughput) {
     StageTimer timer(ws, kStageIter);
     gicp_loop_kernel<<<loop_grid(ws.device), kIterTile, kSmLoop, st>>>(dargs);
@@ -893,7 +920,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   } else {
     if (!ws.profiling && loop_mode != 3) {
       StageTimer timer(ws, kStageIter);
-      S3D_CUDA(cudaGraphLaunch(loop_graph_for(ws, tiles_per_pair, np), st));
+      S3D_CUDA(cudaGraphLaunch(loop_graph_for(ws, dargs, tiles_per_pair, np), st));
     } else {
       // the same kernels from the host, one poll per round, so that each can be timed
       for (uint32_t round = 0; round < (1u << 20); ++round) {
@@ -925,7 +952,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
     }
     S3D_CUDA(cudaGetLastError());
   }
-  S3D_CUDA(cudaMemcpyAsync(h_ctl, ctl, 16, cudaMemcpyDeviceToHost, st));
+  S3D_CUDA(cudaMemcpyAsync(h_ctl, ctl, 32, cudaMemcpyDeviceToHost, st));
   S3D_CUDA(cudaMemcpyAsync(hp, pairs, sizeof(PairState) * np, cudaMemcpyDeviceToHost, st));
   SlotInfo* hs = ws.h_slots.as<SlotInfo>();
   S3D_CUDA(cudaMemcpyAsync(hs, slots, sizeof(SlotInfo) * ws.n_slots, cudaMemcpyDeviceToHost, st));
@@ -933,6 +960,9 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   ws.sync();
   ws.d2h += sizeof(PairState) * np + sizeof(SlotInfo) * ws.n_slots + 32;
   ws.passes += h_ctl[0]; ws.ctrl_steps += h_ctl[1];
+  if (getenv("S3D_LOOP_STATS") && !throughput)
+    fprintf(stderr, "[s3d loop] pairs %u tiles %u control steps %u | per control step %.1f us | CTA-time in search tiles %.0f us, trial tiles %.0f us, fitness tiles %.0f us\n",
+            np, h_ctl[0], h_ctl[1], h_ctl[1] ? 1e-3 * h_ctl[7] / h_ctl[1] : 0.0, 1e-3 * h_ctl[4], 1e-3 * h_ctl[5], 1e-3 * h_ctl[6]);
   ws.launches += 7ull * h_ctl[3];  // rounds replayed by the graph's WHILE node (throughput mode): 7 kernels each
   for (auto& sp : ws.spans) if (sp.stage == kStageIter && h_ctl[3]) sp.n_launch = 7 * h_ctl[3];
   ws.collect_spans();

@@ -92,13 +92,16 @@ struct PairSched {
   unsigned long long desc;   // tiles of the open pass (0: nothing to claim)
 };
 
-// Arguments of the GICP loop kernel (device resident).
+// Arguments of the GICP loop kernels, passed BY VALUE as a kernel parameter: pointers that arrive in parameter space are known to
+// be global (LDG / STG); the same pointers read from a block in device memory compile to generic LD / ST (measured: the search
+// kernel 5 % slower).  The cached loop graphs therefore hold these values, and are dropped when a workspace buffer moves.
 struct GicpArgs {
-  const SlotInfo* slots; PairState* pairs;
-  const float4* moved; uint32_t* prev_nn; float* sec_lb; uint32_t* corr; double* mahal; double* moments; double* eval_part; double* fit_partial;
-  int32_t* flags;          // [0] error bits, [1] active pairs
-  PairSched* psched;
-  uint32_t* ctl;           // [0] tiles processed, [1] control steps (statistics); [3] rounds (throughput mode)
+  const SlotInfo* __restrict__ slots; PairState* __restrict__ pairs;
+  const float4* __restrict__ moved; uint32_t* __restrict__ prev_nn; float* __restrict__ sec_lb; uint32_t* __restrict__ corr; double* __restrict__ mahal;
+  double* __restrict__ moments; double* __restrict__ eval_part; double* __restrict__ fit_partial;
+  int32_t* __restrict__ flags;          // [0] error bits, [1] active pairs
+  PairSched* __restrict__ psched;
+  uint32_t* __restrict__ ctl;           // [0] tiles processed, [1] control steps (statistics); [3] rounds (throughput mode)
   uint32_t tiles_per_pair, n_pairs;
   uint32_t reserved;
   uint32_t max_launches;   // throughput mode: rounds after which the loop gives up (scheduler fault)
@@ -132,6 +135,7 @@ struct Workspace {
   DevBuf hash;                                // HashEntry[hash_cap]
   size_t hash_cap = 0;
   size_t hash_want = 0;                       // entries requested by the last arena overflow (0: default sizing)
+  DevBuf knn_arena;                           // uint64[k * threads of the launch]: kNN heaps in global memory when k > kMaxKShared
   DevBuf normals;                             // double[total*4]  unit normal of the regularised covariance (+pad)
   DevBuf moved;                               // float4[total]   guess * A (Morton order of A)
   DevBuf prev_nn;                             // uint32[total]   last correspondence (warm start bound)
@@ -149,6 +153,7 @@ struct Workspace {
   uint64_t passes = 0, ctrl_steps = 0;        // tiles processed / control steps run by the loop kernel (statistics)
   std::map<uint64_t, cudaGraphExec_t> loop_graphs;  // throughput mode: WHILE (a pair iterates) { per-pass kernels }, by (tiles per pair, pairs)
   std::vector<cudaGraph_t> loop_graph_defs;
+  uint64_t loop_graph_sig = 0;                // hash of the pointer values the cached graphs were built with
   DevBuf flags;                               // int32[16]: [0] error bits, [1] active pairs, [2] hash entries used, [3] entries needed, [8] long voxel runs, [9] kept points
   PinnedBuf h_slots, h_pairs, h_small, h_tiles;  // pinned host mirrors
   PinnedBuf h_bounce;                            // pinned landing zone for pageable host clouds (setup_batch)

@@ -30,14 +30,15 @@ namespace s3d {
 // the exponent range (a few integer min/max per neighbour) and only falls back to heapsort + ordered sums when that exactness
 // certificate fails (a neighbourhood that straddles a coordinate plane within ~1e-4 of its extent) or when the caller wants the
 // sorted lists.  The result is bit-identical to the ordered sums either way; the heapsort was 18 % of this kernel.
-__device__ __forceinline__ void knn_finish(const SlotInfo& si, const float4* __restrict__ cloud, uint64_t* h, int cnt, int k, uint32_t r, uint32_t q_orig,
+template <typename Heap>
+__device__ __forceinline__ void knn_finish(const SlotInfo& si, const float4* __restrict__ cloud, const Heap& h, int cnt, int k, uint32_t r, uint32_t q_orig,
                                            double4* __restrict__ normals, uint32_t* __restrict__ knn_index, float* __restrict__ knn_dist2) {
   double mean[3] = {0, 0, 0}, cov[6] = {0, 0, 0, 0, 0, 0};  // cov: 00,10,11,20,21,22
   bool ordered = knn_index != nullptr || knn_dist2 != nullptr;
   if (!ordered) {
     uint32_t elo[3] = {255u, 255u, 255u}, ehi[3] = {0u, 0u, 0u};
     for (int j = 0; j < cnt; ++j) {
-      const float4 pt = __ldg(cloud + (uint32_t)h[j * kKnnThreads]);
+      const float4 pt = __ldg(cloud + (uint32_t)h.at(j));
       const float c3v[3] = {pt.x, pt.y, pt.z};
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
@@ -61,12 +62,12 @@ __device__ __forceinline__ void knn_finish(const SlotInfo& si, const float4* __r
   }
   if (ordered) {
     for (int m = cnt - 1; m > 0; --m) {  // heapsort: ascending (d2, idx)
-      const uint64_t last = h[m * kKnnThreads];
-      h[m * kKnnThreads] = h[0];
+      const uint64_t last = h.at(m);
+      h.at(m) = h.at(0);
       heap_sift_down(h, m, last);
     }
     for (int j = 0; j < cnt; ++j) {
-      const uint64_t key = h[j * kKnnThreads];
+      const uint64_t key = h.at(j);
       const uint32_t id = (uint32_t)key;
       const float4 pt = __ldg(cloud + id);
       mean[0] += (double)pt.x; mean[1] += (double)pt.y; mean[2] += (double)pt.z;
@@ -98,26 +99,45 @@ __device__ __forceinline__ void knn_finish(const SlotInfo& si, const float4* __r
   normals[si.off + r] = make_double4(nrm[0], nrm[1], nrm[2], 0.0);
 }
 
-__global__ void __launch_bounds__(kKnnThreads, S3D_KNN_MINBLOCKS) knn_cov_kernel(const SlotInfo* __restrict__ slots, const float4* __restrict__ work,
-                                                              double4* __restrict__ normals, int k, uint32_t* __restrict__ knn_index,
-                                                              float* __restrict__ knn_dist2) {
-  extern __shared__ uint64_t heap_smem[];  // k * kKnnThreads keys
-  const SlotInfo& si = slots[blockIdx.y];
-  const uint32_t n = si.n_pts;
-  const uint32_t r = blockIdx.x * kKnnThreads + threadIdx.x;
-  if (r >= n) return;
-  const GridView g = make_grid_view(si);
-  if (g.cap == 0) return;  // grid build overflowed its arena: the host re-runs the batch
-  const int kk = k < (int)n ? k : (int)n;  // FLANN clamps k to the cloud size
-  uint64_t* h = heap_smem + threadIdx.x;
+template <typename Heap>
+__device__ __forceinline__ void knn_cov_query(const SlotInfo& si, const GridView& g, const float4* __restrict__ work, double4* __restrict__ normals, int k, uint32_t r,
+                                              const Heap& h, uint32_t* __restrict__ knn_index, float* __restrict__ knn_dist2) {
+  const int kk = k < (int)si.n_pts ? k : (int)si.n_pts;  // FLANN clamps k to the cloud size
   const float4 qv = g.pts[r];
   const float ux = clamp_coord(grid_coord(qv.x, g.ox, g.inv_h0));
   const float uy = clamp_coord(grid_coord(qv.y, g.oy, g.inv_h0));
   const float uz = clamp_coord(grid_coord(qv.z, g.oz, g.inv_h0));
   KSTAT(0, 1);
   const int cnt = thread_walk(g, qv, ux, uy, uz, knn_start_level(g, ux, uy, uz), KMAX, h, kk);
-  if (cnt < kk) for (int i = heap_last_parent(cnt); i >= 0; --i) heap_sift_down(h, cnt, h[i * kKnnThreads], i);  // top level ended before the list filled
+  if (cnt < kk) for (int i = heap_last_parent(cnt); i >= 0; --i) heap_sift_down(h, cnt, h.at(i), i);  // top level ended before the list filled
   knn_finish(si, work + si.off, h, cnt, k, r, __float_as_uint(qv.w), normals, knn_index, knn_dist2);
+}
+
+__global__ void __launch_bounds__(kKnnThreads, S3D_KNN_MINBLOCKS) knn_cov_kernel(const SlotInfo* __restrict__ slots, const float4* __restrict__ work,
+                                                              double4* __restrict__ normals, int k, uint32_t* __restrict__ knn_index,
+                                                              float* __restrict__ knn_dist2) {
+  extern __shared__ uint64_t heap_smem[];  // k * kKnnThreads keys
+  const SlotInfo& si = slots[blockIdx.y];
+  const uint32_t r = blockIdx.x * kKnnThreads + threadIdx.x;
+  if (r >= si.n_pts) return;
+  const GridView g = make_grid_view(si);
+  if (g.cap == 0) return;  // grid build overflowed its arena: the host re-runs the batch
+  knn_cov_query(si, g, work, normals, k, r, SmemHeap{heap_smem + threadIdx.x}, knn_index, knn_dist2);
+}
+
+// correspondence_randomness beyond what the shared-memory heap holds: the same walk on a heap in global memory (one column per
+// thread of the launch).  PCL accepts any k; this keeps the GPU path from refusing what the reference runs.
+__global__ void __launch_bounds__(kKnnThreads) knn_cov_bigk_kernel(const SlotInfo* __restrict__ slots, const float4* __restrict__ work,
+                                                                   double4* __restrict__ normals, int k, uint64_t* __restrict__ arena,
+                                                                   uint32_t* __restrict__ knn_index, float* __restrict__ knn_dist2) {
+  const SlotInfo& si = slots[blockIdx.y];
+  const uint32_t r = blockIdx.x * kKnnThreads + threadIdx.x;
+  if (r >= si.n_pts) return;
+  const GridView g = make_grid_view(si);
+  if (g.cap == 0) return;
+  const size_t stride = (size_t)gridDim.x * gridDim.y * kKnnThreads;
+  const size_t column = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kKnnThreads + threadIdx.x;
+  knn_cov_query(si, g, work, normals, k, r, GlobalHeap{arena + column, stride}, knn_index, knn_dist2);
 }
 
 // stage-API helper: full regularised covariance per ORIGINAL index, column-major 3x3
@@ -139,8 +159,14 @@ void run_knn_covariances(Workspace& ws, int k, uint32_t* knn_index, float* knn_d
   StageTimer timer(ws, kStageKnn);
   dim3 grid((max_n + kKnnThreads - 1) / kKnnThreads, ws.n_slots);
   const size_t heap_bytes = sizeof(uint64_t) * k * kKnnThreads;
-  if (heap_bytes > 48 * 1024) S3D_CUDA(cudaFuncSetAttribute(knn_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heap_bytes));
-  knn_cov_kernel<<<grid, kKnnThreads, heap_bytes, ws.stream>>>(ws.slots.as<SlotInfo>(), ws.work.as<float4>(), ws.normals.as<double4>(), k, knn_index, knn_dist2);
+  if (k <= kMaxKShared) {
+    if (heap_bytes > 48 * 1024) S3D_CUDA(cudaFuncSetAttribute(knn_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heap_bytes));
+    knn_cov_kernel<<<grid, kKnnThreads, heap_bytes, ws.stream>>>(ws.slots.as<SlotInfo>(), ws.work.as<float4>(), ws.normals.as<double4>(), k, knn_index, knn_dist2);
+  } else {
+    ws.knn_arena.reserve(heap_bytes * grid.x * grid.y);
+    knn_cov_bigk_kernel<<<grid, kKnnThreads, 0, ws.stream>>>(ws.slots.as<SlotInfo>(), ws.work.as<float4>(), ws.normals.as<double4>(), k, ws.knn_arena.as<uint64_t>(),
+                                                             knn_index, knn_dist2);
+  }
   ++ws.launches;
   S3D_CUDA(cudaGetLastError());
 }

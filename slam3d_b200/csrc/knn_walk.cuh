@@ -24,7 +24,7 @@ __device__ unsigned long long g_knn_stats[8];  // queries, level scans, cells pr
 #define KSTAT(i, v)
 #endif
 
-// d-ary max-heap of 64-bit keys in shared memory, element j of thread t at h[j * kKnnThreads]; children of node i are
+// d-ary max-heap of 64-bit keys in shared memory, element j of thread t at h.at(j); children of node i are
 // D i + 1 .. D i + D.  With D = 4 a 20-element heap is two levels deep instead of five, and the child loads of a level are
 // independent (their latencies overlap), so a sift-down is two short rounds instead of four or five dependent ones
 // (B200, 64 pairs per step: see profiles/r01h_summary.md).  Any heap order gives the same k-NN set and the heapsort below
@@ -35,24 +35,38 @@ __device__ unsigned long long g_knn_stats[8];  // queries, level scans, cells pr
 constexpr int kHeapD = S3D_KNN_HEAP_ARITY;
 __device__ __forceinline__ int heap_last_parent(int n) { return n >= 2 ? (n - 2) / kHeapD : -1; }
 
+// Where a thread's heap lives.  SmemHeap: element j of thread t at smem[j * kKnnThreads + t] (bank-conflict free, compile-time
+// stride) — k up to kMaxKShared.  GlobalHeap: the same layout in a global-memory arena with a run-time stride (the number of
+// threads of the launch), for the k beyond what shared memory holds; slower per access, but the walk and its results are the same.
+struct SmemHeap {
+  uint64_t* base;
+  __device__ __forceinline__ uint64_t& at(int j) const { return base[j * kKnnThreads]; }
+};
+struct GlobalHeap {
+  uint64_t* base;
+  size_t stride;
+  __device__ __forceinline__ uint64_t& at(int j) const { return base[(size_t)j * stride]; }
+};
+
 // puts x at node i (whose subtrees are heaps) and restores the heap below it; i = 0 replaces the root
-__device__ __forceinline__ void heap_sift_down(uint64_t* h, int n, uint64_t x, int i = 0) {
+template <typename Heap>
+__device__ __forceinline__ void heap_sift_down(const Heap& h, int n, uint64_t x, int i = 0) {
   for (;;) {
     const int c0 = kHeapD * i + 1;
     if (c0 >= n) break;
     int c = c0;
-    uint64_t hc = h[c0 * kKnnThreads];
+    uint64_t hc = h.at(c0);
 #pragma unroll
     for (int j = 1; j < kHeapD; ++j) {
       const int cj = min(c0 + j, n - 1);  // past the end: the last element again (a real child, compared twice)
-      const uint64_t hj = h[cj * kKnnThreads];
+      const uint64_t hj = h.at(cj);
       if (hj > hc) { hc = hj; c = cj; }
     }
     if (hc <= x) break;
-    h[i * kKnnThreads] = hc;
+    h.at(i) = hc;
     i = c;
   }
-  h[i * kKnnThreads] = x;
+  h.at(i) = x;
 }
 
 // ---- per-thread walk ---------------------------------------------------------------------------------------------
@@ -70,7 +84,8 @@ constexpr uint64_t KMAX = 0xFFFFFFFFFFFFFFFFull;
 // scans the points [begin, end) of one cell for the query qv: fill phase (append, heapify once when the k-th candidate
 // arrives), then replace-the-root insertions.  S3D_KNN_BATCH points are fetched before the first of them is examined, so
 // their load latencies overlap (B200, 32 pairs per step: 4.41 / 4.30 / 4.06 ms for batches of 1 / 2 / 4).
-__device__ __forceinline__ void knn_scan_range(const GridView& g, const float4 qv, uint32_t begin, uint32_t end, uint64_t bound, uint64_t* h, int kk,
+template <typename Heap>
+__device__ __forceinline__ void knn_scan_range(const GridView& g, const float4 qv, uint32_t begin, uint32_t end, uint64_t bound, const Heap& h, int kk,
                                                int& cnt, uint64_t& tau, float& tau_d2) {
   for (uint32_t p0 = begin; p0 < end; p0 += S3D_KNN_BATCH) {
     float4 vb[S3D_KNN_BATCH];
@@ -85,15 +100,15 @@ __device__ __forceinline__ void knn_scan_range(const GridView& g, const float4 q
       const uint64_t ck = ((uint64_t)__float_as_uint(cd) << 32) | (uint64_t)__float_as_uint(v.w);
       if (cnt < kk) {
         if (ck <= bound) {
-          h[cnt * kKnnThreads] = ck; ++cnt; KSTAT(5, 1);
+          h.at(cnt) = ck; ++cnt; KSTAT(5, 1);
           if (cnt == kk) {
-            for (int i = heap_last_parent(kk); i >= 0; --i) heap_sift_down(h, kk, h[i * kKnnThreads], i);
-            tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
+            for (int i = heap_last_parent(kk); i >= 0; --i) heap_sift_down(h, kk, h.at(i), i);
+            tau = h.at(0); tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
           }
         }
       } else if (ck < tau) {
         heap_sift_down(h, kk, ck); KSTAT(6, 1);
-        tau = h[0]; tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
+        tau = h.at(0); tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
       }
     }
   }
@@ -102,7 +117,8 @@ __device__ __forceinline__ void knn_scan_range(const GridView& g, const float4 q
 // (Tried and dropped, B200: noting the occupied cells of the 27-block in a first lockstep pass and letting every lane scan its
 // noted cells back to back in a second pass — the variant that speeds up the 1-NN walk of nn_search.cuh by 4 % — costs the kNN
 // kernel 27 %: while the heap is filling nothing can be pruned, so all 27 cells are probed, and the list takes shared memory.)
-__device__ __forceinline__ int thread_walk(const GridView& g, const float4 qv, float ux, float uy, float uz, int L, uint64_t bound, uint64_t* h, int kk) {
+template <typename Heap>
+__device__ __forceinline__ int thread_walk(const GridView& g, const float4 qv, float ux, float uy, float uz, int L, uint64_t bound, const Heap& h, int kk) {
   int cnt = 0;
   for (;; ++L) {
     int cx, cy, cz;

@@ -78,7 +78,7 @@ Transform align(PointCloudMeasurement::Ptr source, PointCloudMeasurement::Ptr ta
   int st;
   bool use_cache;
   { std::lock_guard<std::mutex> g(g_cache_mutex); use_cache = g_cache_capacity > 0; }
-  if (use_cache && (config.registration_algorithm == GICP || config.registration_algorithm == GICP_OMP) && config.correspondence_randomness >= 1 && config.correspondence_randomness <= 200) {
+  if (use_cache && (config.registration_algorithm == GICP || config.registration_algorithm == GICP_OMP) && config.correspondence_randomness >= 1 && config.correspondence_randomness <= 4096) {
     std::shared_ptr<Prepared> ps = prepared(source->getPointCloud(), config.point_cloud_density, config.correspondence_randomness);
     std::shared_ptr<Prepared> pt = prepared(target->getPointCloud(), config.point_cloud_density, config.correspondence_randomness);
     st = s3d_gicp_align_prepared(defaultContext(), ps->h, pt->h, guess.data(), &c, &res);

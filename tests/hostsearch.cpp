@@ -117,7 +117,7 @@ void hs_knn(void* grid, int k, uint32_t* idx, float* d2) {
   const uint32_t n = g.n;
   const int kk = k < (int)n ? k : (int)n;
   std::vector<uint64_t> heap((size_t)k * s3d::kKnnThreads);
-  uint64_t* h = heap.data();
+  const s3d::SmemHeap h{heap.data()};
   for (uint32_t r = 0; r < n; ++r) {
     hs_trace_next_query(r);  // sorted position = thread number
     const float4 qv = g.pts[r];
@@ -126,16 +126,16 @@ void hs_knn(void* grid, int k, uint32_t* idx, float* d2) {
     const float uy = s3d::clamp_coord(s3d::grid_coord(qv.y, g.oy, g.inv_h0));
     const float uz = s3d::clamp_coord(s3d::grid_coord(qv.z, g.oz, g.inv_h0));
     const int cnt = s3d::thread_walk(g, qv, ux, uy, uz, s3d::knn_start_level(g, ux, uy, uz), s3d::KMAX, h, kk);
-    if (cnt < kk) for (int i = s3d::heap_last_parent(cnt); i >= 0; --i) s3d::heap_sift_down(h, cnt, h[i * s3d::kKnnThreads], i);
+    if (cnt < kk) for (int i = s3d::heap_last_parent(cnt); i >= 0; --i) s3d::heap_sift_down(h, cnt, h.at(i), i);
     for (int m = cnt - 1; m > 0; --m) {  // heapsort, as knn_finish
-      const uint64_t last = h[m * s3d::kKnnThreads];
-      h[m * s3d::kKnnThreads] = h[0];
+      const uint64_t last = h.at(m);
+      h.at(m) = h.at(0);
       s3d::heap_sift_down(h, m, last);
     }
     for (int j = 0; j < k; ++j) {
       const bool have = j < cnt;
-      idx[(size_t)q_orig * k + j] = have ? (uint32_t)h[j * s3d::kKnnThreads] : s3d::kNoIndex;
-      d2[(size_t)q_orig * k + j] = have ? __uint_as_float((uint32_t)(h[j * s3d::kKnnThreads] >> 32)) : INFINITY;
+      idx[(size_t)q_orig * k + j] = have ? (uint32_t)h.at(j) : s3d::kNoIndex;
+      d2[(size_t)q_orig * k + j] = have ? __uint_as_float((uint32_t)(h.at(j) >> 32)) : INFINITY;
     }
   }
 }

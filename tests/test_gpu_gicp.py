@@ -76,6 +76,7 @@ def test_gates_match_oracle(ctx, oracle_mod, kitti):
         dict(point_cloud_density=0.5, maximum_iterations=3, max_correspondence_distance=1.0),
         dict(point_cloud_density=0.5, correspondence_randomness=10),
         dict(point_cloud_density=0.5, correspondence_randomness=48),
+        dict(point_cloud_density=1.0, correspondence_randomness=256),  # beyond the shared-memory heap: global-memory heap, same result
         dict(point_cloud_density=0.5, maximum_optimizer_iterations=1),
         dict(point_cloud_density=0.5, rotation_epsilon=1e-5, transformation_epsilon=1e-7),
     ]
