@@ -6,6 +6,7 @@
 TAG=${1:-r02}
 B="python bench.py --steps 1 --warmup 1 --pairs 16 --distinct 4 --no-chain --no-cpu-baseline --no-extras"
 export S3D_STREAMS_PER_DEVICE=3   # fewer, larger chunks per launch: the captured launches then hold 5-6 pairs each
+export S3D_LOOP_MODE=3            # the per-pass kernels launched from the host: ncu does not see the kernel nodes inside a graph's WHILE body
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_${TAG}.csv $B > gpurun_out/b_launch_${TAG}.log 2>&1
 for K in knn_cov_kernel gicp_search_kernel; do
@@ -18,6 +19,6 @@ for K in knn_cov_kernel gicp_search_kernel; do
   ncu --set full --clock-control none --cache-control none -k regex:$K --launch-skip 4 -c 1 -f -o gpurun_out/${K}_warm_${TAG} $B > gpurun_out/b_${K}_warm_${TAG}.log 2>&1
 done
 # the persistent loop kernel of the single-call path (one pair) and the control kernel of the batch path
-ncu --set full --clock-control none --import-source on -k regex:gicp_loop_kernel --launch-skip 2 -c 1 -f -o gpurun_out/gicp_loop_kernel_${TAG} python scripts/single_pair.py > gpurun_out/b_gicp_loop_kernel_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gicp_loop_kernel --launch-skip 2 -c 1 -f -o gpurun_out/gicp_loop_kernel_${TAG} env -u S3D_LOOP_MODE python scripts/single_pair.py > gpurun_out/b_gicp_loop_kernel_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gicp_ctrl_kernel --launch-skip 6 -c 1 -f -o gpurun_out/gicp_ctrl_kernel_${TAG} $B > gpurun_out/b_gicp_ctrl_kernel_${TAG}.log 2>&1
 ls -la gpurun_out/*${TAG}*

@@ -13,5 +13,8 @@ out, li, ov = ctx.voxel_downsample(src, 0.3)
 idx, d2, cov = ctx.knn_covariances(out, 20)
 nn_i, nn_d = ctx.nearest_neighbors(out, out[::3])
 res = ctx.gicp_align_batch([src, tgt, src[:50]], [tgt, src, tgt], None, RegistrationParameters.defaults(point_cloud_density=0.3))
-print("sanitize smoke:", out.shape, idx.shape, [(r.status, r.outer_iterations) for r in res])
+one = ctx.gicp_align(src, tgt, None, RegistrationParameters.defaults(point_cloud_density=0.3))          # the persistent loop kernel (single call)
+comb = ctx.combined_measurement([src, tgt], [np.eye(4), np.eye(4)], np.eye(4))
+big_k = ctx.knn_covariances(out[::4], 210)                                                              # heap in global memory
+print("sanitize smoke:", out.shape, idx.shape, [(r.status, r.outer_iterations) for r in res], (one.status, one.outer_iterations), comb.shape, big_k[0].shape)
 ctx.close()

@@ -168,6 +168,14 @@ S3D_CELL_LOOP_PRAGMA
   return cnt;
 }
 
+// (Tried and dropped in round 2, B200: a two-pass walk without a heap — pass 1 histograms the squared distances of the points
+// within the block's certified radius into 32 bins of [0, g2], the bin in which the count reaches k bounds the k-th distance,
+// pass 2 collects everything up to that bin and drops the surplus.  Bit-exact on the host and on the device, 0.14 % of the queries
+// fall back to the heap walk — and 2.1x SLOWER: it executes as many warp instructions as the heap walk (477 M against 429 M per
+// launch: 129 + ~50 points scanned per query instead of 87, no pruning while counting), at 93 registers and 40 KB of shared
+// memory only 18 % of the warp slots are occupied, and with no heap work between the point loads 34 % of the stall samples sit on
+// the first use of a loaded point.  The heap is also what hides the load latency.  profiles/r02_summary.md.)
+
 // start level of a query: smallest L whose parent cell (level L+1) already holds >= 20 points (swept 8..40 on B200)
 __device__ __forceinline__ int knn_start_level(const GridView& g, float ux, float uy, float uz) {
   const int c0x = (int)floorf(ux), c0y = (int)floorf(uy), c0z = (int)floorf(uz);

@@ -173,3 +173,4 @@ def test_knn_walk_far_field_ties_and_small_clouds(hs, oracle_mod):
     oi, _ = oracle_mod.knn_bruteforce(tiny, tiny, 7)
     assert np.array_equal(idx[:, :7], oi) and np.all(idx[:, 7:] == NO_INDEX) and np.all(np.isinf(d2[:, 7:]))
     g.close()
+
