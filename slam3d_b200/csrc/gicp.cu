@@ -775,9 +775,8 @@ void check_arena(Workspace& ws, const int32_t* h_flags) {
   if (h_flags[0] & kErrHashArena) throw ArenaOverflow{(size_t)h_flags[3] + (size_t)h_flags[3] / 8 + 64};
 }
 
-static int loop_grid(int device) {
-  int sms = 0;
-  S3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+static int loop_grid(const Workspace& ws) {
+  const int sms = ws.n_sms;
   static const int per_sm = [] { const char* e = getenv("S3D_LOOP_CTAS_PER_SM"); return e ? std::max(1, atoi(e)) : 2; }();  // A/B measurements
   return std::max(1, sms) * per_sm;  // 2 resident CTAs per SM (128 registers, 46 KB shared memory)
 }
@@ -914,7 +913,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   const GicpArgs dargs = *ha;
   if (!throughput) {
     StageTimer timer(ws, kStageIter);
-    gicp_loop_kernel<<<loop_grid(ws.device), kIterTile, kSmLoop, st>>>(dargs);
+    gicp_loop_kernel<<<loop_grid(ws), kIterTile, kSmLoop, st>>>(dargs);
     ++ws.launches;
     S3D_CUDA(cudaGetLastError());
   } else {

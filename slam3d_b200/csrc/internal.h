@@ -113,6 +113,7 @@ constexpr int kIterTile = 256;   // source points per CTA in the fused correspon
 // All device memory of one in-flight batch on one device.
 struct Workspace {
   int device = 0;
+  int n_sms = 148;                            // cudaDevAttrMultiProcessorCount of `device` (grid sizes of the grid-stride kernels)
   cudaStream_t stream = nullptr;
   cudaEvent_t sync_event = nullptr;           // cudaEventBlockingSync: a worker of a batch call sleeps in sync() instead of spinning on the stream
   bool blocking_sync = false;                 // set for the chunks of multi-threaded batch calls (many host threads per device, several ranks per box)

@@ -18,6 +18,7 @@ namespace s3d {
 void Workspace::init(int dev) {
   device = dev;
   S3D_CUDA(cudaSetDevice(dev));
+  S3D_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
   S3D_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   S3D_CUDA(cudaEventCreateWithFlags(&sync_event, cudaEventBlockingSync | cudaEventDisableTiming));
   S3D_CUDA(cudaEventCreateWithFlags(&input_event, cudaEventDisableTiming));
@@ -509,7 +510,7 @@ void run_voxel(Workspace& ws, float leaf, uint32_t* leaf_keys) {
     voxel_gather_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, vals[0], sorted);
     voxel_centroid_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, keys[0], sorted, ws.tile_heads.as<uint32_t>(), ws.work.as<float4>(),
                                                                ws.long_runs.as<uint4>(), n_long);
-    voxel_long_centroid_kernel<<<148 * 2, 256, 0, st>>>(slots, keys[0], sorted, ws.work.as<float4>(), ws.long_runs.as<uint4>(), n_long);
+    voxel_long_centroid_kernel<<<ws.n_sms * 2, 256, 0, st>>>(slots, keys[0], sorted, ws.work.as<float4>(), ws.long_runs.as<uint4>(), n_long);
     ws.launches += 5;
   }
   voxel_passthrough_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.work.as<float4>());

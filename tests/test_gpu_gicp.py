@@ -230,3 +230,57 @@ def test_loop_batch_equals_two_batches(ctx, kitti):
     dc, df = ctx.gicp_align_loop_batch(ds, dt_, None, coarse, fine)
     for i in range(3):
         assert np.array_equal(df[i].pose(), rf[i].pose())
+
+
+def test_batch_error_text_reaches_the_caller(ctx, kitti):
+    """A per-pair status >= 4 inside a batch that ran (the call itself returns S3D_OK) leaves its message on the CALLING thread
+    (the chunks run on worker threads; round 1 lost the text there)."""
+    import slam3d_b200
+    src, tgt = kitti[0][::4], kitti[1][::4]
+    p = RegistrationParameters.defaults(point_cloud_density=0.5, registration_algorithm=_abi.ALG_ICP)
+    res = ctx.gicp_align_batch([src, src, src, src], [tgt, tgt, tgt, tgt], None, p)
+    assert all(r.status == _abi.S3D_UNKNOWN_ALGORITHM for r in res)
+    assert "Unknown registration algorithm" in slam3d_b200.last_error()
+    p = RegistrationParameters.defaults(point_cloud_density=0.5, correspondence_randomness=5000)
+    res = ctx.gicp_align_batch([src, src, src], [tgt, tgt, tgt], None, p)
+    assert all(r.status == _abi.S3D_INVALID_ARGUMENT for r in res) and "correspondence_randomness" in slam3d_b200.last_error()
+
+
+def test_device_inputs_are_ordered_after_the_producing_stream(ctx, kitti):
+    """Device-pointer inputs are read on the library's own streams: the Python wrapper names torch's current stream
+    (s3d_set_input_stream), so a cloud that is still being produced there when the call starts is waited for."""
+    import torch
+    import slam3d_b200
+    p = RegistrationParameters.defaults(point_cloud_density=0.5)
+    src = torch.from_numpy(slam3d_b200.as_xyzw(kitti[0][::2])).pin_memory()
+    tgt = torch.from_numpy(slam3d_b200.as_xyzw(kitti[1][::2])).pin_memory()
+    want = ctx.gicp_align(src, tgt, None, p)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        junk = torch.empty(64 * 1024 * 1024, device="cuda")
+        for _ in range(20):
+            junk.normal_()                      # keeps the side stream busy while the copies below are queued behind it
+        d_src = src.cuda(non_blocking=True)
+        d_tgt = tgt.cuda(non_blocking=True)
+        got = ctx.gicp_align(d_src, d_tgt, None, p)   # no synchronisation on the caller's side
+    assert got.status == want.status == 0 and np.array_equal(got.pose(), want.pose()) and got.fitness == want.fitness
+
+
+def test_watchdog_reports_a_stalled_loop_as_internal_error():
+    """A loop kernel that waits longer than the watchdog allows ends with an error flag instead of hanging, and the pair is
+    reported as S3D_INTERNAL_ERROR — never as a NoMatch.  Forced here by a watchdog of zero cycles."""
+    import subprocess, sys, os
+    code = (
+        "import numpy as np, slam3d_b200\n"
+        "from slam3d_b200 import synth\n"
+        "from slam3d_b200._abi import RegistrationParameters\n"
+        "s, t, _ = synth.scan_pair(seed=3)\n"
+        "ctx = slam3d_b200.Context()\n"
+        "try:\n"
+        "    r = ctx.gicp_align(s[::8], t[::8], None, RegistrationParameters.defaults(point_cloud_density=0.3))\n"
+        "    print('STATUS', r.status)\n"
+        "except slam3d_b200.S3DError as e:\n"
+        "    print('ERROR', e)\n")
+    env = dict(os.environ, S3D_WATCHDOG_MCYCLES="0")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
+    assert "watchdog" in out.stdout or "STATUS 5" in out.stdout, out.stdout + out.stderr
