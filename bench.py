@@ -205,8 +205,10 @@ def main():
     from slam3d_b200 import _abi, sharding, synth
 
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")  # host-side barrier for the in-process leg: an NCCL barrier keeps the waiting GPUs busy
     in_process = args.in_process and world == 1 and args.gpus > 1
     devices = list(range(args.gpus)) if in_process else [local_rank]
     n_dev = len(devices)
@@ -274,6 +276,8 @@ def main():
 
     stream = torch.cuda.ExternalStream(ctx.stream_handle(0), device=torch.device("cuda", devices[0]))
 
+    rank_ms = []
+
     def timed(srcs, tgts, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -284,9 +288,14 @@ def main():
         for _ in range(steps):
             last = ctx.gicp_align_batch(srcs, tgts, None, p)
         e1.record(stream)
+        local = 1e3 * (time.perf_counter() - t0)  # this rank alone, before the closing barrier (the calls are synchronous)
         barrier()
         wall = time.perf_counter() - t0
         ms = max(e0.elapsed_time(e1), 0.0)
+        if world > 1:  # the spread over ranks next to the max the contract asks for: GPU-to-GPU variation vs. contention
+            g = [torch.zeros(1, device="cuda") for _ in range(world)]
+            dist.all_gather(g, torch.tensor([local / steps], device="cuda"))
+            rank_ms[:] = [round(float(x), 3) for x in g]
         c1 = ctx.counters()
         # the call is synchronous and uses several streams: the wall span covers the device span; max over ranks
         el = sharding.max_over_ranks(max(ms, 1e3 * wall), device="cuda")
@@ -300,6 +309,7 @@ def main():
             ctx.gicp_align_batch(dev_src, dev_tgt, None, p)
         ev_ms, wall_ms, cnt, last = timed(dev_src, dev_tgt, args.steps)
     value = world * B * args.steps / (wall_ms / 1e3)
+    rank_ms_value = list(rank_ms)  # of the device-resident timed region (later timed() calls overwrite rank_ms)
     ok = sum(1 for r in last if r.status == _abi.S3D_OK)
 
     # per-kernel durations for the roofline: same workload, same process, right after the timed region, but on ONE stream
@@ -377,7 +387,9 @@ def main():
         extras["c4_loop_closure_256_pairs"] = bench_c4(ctx, args, rank, world, n_dev, headline=False, barrier=barrier)
         if world > 1:
             # ---- the in-process multi-device path: ONE process (rank 0) shards a batch over all N GPUs through one context -------
+            # (the other ranks wait on the HOST — gloo — so that their GPUs are really idle)
             barrier()
+            dist.barrier(group=cpu_group)
             if rank == 0:
                 ctx_all = slam3d_b200.Context(list(range(world)))
                 bsrc = [host_src[i % len(host_src)] for i in range(args.pairs * world)]
@@ -394,6 +406,7 @@ def main():
                     "registrations_ok": sum(1 for r in rr if r.status == _abi.S3D_OK),
                     "what": "s3d_create_context(devices = all N) in ONE process, pinned host scans in, results out; the other ranks idle"}
                 ctx_all.close()
+            dist.barrier(group=cpu_group)
             barrier()
 
     if rank != 0:
@@ -450,7 +463,7 @@ def main():
         "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64",
         "data": "synthetic",
         "config": {"workload": "synthetic 64-beam LiDAR scan pair, 131072 points, 0.1 m voxel, GICP odometry (BASELINE.json configs[1])",
-                   "pairs_per_step_per_gpu": args.pairs, "distinct_scenes": args.distinct, "ms_per_align": wall_ms / args.steps / B,
+                   "rank_ms_per_step": rank_ms_value, "pairs_per_step_per_gpu": args.pairs, "distinct_scenes": args.distinct, "ms_per_align": wall_ms / args.steps / B,
                    "processes": "one process, one context over all devices (--in-process)" if in_process else "one process per GPU",
                    "l2": f"inputs larger than L2: {args.pairs} pairs x 4.2 MB raw + ~50 MB working set per pair per step",
                    "registrations_ok": ok, "mean_outer_iterations": float(np.mean([r.outer_iterations for r in last])),

@@ -69,6 +69,30 @@ __device__ __forceinline__ void heap_sift_down(const Heap& h, int n, uint64_t x,
   h.at(i) = x;
 }
 
+// Replace-the-root for the one shape that matters — a 4-ary heap of exactly 20 keys (PCL's default k): root, nodes 1..4, leaves
+// 5..19 (node 4 has three children).  Same result as heap_sift_down(h, 20, x), without its loop, bounds and clamps (the generic
+// sift-down was 30 % of the kernel's warp instructions at 6.6 of 32 lanes, profiles/r02_summary.md); returns the new root.
+template <typename Heap>
+__device__ __forceinline__ uint64_t heap_replace_root_20(const Heap& h, uint64_t x) {
+  const uint64_t a1 = h.at(1), a2 = h.at(2), a3 = h.at(3), a4 = h.at(4);
+  int c = 1;
+  uint64_t hc = a1;
+  if (a2 > hc) { hc = a2; c = 2; }
+  if (a3 > hc) { hc = a3; c = 3; }
+  if (a4 > hc) { hc = a4; c = 4; }
+  if (hc <= x) { h.at(0) = x; return x; }
+  h.at(0) = hc;
+  const int c0 = 4 * c + 1;  // 5, 9, 13 or 17
+  const uint64_t b1 = h.at(c0), b2 = h.at(c0 + 1), b3 = h.at(c0 + 2), b4 = c < 4 ? h.at(c0 + 3) : 0ull;  // node 20 does not exist
+  int d = c0;
+  uint64_t hd = b1;
+  if (b2 > hd) { hd = b2; d = c0 + 1; }
+  if (b3 > hd) { hd = b3; d = c0 + 2; }
+  if (b4 > hd) { hd = b4; d = c0 + 3; }
+  if (hd <= x) { h.at(c) = x; } else { h.at(c) = hd; h.at(d) = x; }
+  return hc;
+}
+
 // ---- per-thread walk ---------------------------------------------------------------------------------------------
 // One query, one thread: scans the 27-block around the query at level L and widens by doubling the cell size until the
 // k-th distance is certified by the block's coverage radius (nn_search.cuh).  Candidates are (d2, original index)
@@ -107,8 +131,10 @@ __device__ __forceinline__ void knn_scan_range(const GridView& g, const float4 q
           }
         }
       } else if (ck < tau) {
-        heap_sift_down(h, kk, ck); KSTAT(6, 1);
-        tau = h.at(0); tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
+        KSTAT(6, 1);
+        if (kHeapD == 4 && kk == 20) tau = heap_replace_root_20(h, ck);
+        else { heap_sift_down(h, kk, ck); tau = h.at(0); }
+        tau_d2 = __uint_as_float((uint32_t)(tau >> 32));
       }
     }
   }
