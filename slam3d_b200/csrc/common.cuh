@@ -142,4 +142,14 @@ __device__ __forceinline__ bool cell_range(const HashEntry* __restrict__ table, 
 // Continuous cell coordinate of a point at level 0 (same expression in key generation and in every query).
 __device__ __forceinline__ float grid_coord(float v, float origin, float inv_h0) { return __fmul_rn(__fsub_rn(v, origin), inv_h0); }
 
+// Look-back state of a workspace (buffers are owned by the caller).  `aux`: kSortPasses * n_slots * 256 digit totals followed by
+// kSortPasses tickets; `status`: n_tiles * 256 words, zero when (re)allocated; `epoch`: bumped once per pass, never reused.
+struct SortState {
+  uint32_t* aux;
+  uint64_t* status;
+  size_t status_words;  // capacity of `status`
+  uint32_t* epoch;
+  int32_t* flags;
+};
+
 }  // namespace s3d

@@ -772,6 +772,7 @@ static double rotation_angle(const double T[16]) {
 double rotation_angle_of(const double T[16]) { return rotation_angle(T); }  // shared with ndt.cu
 
 void check_arena(Workspace& ws, const int32_t* h_flags) {
+  if (h_flags[0] & kErrSortStall) throw CudaError{"radix sort: look-back spin limit reached (scheduler fault)"};
   if (h_flags[0] & kErrHashArena) throw ArenaOverflow{(size_t)h_flags[3] + (size_t)h_flags[3] / 8 + 64};
 }
 

@@ -167,7 +167,7 @@ void run_grid(Workspace& ws, float leaf_hint) {
   uint32_t* vals[2] = {ws.vals0.as<uint32_t>(), ws.vals1.as<uint32_t>()};
   grid_keys_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.work.as<float4>(), keys[0]);
   ws.launches += 2;
-  radix_sort_segmented(st, slots, ws.n_slots, tm, ws.slot_tile_begin.as<uint32_t>(), keys, vals, ws.hist.as<uint32_t>(), ws.sort_totals.as<uint32_t>(), 4, kCountPts, &ws.launches);
+  radix_sort_segmented(st, slots, ws.n_slots, tm, ws.slot_tile_begin.as<uint32_t>(), keys, vals, ws.sort_state(), kCountPts, /*digits_done=*/false, &ws.launches);
   grid_gather_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.work.as<float4>(), keys[0], vals[0], ws.gpts.as<float4>());
   hash_layout_kernel<<<1, 32, 0, st>>>(slots, ws.n_slots, (uint32_t)std::min<size_t>(ws.hash_cap, 0xFFFFFFF0u), ws.flags.as<int32_t>());
   hash_clear_kernel<<<ws.n_sms * 4, 256, 0, st>>>(ws.hash.as<HashEntry>(), ws.flags.as<int32_t>());

@@ -129,8 +129,10 @@ struct Workspace {
   DevBuf raw_stage;                           // float4[total]   H2D landing zone for host inputs
   DevBuf work, gpts;                          // float4[total]
   DevBuf keys0, keys1, vals0, vals1;          // uint32[total]
-  DevBuf hist;                                // uint32[n_tiles*256]
-  DevBuf sort_totals;                         // uint32[4 passes * n_slots * 256]
+  DevBuf hist;                                // uint64[n_tiles*256]: look-back status words of the radix sort (sort.cuh), zero when (re)allocated
+  DevBuf sort_totals;                         // uint32[4 passes * n_slots * 256] digit totals + 4 tile tickets
+  uint32_t sort_epoch = 0;                    // bumped once per sort pass: tags the status words, so that they are never cleared
+  size_t status_words = 0;
   DevBuf long_runs;                           // uint4[total/64]  voxels with more than 64 points: (slot, first sorted position, output rank)
   DevBuf tile_slot, tile_first, slot_tile_begin, tile_heads;
   DevBuf hash;                                // HashEntry[hash_cap]
@@ -171,11 +173,12 @@ struct Workspace {
 
   void init(int dev);
   void destroy();
+  SortState sort_state() { return SortState{sort_totals.as<uint32_t>(), hist.as<uint64_t>(), status_words, &sort_epoch, flags.as<int32_t>()}; }
   void sync();  // wait for everything enqueued on `stream`
   void order_after_input();  // s3d_set_input_stream: enqueue a wait for what the caller's stream holds now
 };
 
-enum ErrorBits { kErrHashArena = 1, kErrWatchdog = 2 };
+enum ErrorBits { kErrHashArena = 1, kErrWatchdog = 2, kErrSortStall = 4 };
 enum PairPhase { kPhaseNeedNN = 0, kPhaseEval = 1, kPhaseFinished = 2, kPhaseFitness = 3 };
 constexpr int kEvalSums = 13;  // sums 60..72 of gicp_math.h: the residual-dependent part of an evaluation (per trial)
 enum Stage { kStageVoxel = 0, kStageGrid = 1, kStageKnn = 2, kStageIter = 3, kStageSolve = 4, kStageFitness = 5 };

@@ -530,8 +530,8 @@ void run_ndt(Workspace& ws, const std::vector<s3d_registration_parameters>& para
     ndt_params_kernel<<<(np + 63) / 64, 64, 0, st>>>(slots, pairs, np);
     ndt_keys_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.work.as<float4>(), pairs, keys[0]);
     ws.launches += 2;
-    radix_sort_segmented(st, slots, ws.n_slots, tm, ws.slot_tile_begin.as<uint32_t>(), keys, vals, ws.hist.as<uint32_t>(), ws.sort_totals.as<uint32_t>(), 4,
-                         kCountPts, &ws.launches);
+    radix_sort_segmented(st, slots, ws.n_slots, tm, ws.slot_tile_begin.as<uint32_t>(), keys, vals, ws.sort_state(), kCountPts, /*digits_done=*/false,
+                         &ws.launches);
     ndt_heads_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, pairs, keys[0], ws.tile_heads.as<uint32_t>());
     ndt_scan_kernel<<<np, 32, 0, st>>>(slots, pairs, ws.slot_tile_begin.as<uint32_t>(), ws.tile_heads.as<uint32_t>());
     ndt_hash_clear_kernel<<<dim3(32, np), 256, 0, st>>>(pairs, table);

@@ -115,8 +115,15 @@ void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const s
   ws.max_na = 0;
   for (uint32_t p = 0; p < n_pairs; ++p) { ws.pair_off[p] = ws.h_off[2 * p + 1]; ws.max_na = std::max(ws.max_na, ws.h_n[2 * p + 1]); }
   ws.keys0.reserve(4 * tot); ws.keys1.reserve(4 * tot); ws.vals0.reserve(4 * tot); ws.vals1.reserve(4 * tot);
-  ws.hist.reserve(sizeof(uint32_t) * 256 * std::max<uint32_t>(n_tiles, 1));
-  ws.sort_totals.reserve(sizeof(uint32_t) * 256 * 4 * std::max<uint32_t>(ns, 1));
+  {
+    const size_t words = 256 * size_t(std::max<uint32_t>(n_tiles, 1));
+    if (words > ws.status_words) {  // new memory must not hold words that look like a current epoch
+      ws.hist.reserve(sizeof(uint64_t) * words);
+      ws.status_words = ws.hist.cap / sizeof(uint64_t);
+      S3D_CUDA(cudaMemsetAsync(ws.hist.p, 0, ws.hist.cap, ws.stream));
+    }
+  }
+  ws.sort_totals.reserve(sort_aux_bytes(std::max<uint32_t>(ns, 1)));
   ws.long_runs.reserve(sizeof(uint4) * (tot / 64 + ns + 1));
   ws.tile_slot.reserve(4 * std::max<uint32_t>(n_tiles, 1)); ws.tile_first.reserve(4 * std::max<uint32_t>(n_tiles, 1));
   ws.tile_heads.reserve(4 * std::max<uint32_t>(n_tiles, 1));
@@ -271,11 +278,17 @@ __global__ void voxel_params_kernel(SlotInfo* __restrict__ slots, uint32_t n_slo
 }
 
 // A.1 step 5
-__global__ void __launch_bounds__(kSortThreads) voxel_keys_kernel(const SlotInfo* __restrict__ slots, TileMap tm, uint32_t* __restrict__ keys) {
+// + the digit totals of all four sort passes (sort.cuh), so that the sort never reads the keys just to count them
+__global__ void __launch_bounds__(kSortThreads) voxel_keys_kernel(const SlotInfo* __restrict__ slots, TileMap tm, uint32_t n_slots, uint32_t* __restrict__ keys,
+                                                                   uint32_t* __restrict__ totals) {
+  __shared__ uint32_t sh[kSortPasses][256];
   const uint32_t t = blockIdx.x;
   const uint32_t slot = tm.tile_slot[t], first = tm.tile_first[t];
   const SlotInfo& si = slots[slot];
   if (si.overflow) return;
+#pragma unroll
+  for (int p = 0; p < kSortPasses; ++p) sh[p][threadIdx.x] = 0;
+  __syncthreads();
   const float inv = si.inv_leaf;
   const float mb0 = (float)si.min_b[0], mb1 = (float)si.min_b[1], mb2 = (float)si.min_b[2];
 #pragma unroll
@@ -291,8 +304,11 @@ __global__ void __launch_bounds__(kSortThreads) voxel_keys_kernel(const SlotInfo
         key = (uint32_t)i0 + (uint32_t)i1 * si.mul1 + (uint32_t)i2 * si.mul2;
       }
       keys[si.off + e] = key;
+      count_digits(sh, key);
     }
   }
+  __syncthreads();
+  flush_digits(sh, totals, n_slots, slot);
 }
 
 // run starts among the first n_finite sorted keys -> count per tile
@@ -499,10 +515,12 @@ void run_voxel(Workspace& ws, float leaf, uint32_t* leaf_keys) {
     uint32_t* keys[2] = {ws.keys0.as<uint32_t>(), ws.keys1.as<uint32_t>()};
     uint32_t* vals[2] = {ws.vals0.as<uint32_t>(), ws.vals1.as<uint32_t>()};
     if (leaf_keys) S3D_CUDA(cudaMemsetAsync(keys[0], 0xFF, 4 * size_t(ws.total), st));  // skipped / overflow points report 0xFFFFFFFF
-    voxel_keys_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, keys[0]);
+    const SortState ss = ws.sort_state();
+    sort_clear_aux(st, ss, ws.n_slots);
+    voxel_keys_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.n_slots, keys[0], ss.aux);
     ++ws.launches;
     if (leaf_keys) S3D_CUDA(cudaMemcpyAsync(leaf_keys, keys[0], 4 * size_t(ws.total), cudaMemcpyDeviceToDevice, st));
-    radix_sort_segmented(st, slots, ws.n_slots, tm, ws.slot_tile_begin.as<uint32_t>(), keys, vals, ws.hist.as<uint32_t>(), ws.sort_totals.as<uint32_t>(), 4, kCountRaw, &ws.launches);
+    radix_sort_segmented(st, slots, ws.n_slots, tm, ws.slot_tile_begin.as<uint32_t>(), keys, vals, ss, kCountRaw, /*digits_done=*/true, &ws.launches);
     voxel_heads_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, keys[0], ws.tile_heads.as<uint32_t>());
     voxel_scan_kernel<<<ws.n_slots, 32, 0, st>>>(slots, ws.n_slots, ws.slot_tile_begin.as<uint32_t>(), ws.tile_heads.as<uint32_t>());
     uint32_t* n_long = ws.flags.as<uint32_t>() + 8;  // flags[8]: number of queued long runs (flags are zeroed by setup_batch)
