@@ -11,14 +11,15 @@
 // gpts[] holds the sorted points as float4 with the ORIGINAL index bit-cast into .w, so one 16-byte coalesced load
 // yields both the coordinates and the tie-break key.
 #include "internal.h"
+#include "bbox.cuh"
 #include "sort.cuh"
 
 namespace s3d {
 
-__global__ void grid_params_kernel(SlotInfo* __restrict__ slots, uint32_t n_slots, float leaf_hint) {
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_slots) return;
-  SlotInfo& si = slots[s];
+// run per slot by the last CTA of the bbox launch (bbox.cuh)
+struct GridParams {
+  float leaf_hint;
+  __device__ void operator()(SlotInfo& si) const {
   float ext = 0.f, amax = 0.f;
   for (int a = 0; a < 3; ++a) {
     si.g_min[a] = ordered_to_float(reinterpret_cast<uint32_t&>(si.g_min[a]));
@@ -41,7 +42,8 @@ __global__ void grid_params_kernel(SlotInfo* __restrict__ slots, uint32_t n_slot
   if (h0 * (float)(1 << nlev) <= span) h0 = span / (float)(1 << nlev);
   si.h0 = h0; si.inv_h0 = 1.0f / h0; si.nlev = nlev;
   si.margin = 1e-4f * h0 + 16.f * 1.1920929e-7f * (amax + ext);
-}
+  }
+};
 
 __device__ __forceinline__ int cell_of(float u, int dim) {
   // u >= 0 inside the bbox; NaN -> 0; clamp keeps non-finite / out-of-box inputs inside the key range
@@ -161,8 +163,8 @@ void run_grid(Workspace& ws, float leaf_hint) {
   StageTimer timer(ws, kStageGrid);
   SlotInfo* slots = ws.slots.as<SlotInfo>();
   TileMap tm{ws.tile_slot.as<uint32_t>(), ws.tile_first.as<uint32_t>(), ws.n_tiles};
-  launch_bbox(ws, kCountPts);
-  grid_params_kernel<<<(ws.n_slots + 63) / 64, 64, 0, st>>>(slots, ws.n_slots, leaf_hint);
+  uint32_t* bbox_done = ws.flags.as<uint32_t>() + 10;  // zero between launches (bbox.cuh)
+  bbox_kernel<kCountPts><<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.work.as<float4>(), ws.n_slots, bbox_done, GridParams{leaf_hint});
   uint32_t* keys[2] = {ws.keys0.as<uint32_t>(), ws.keys1.as<uint32_t>()};
   uint32_t* vals[2] = {ws.vals0.as<uint32_t>(), ws.vals1.as<uint32_t>()};
   grid_keys_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.work.as<float4>(), keys[0]);

@@ -10,6 +10,7 @@
 //   centroid  one thread per run sums its points in ascending input order in float, / float(count)   A.1 steps 8,9
 // All kernels are streaming and HBM/L2-bandwidth bound: 16 B/point in, 8 B/point keys, 16 B/voxel out.
 #include "internal.h"
+#include "bbox.cuh"
 #include "sort.cuh"
 
 namespace s3d {
@@ -196,86 +197,33 @@ void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const s
   S3D_CUDA(cudaMemsetAsync(ws.flags.p, 0, 64, ws.stream));
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// bbox over finite points of the raw cloud (which = kCountRaw -> bb_*) or the working cloud (kCountPts -> g_*)
-__global__ void __launch_bounds__(kSortThreads) bbox_kernel(SlotInfo* __restrict__ slots, TileMap tm, const float4* __restrict__ work, int which) {
-  const uint32_t t = blockIdx.x;
-  const uint32_t slot = tm.tile_slot[t], first = tm.tile_first[t];
-  SlotInfo& si = slots[slot];
-  const uint32_t n = slot_count(si, which);
-  if (first >= n) return;
-  const float4* p = which == kCountRaw ? si.raw : work + si.off;
-  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-  uint32_t cnt = 0;
-#pragma unroll
-  for (int j = 0; j < kSortTile / kSortThreads; ++j) {
-    const uint32_t e = first + j * kSortThreads + threadIdx.x;
-    if (e < n) {
-      const float4 v = p[e];
-      if (finite3(v.x, v.y, v.z)) {
-        ++cnt;
-        mn[0] = fminf(mn[0], v.x); mn[1] = fminf(mn[1], v.y); mn[2] = fminf(mn[2], v.z);
-        mx[0] = fmaxf(mx[0], v.x); mx[1] = fmaxf(mx[1], v.y); mx[2] = fmaxf(mx[2], v.z);
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
+// A.1 steps 1, 3, 4 — run per slot by the last CTA of the bbox launch (bbox.cuh).  leaf <= 0: no filtering, the working cloud is the raw cloud.
+struct VoxelParams {
+  float leaf;
+  __device__ void operator()(SlotInfo& si) const {
     for (int a = 0; a < 3; ++a) {
-      mn[a] = fminf(mn[a], __shfl_xor_sync(0xFFFFFFFFu, mn[a], o));
-      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xFFFFFFFFu, mx[a], o));
+      si.bb_min[a] = ordered_to_float(reinterpret_cast<uint32_t&>(si.bb_min[a]));
+      si.bb_max[a] = ordered_to_float(reinterpret_cast<uint32_t&>(si.bb_max[a]));
     }
-    cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-  }
-  // one set of atomics per CTA (8192 warps hammering 7 addresses cost 40 us on a 2M-point cloud)
-  __shared__ float smn[8][3], smx[8][3];
-  __shared__ uint32_t scnt[8];
-  const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) { for (int a = 0; a < 3; ++a) { smn[w][a] = mn[a]; smx[w][a] = mx[a]; } scnt[w] = cnt; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < 8; ++i) {
-      for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], smn[i][a]); mx[a] = fmaxf(mx[a], smx[i][a]); }
-      cnt += scnt[i];
+    if (!(leaf > 0.f)) { si.overflow = 1; si.n_pts = si.n_raw; return; }  // pass-through (treated like the overflow copy)
+    if (si.n_finite == 0) { si.n_pts = 0; si.overflow = 0; return; }
+    const float inv = __fdiv_rn(1.0f, leaf);
+    si.inv_leaf = inv;
+    const long long dx = (long long)__fmul_rn(__fsub_rn(si.bb_max[0], si.bb_min[0]), inv) + 1;
+    const long long dy = (long long)__fmul_rn(__fsub_rn(si.bb_max[1], si.bb_min[1]), inv) + 1;
+    const long long dz = (long long)__fmul_rn(__fsub_rn(si.bb_max[2], si.bb_min[2]), inv) + 1;
+    if (dx * dy * dz > 2147483647ll) { si.overflow = 1; si.n_pts = si.n_raw; return; }  // "output = *input_"
+    int div_b[3];
+    for (int a = 0; a < 3; ++a) {
+      si.min_b[a] = (int)floorf(__fmul_rn(si.bb_min[a], inv));
+      const int max_b = (int)floorf(__fmul_rn(si.bb_max[a], inv));
+      div_b[a] = max_b - si.min_b[a] + 1;
     }
-    if (cnt) {
-      uint32_t* dmin = reinterpret_cast<uint32_t*>(which == kCountRaw ? si.bb_min : si.g_min);
-      uint32_t* dmax = reinterpret_cast<uint32_t*>(which == kCountRaw ? si.bb_max : si.g_max);
-#pragma unroll
-      for (int a = 0; a < 3; ++a) { atomicMin(&dmin[a], float_to_ordered(mn[a])); atomicMax(&dmax[a], float_to_ordered(mx[a])); }
-      if (which == kCountRaw) atomicAdd(&si.n_finite, cnt);
-    }
+    si.mul1 = (uint32_t)div_b[0];
+    si.mul2 = (uint32_t)div_b[0] * (uint32_t)div_b[1];
+    si.overflow = 0;
   }
-}
-
-// A.1 steps 1, 3, 4 — one thread per slot.  leaf <= 0: no filtering, the working cloud is the raw cloud.
-__global__ void voxel_params_kernel(SlotInfo* __restrict__ slots, uint32_t n_slots, float leaf) {
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_slots) return;
-  SlotInfo& si = slots[s];
-  for (int a = 0; a < 3; ++a) {
-    si.bb_min[a] = ordered_to_float(reinterpret_cast<uint32_t&>(si.bb_min[a]));
-    si.bb_max[a] = ordered_to_float(reinterpret_cast<uint32_t&>(si.bb_max[a]));
-  }
-  if (!(leaf > 0.f)) { si.overflow = 1; si.n_pts = si.n_raw; return; }  // pass-through (treated like the overflow copy)
-  if (si.n_finite == 0) { si.n_pts = 0; si.overflow = 0; return; }
-  const float inv = __fdiv_rn(1.0f, leaf);
-  si.inv_leaf = inv;
-  const long long dx = (long long)__fmul_rn(__fsub_rn(si.bb_max[0], si.bb_min[0]), inv) + 1;
-  const long long dy = (long long)__fmul_rn(__fsub_rn(si.bb_max[1], si.bb_min[1]), inv) + 1;
-  const long long dz = (long long)__fmul_rn(__fsub_rn(si.bb_max[2], si.bb_min[2]), inv) + 1;
-  if (dx * dy * dz > 2147483647ll) { si.overflow = 1; si.n_pts = si.n_raw; return; }  // "output = *input_"
-  int div_b[3];
-  for (int a = 0; a < 3; ++a) {
-    si.min_b[a] = (int)floorf(__fmul_rn(si.bb_min[a], inv));
-    const int max_b = (int)floorf(__fmul_rn(si.bb_max[a], inv));
-    div_b[a] = max_b - si.min_b[a] + 1;
-  }
-  si.mul1 = (uint32_t)div_b[0];
-  si.mul2 = (uint32_t)div_b[0] * (uint32_t)div_b[1];
-  si.overflow = 0;
-}
+};
 
 // A.1 step 5
 // + the digit totals of all four sort passes (sort.cuh), so that the sort never reads the keys just to count them
@@ -311,99 +259,69 @@ __global__ void __launch_bounds__(kSortThreads) voxel_keys_kernel(const SlotInfo
   flush_digits(sh, totals, n_slots, slot);
 }
 
-// run starts among the first n_finite sorted keys -> count per tile
-__global__ void __launch_bounds__(kSortThreads) voxel_heads_kernel(const SlotInfo* __restrict__ slots, TileMap tm,
-                                                                    const uint32_t* __restrict__ keys, uint32_t* __restrict__ tile_heads) {
-  __shared__ uint32_t wsum[8];
-  const uint32_t t = blockIdx.x;
-  const uint32_t slot = tm.tile_slot[t], first = tm.tile_first[t];
-  const SlotInfo& si = slots[slot];
-  if (si.overflow) return;
-  const uint32_t n = si.n_finite;
-  const uint32_t* k = keys + si.off;
-  uint32_t c = 0;
-#pragma unroll
-  for (int j = 0; j < kSortTile / kSortThreads; ++j) {
-    const uint32_t e = first + j * kSortThreads + threadIdx.x;
-    if (e < n) c += (e == 0 || k[e] != k[e - 1]) ? 1u : 0u;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) { uint32_t s = 0; for (int i = 0; i < 8; ++i) s += wsum[i]; tile_heads[t] = s; }
-}
-
-// exclusive scan of the tile counts of each slot (one warp per slot); n_pts = number of voxels
-__global__ void voxel_scan_kernel(SlotInfo* __restrict__ slots, uint32_t n_slots, const uint32_t* __restrict__ slot_tile_begin,
-                                  uint32_t* __restrict__ tile_heads) {
-  const uint32_t s = blockIdx.x;
-  if (s >= n_slots) return;
-  SlotInfo& si = slots[s];
-  if (si.overflow) return;
-  const uint32_t ntiles = (si.n_finite + kSortTile - 1) / kSortTile;
-  uint32_t* h = tile_heads + slot_tile_begin[s];
-  const int lane = threadIdx.x;
-  uint32_t running = 0;
-  for (uint32_t b = 0; b < ntiles; b += 32) {
-    const uint32_t t = b + lane;
-    const uint32_t v = t < ntiles ? h[t] : 0u;
-    uint32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += u; }
-    if (t < ntiles) h[t] = running + incl - v;
-    running += __shfl_sync(0xFFFFFFFFu, incl, 31);
-  }
-  if (lane == 0) si.n_pts = running;
-}
-
 // A.1 steps 8-9: float centroid per run (voxel), summed in ascending input order — (((p0 + p1) + p2) + ...) exactly as
-// PCL's CentroidPoint — and written in ascending key order.  Two kernels:
-//   voxel_centroid_kernel       one thread per run; right for scan-sized clouds (2-3 points per voxel).  Runs longer than
-//                               kLongRun are only queued: with dependent index->point loads a thread needs ~0.4 us per point,
-//                               and map-sized clouds have voxels with thousands of points (1.16 ms on 2M points, 0.2 m leaf);
+// PCL's CentroidPoint — and written in ascending key order.  ONE kernel over the sorted (key, index) pairs:
+//   * a tile (2048 sorted positions) loads its keys and gathers its points raw[vals[e]] into shared memory — all loads of a
+//     thread independent, no sorted copy of the cloud in global memory;
+//   * run heads are counted, and the tile's first output rank comes from a decoupled look-back over the earlier tiles of the
+//     slot (same status words / tickets as the sort); the last live tile writes n_pts;
+//   * the thread that owns a head walks its run through shared memory (continuing in global memory when the run leaves the
+//     tile).  Runs longer than kLongRun are only queued: a serial walk needs ~0.4 us per point once it leaves shared memory, and
+//     map-sized clouds have voxels with thousands of points;
 //   voxel_long_centroid_kernel  one warp per queued run: 32 lanes fetch 32 points at once, then the warp consumes them in
 //                               order through shuffles, so the additions stay strictly sequential but never wait for loads.
+// Pass-through slots (overflow) are copied here too.
+// (Round 1: heads, scan, gather, centroid = four kernels, with the gathered cloud written to and re-read from global memory.)
 constexpr uint32_t kLongRun = 64;
 
-// sorted[e] = raw[vals[e]]: the points in voxel-key order, so that the centroid kernels stream them instead of chasing
-// index -> point through two dependent loads per addition
-__global__ void __launch_bounds__(kSortThreads) voxel_gather_kernel(const SlotInfo* __restrict__ slots, TileMap tm, const uint32_t* __restrict__ vals,
-                                                                     float4* __restrict__ sorted) {
-  const uint32_t t = blockIdx.x;
+__global__ void __launch_bounds__(kSortThreads) voxel_centroid_kernel(SlotInfo* __restrict__ slots, TileMap tm, const uint32_t* __restrict__ slot_tile_begin,
+                                                                       const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                                       uint64_t* __restrict__ status, uint32_t* __restrict__ ticket, uint32_t epoch,
+                                                                       float4* __restrict__ work, uint4* __restrict__ long_runs, uint32_t* __restrict__ n_long,
+                                                                       int32_t* __restrict__ flags) {
+  __shared__ float sx[kSortTile], sy[kSortTile], sz[kSortTile];
+  __shared__ uint32_t sk[kSortTile];
+  __shared__ uint16_t s_head[kSortTile];  // tile positions of the run heads, in order
+  __shared__ uint32_t wsum[8];
+  __shared__ uint32_t s_tile, s_base;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t t = s_tile;
   const uint32_t slot = tm.tile_slot[t], first = tm.tile_first[t];
-  const SlotInfo& si = slots[slot];
-  if (si.overflow) return;
+  SlotInfo& si = slots[slot];
+  if (si.overflow) {  // working cloud = raw cloud verbatim
+#pragma unroll
+    for (int j = 0; j < kSortTile / kSortThreads; ++j) {
+      const uint32_t e = first + j * kSortThreads + threadIdx.x;
+      if (e < si.n_raw) work[si.off + e] = si.raw[e];
+    }
+    return;
+  }
+  const uint32_t n = si.n_finite;
+  if (first >= n) return;  // dead tiles are a suffix of their slot
+  const uint32_t* k = keys + si.off;
+  const uint32_t* v = vals + si.off;
+  const float4* raw = si.raw;
+  const uint32_t live = min(n - first, (uint32_t)kSortTile);
 #pragma unroll
   for (int j = 0; j < kSortTile / kSortThreads; ++j) {
-    const uint32_t e = first + j * kSortThreads + threadIdx.x;
-    if (e < si.n_finite) sorted[si.off + e] = si.raw[vals[si.off + e]];
+    const uint32_t i = j * kSortThreads + threadIdx.x;
+    if (i < live) {
+      const float4 p = raw[v[first + i]];
+      sk[i] = k[first + i]; sx[i] = p.x; sy[i] = p.y; sz[i] = p.z;
+    }
   }
-}
-
-__global__ void __launch_bounds__(kSortThreads) voxel_centroid_kernel(const SlotInfo* __restrict__ slots, TileMap tm,
-                                                                       const uint32_t* __restrict__ keys, const float4* __restrict__ sorted,
-                                                                       const uint32_t* __restrict__ tile_heads, float4* __restrict__ work,
-                                                                       uint4* __restrict__ long_runs, uint32_t* __restrict__ n_long) {
-  __shared__ uint32_t wsum[8];
-  const uint32_t t = blockIdx.x;
-  const uint32_t slot = tm.tile_slot[t], first = tm.tile_first[t];
-  const SlotInfo& si = slots[slot];
-  if (si.overflow) return;
-  const uint32_t n = si.n_finite;
-  if (first >= n) return;
-  const uint32_t* k = keys + si.off;
-  const float4* pts = sorted + si.off;
+  __syncthreads();
   constexpr int kPer = kSortTile / kSortThreads;
-  const uint32_t e0 = first + threadIdx.x * kPer;  // kPer consecutive sorted positions per thread
+  const uint32_t i0 = threadIdx.x * kPer;  // kPer consecutive sorted positions per thread
   uint32_t head_mask = 0, cnt = 0;
-  uint32_t prev = (e0 > 0 && e0 < n) ? k[e0 - 1] : 0u;
+  uint32_t prev = i0 > 0 ? sk[min(i0, live) - 1] : (first > 0 ? k[first - 1] : 0u);
 #pragma unroll
   for (int j = 0; j < kPer; ++j) {
-    const uint32_t e = e0 + j;
-    if (e < n) {
-      const uint32_t kk = k[e];
-      if (e == 0 || kk != prev) { head_mask |= 1u << j; ++cnt; }
+    const uint32_t i = i0 + j;
+    if (i < live) {
+      const uint32_t kk = sk[i];
+      if (first + i == 0 || kk != prev) { head_mask |= 1u << j; ++cnt; }
       prev = kk;
     }
   }
@@ -414,69 +332,157 @@ __global__ void __launch_bounds__(kSortThreads) voxel_centroid_kernel(const Slot
   for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += u; }
   if (lane == 31) wsum[w] = incl;
   __syncthreads();
-  uint32_t rank = tile_heads[t] + incl - cnt;
-  for (int i = 0; i < w; ++i) rank += wsum[i];
-  float4* out = work + si.off;
+  if (w == 0) {  // warp 0 publishes the tile's head count and looks back, 32 earlier tiles per step, for its first rank
+    uint32_t total = lane < 8 ? wsum[lane] : 0u;
 #pragma unroll
-  for (int j = 0; j < kPer; ++j) {
-    if (!(head_mask & (1u << j))) continue;
-    const uint32_t e = e0 + j;
-    const uint32_t kk = k[e];
+    for (int o = 4; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+    total = __shfl_sync(0xFFFFFFFFu, total, 0);
+    const uint64_t tag = uint64_t(epoch) << 32;
+    const uint32_t begin = slot_tile_begin[slot];
+    uint64_t* mine = status + size_t(t) * 256;
+    if (lane == 0) lb_store(mine, tag | (uint64_t(t == begin ? kLbInclusive : kLbAggregate) << 30) | total);
+    uint32_t excl = 0;
+    if (t != begin) {
+      long long q = (long long)t - 1;
+      for (;;) {
+        const long long qi = q - lane;
+        uint64_t x = tag | (uint64_t(kLbInclusive) << 30);  // lanes before the slot's first tile: inclusive, nothing to add
+        if (qi >= (long long)begin) {
+          const uint64_t* theirs = status + size_t(qi) * 256;
+          x = lb_load(theirs);
+          uint32_t spin = 0;
+          while (uint32_t(x >> 32) != epoch) {
+            if (++spin > kLbSpinLimit) { atomicOr(&flags[0], kErrSortStall); x = tag | (uint64_t(kLbInclusive) << 30); break; }
+            __nanosleep(20);
+            x = lb_load(theirs);
+          }
+        }
+        const uint32_t inclusive = __ballot_sync(0xFFFFFFFFu, (uint32_t(x) >> 30) == kLbInclusive);
+        const int stop = inclusive ? __ffs(inclusive) - 1 : 31;  // nearest tile that already knows its prefix
+        uint32_t add = lane <= stop ? (uint32_t(x) & kLbValueMask) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xFFFFFFFFu, add, o);
+        excl += add;
+        if (inclusive) break;
+        q -= 32;
+      }
+      if (lane == 0) lb_store(mine, tag | (uint64_t(kLbInclusive) << 30) | (excl + total));
+    }
+    if (lane == 0) {
+      s_base = excl;
+      if (first + live == n) si.n_pts = excl + total;  // last live tile of the slot: the number of voxels
+    }
+  }
+  __syncthreads();
+  // Heads are compacted into a list and dealt out to consecutive threads: with one thread walking the heads of its own 8
+  // positions only 3 of 32 lanes were busy in the walk (ncu, profiles/r02_summary.md), and the centroids of a warp now land on
+  // consecutive addresses.
+  uint32_t lr = incl - cnt, heads = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { if (i < w) lr += wsum[i]; heads += wsum[i]; }
+#pragma unroll
+  for (int j = 0; j < kPer; ++j)
+    if (head_mask & (1u << j)) s_head[lr++] = (uint16_t)(i0 + j);
+  __syncthreads();
+  float4* out = work + si.off;
+  for (uint32_t h = threadIdx.x; h < heads; h += kSortThreads) {
+    const uint32_t i = s_head[h], e = first + i, rank = s_base + h;
+    const uint32_t kk = sk[i];
     if (e + kLongRun < n && k[e + kLongRun] == kk) {  // sorted keys: the run has more than kLongRun points
       long_runs[atomicAdd(n_long, 1u)] = make_uint4(slot, e, rank, 0u);
-      ++rank;
       continue;
     }
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    uint32_t l = e;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    uint32_t l = i;
     do {
-      const float4 p = pts[l];
-      sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z);
+      ax = __fadd_rn(ax, sx[l]); ay = __fadd_rn(ay, sy[l]); az = __fadd_rn(az, sz[l]);
       ++l;
-    } while (l < n && k[l] == kk);
-    const float c = (float)(l - e);
-    out[rank++] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), 1.0f);
+    } while (l < live && sk[l] == kk);
+    uint32_t g = first + l;
+    if (l == live) {  // the run may continue in the next tile(s)
+      while (g < n && k[g] == kk) {
+        const float4 p = raw[v[g]];
+        ax = __fadd_rn(ax, p.x); ay = __fadd_rn(ay, p.y); az = __fadd_rn(az, p.z);
+        ++g;
+      }
+    }
+    const float c = (float)(g - e);
+    out[rank] = make_float4(__fdiv_rn(ax, c), __fdiv_rn(ay, c), __fdiv_rn(az, c), 1.0f);
   }
 }
 
-__global__ void __launch_bounds__(256) voxel_long_centroid_kernel(const SlotInfo* __restrict__ slots, const uint32_t* __restrict__ keys,
-                                                                  const float4* __restrict__ sorted, float4* __restrict__ work,
+// Three lanes of the warp carry the x, y and z sums.  A batch of 32 gathered points is staged in shared memory and every lane
+// then reads component (lane & 3) of point j: one LDS + one FADD per point for all three chains, 4 cycles of dependent latency
+// per point.  (Fed by shuffles — 3 SHFL + 3 FADD per point, each FADD waiting for its shuffle — the same loop took ~35 cycles per
+// point: 358 us on the 5289-point voxels of the 2M-point cloud at 0.2 m, profiles/r02_summary.md.)
+__global__ void __launch_bounds__(256, 2) voxel_long_centroid_kernel(const SlotInfo* __restrict__ slots, const uint32_t* __restrict__ keys,
+                                                                  const uint32_t* __restrict__ vals, float4* __restrict__ work,
                                                                   const uint4* __restrict__ long_runs, const uint32_t* __restrict__ n_long) {
   const uint32_t FULL = 0xFFFFFFFFu;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-  constexpr int kDepth = 4;  // batches of 32 points in flight per warp
-  for (uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < *n_long; q += warps) {
+  // One warp walks one run, so its own look-ahead must hide the loads, and a warp issues in order: a point load that waits for
+  // its index stalls everything behind it.  Two stages: keys + indices are fetched 2 x kDepth batches ahead, the points kDepth
+  // batches ahead with indices that arrived an iteration ago — no load ever waits.  (Index and point fetched in the same
+  // iteration cost one L2 round trip per batch: 27 cycles per point instead of ~7.)
+  constexpr int kDepth = 8;
+  __shared__ float4 s_pts[8][2][32];  // per warp: two staging buffers, so that one __syncwarp per batch is enough
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int comp = lane & 3;
+  for (uint32_t q = blockIdx.x * (blockDim.x >> 5) + w; q < *n_long; q += warps) {
     const uint4 job = long_runs[q];
     const SlotInfo& si = slots[job.x];
     const uint32_t n = si.n_finite;
     const uint32_t* k = keys + si.off;
-    const float4* pts = sorted + si.off;
+    const uint32_t* v = vals + si.off;
+    const float4* raw = si.raw;
     const uint32_t kk = k[job.y];
-    // length of the run: keys are sorted, so gallop + binary search for the first position with another key
-    uint32_t lo = job.y + kLongRun, step = kLongRun, hi;
-    for (;;) { hi = lo + step; if (hi >= n) { hi = n; break; } if (k[hi] != kk) break; lo = hi; step <<= 1; }
-    while (lo + 1 < hi) { const uint32_t mid = (lo + hi) >> 1; if (k[mid] == kk) lo = mid; else hi = mid; }
-    const uint32_t end = hi;  // k[lo] == kk, k[hi] != kk (or hi == n)
-    float sx = 0.f, sy = 0.f, sz = 0.f;
+    // The run ends where the key changes (sorted keys: its members are a prefix of every batch).  The keys ride along with the
+    // points, so the end is found by the walk itself — a separate gallop + binary search was a chain of ~15 dependent loads.
+    float acc = 0.f;
     float4 buf[kDepth];
+    uint32_t nk[kDepth], nv[kDepth];
+    bool in[kDepth];
 #pragma unroll
-    for (int d = 0; d < kDepth; ++d) { const uint32_t e = job.y + d * 32 + lane; buf[d] = e < end ? pts[e] : make_float4(0.f, 0.f, 0.f, 0.f); }
-    for (uint32_t b = job.y; b < end; b += 32 * kDepth) {
+    for (int d = 0; d < kDepth; ++d) {
+      const uint32_t e = job.y + d * 32 + lane, e2 = e + kDepth * 32;
+      const uint32_t ke = e < n ? k[e] : ~kk, ve = e < n ? v[e] : 0u;
+      nk[d] = e2 < n ? k[e2] : ~kk; nv[d] = e2 < n ? v[e2] : 0u;
+      in[d] = ke == kk;
+      buf[d] = in[d] ? raw[ve] : zero;
+    }
+    uint32_t len = 0;
+    int stage = 0;
+    for (uint32_t b = job.y;; b += 32 * kDepth) {
+      bool more = true;
 #pragma unroll
       for (int d = 0; d < kDepth; ++d) {
         const float4 p = buf[d];
-        const uint32_t nb = b + (d + kDepth) * 32 + lane;           // refill this slot with the batch kDepth ahead
-        buf[d] = nb < end ? pts[nb] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const int take = (int)min(32u, end > b + d * 32 ? end - (b + d * 32) : 0u);
-        for (int j = 0; j < take; ++j) {
-          sx = __fadd_rn(sx, __shfl_sync(FULL, p.x, j));
-          sy = __fadd_rn(sy, __shfl_sync(FULL, p.y, j));
-          sz = __fadd_rn(sz, __shfl_sync(FULL, p.z, j));
+        const int take = __popc(__ballot_sync(FULL, in[d]));
+        in[d] = nk[d] == kk;                                         // the batch kDepth ahead: its index is here already
+        buf[d] = in[d] ? raw[nv[d]] : zero;
+        const uint32_t e2 = b + (d + 2 * kDepth) * 32 + lane;      // and the index of the batch 2 x kDepth ahead
+        nk[d] = e2 < n ? k[e2] : ~kk; nv[d] = e2 < n ? v[e2] : 0u;
+        if (more) {
+          s_pts[w][stage][lane] = p;
+          __syncwarp();
+          const float* f = reinterpret_cast<const float*>(&s_pts[w][stage][0]) + comp;
+          if (take == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc = __fadd_rn(acc, f[4 * j]);
+          } else {
+            for (int j = 0; j < take; ++j) acc = __fadd_rn(acc, f[4 * j]);
+          }
+          stage ^= 1;
+          len += take;
+          if (take < 32) more = false;
         }
       }
+      if (!more) break;
     }
-    const float c = (float)(end - job.y);
+    __syncwarp();
+    const float sx = __shfl_sync(FULL, acc, 0), sy = __shfl_sync(FULL, acc, 1), sz = __shfl_sync(FULL, acc, 2);
+    const float c = (float)len;
     if (lane == 0) work[si.off + job.z] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), 1.0f);
   }
 }
@@ -494,12 +500,6 @@ __global__ void __launch_bounds__(kSortThreads) voxel_passthrough_kernel(const S
   }
 }
 
-void launch_bbox(Workspace& ws, int which) {
-  TileMap tm{ws.tile_slot.as<uint32_t>(), ws.tile_first.as<uint32_t>(), ws.n_tiles};
-  bbox_kernel<<<ws.n_tiles, kSortThreads, 0, ws.stream>>>(ws.slots.as<SlotInfo>(), tm, ws.work.as<float4>(), which);
-  ++ws.launches;
-}
-
 void run_voxel(Workspace& ws, float leaf, uint32_t* leaf_keys) {
   if (ws.n_tiles == 0) {  // all clouds empty: n_pts stays 0
     return;
@@ -508,8 +508,8 @@ void run_voxel(Workspace& ws, float leaf, uint32_t* leaf_keys) {
   StageTimer timer(ws, kStageVoxel);
   SlotInfo* slots = ws.slots.as<SlotInfo>();
   TileMap tm{ws.tile_slot.as<uint32_t>(), ws.tile_first.as<uint32_t>(), ws.n_tiles};
-  launch_bbox(ws, kCountRaw);
-  voxel_params_kernel<<<(ws.n_slots + 63) / 64, 64, 0, st>>>(slots, ws.n_slots, leaf);
+  uint32_t* bbox_done = ws.flags.as<uint32_t>() + 10;  // flags are zeroed by setup_batch; the kernel leaves the counter zero
+  bbox_kernel<kCountRaw><<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.work.as<float4>(), ws.n_slots, bbox_done, VoxelParams{leaf});
   ++ws.launches;
   if (leaf > 0.f) {
     uint32_t* keys[2] = {ws.keys0.as<uint32_t>(), ws.keys1.as<uint32_t>()};
@@ -521,18 +521,15 @@ void run_voxel(Workspace& ws, float leaf, uint32_t* leaf_keys) {
     ++ws.launches;
     if (leaf_keys) S3D_CUDA(cudaMemcpyAsync(leaf_keys, keys[0], 4 * size_t(ws.total), cudaMemcpyDeviceToDevice, st));
     radix_sort_segmented(st, slots, ws.n_slots, tm, ws.slot_tile_begin.as<uint32_t>(), keys, vals, ss, kCountRaw, /*digits_done=*/true, &ws.launches);
-    voxel_heads_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, keys[0], ws.tile_heads.as<uint32_t>());
-    voxel_scan_kernel<<<ws.n_slots, 32, 0, st>>>(slots, ws.n_slots, ws.slot_tile_begin.as<uint32_t>(), ws.tile_heads.as<uint32_t>());
     uint32_t* n_long = ws.flags.as<uint32_t>() + 8;  // flags[8]: number of queued long runs (flags are zeroed by setup_batch)
-    float4* sorted = ws.gpts.as<float4>();  // free until the NN grid is built
-    voxel_gather_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, vals[0], sorted);
-    voxel_centroid_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, keys[0], sorted, ws.tile_heads.as<uint32_t>(), ws.work.as<float4>(),
-                                                               ws.long_runs.as<uint4>(), n_long);
-    voxel_long_centroid_kernel<<<ws.n_sms * 2, 256, 0, st>>>(slots, keys[0], sorted, ws.work.as<float4>(), ws.long_runs.as<uint4>(), n_long);
-    ws.launches += 5;
+    voxel_centroid_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.slot_tile_begin.as<uint32_t>(), keys[0], vals[0], ss.status, sort_ticket(ss, ws.n_slots, kSortPasses),
+                                                               sort_next_epoch(st, ss), ws.work.as<float4>(), ws.long_runs.as<uint4>(), n_long, ss.flags);
+    voxel_long_centroid_kernel<<<ws.n_sms * 2, 256, 0, st>>>(slots, keys[0], vals[0], ws.work.as<float4>(), ws.long_runs.as<uint4>(), n_long);
+    ws.launches += 2;
+  } else {
+    voxel_passthrough_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.work.as<float4>());
+    ++ws.launches;
   }
-  voxel_passthrough_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.work.as<float4>());
-  ++ws.launches;
   S3D_CUDA(cudaGetLastError());
 }
 
