@@ -51,11 +51,17 @@ __device__ __forceinline__ int cell_of(float u, int dim) {
   return (int)f;
 }
 
-__global__ void __launch_bounds__(kSortThreads) grid_keys_kernel(const SlotInfo* __restrict__ slots, TileMap tm, const float4* __restrict__ work,
-                                                                  uint32_t* __restrict__ keys) {
+// + the digit totals of all four sort passes (sort.cuh)
+__global__ void __launch_bounds__(kSortThreads) grid_keys_kernel(const SlotInfo* __restrict__ slots, TileMap tm, uint32_t n_slots, const float4* __restrict__ work,
+                                                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ totals) {
+  __shared__ uint32_t sh[kSortPasses][256];
   const uint32_t t = blockIdx.x;
   const uint32_t slot = tm.tile_slot[t], first = tm.tile_first[t];
   const SlotInfo& si = slots[slot];
+  if (first >= si.n_pts) return;
+#pragma unroll
+  for (int p = 0; p < kSortPasses; ++p) sh[p][threadIdx.x] = 0;
+  __syncthreads();
   const int dim = 1 << si.nlev;
 #pragma unroll
   for (int j = 0; j < kSortTile / kSortThreads; ++j) {
@@ -65,9 +71,13 @@ __global__ void __launch_bounds__(kSortThreads) grid_keys_kernel(const SlotInfo*
       const int cx = cell_of(grid_coord(v.x, si.g_min[0], si.inv_h0), dim);
       const int cy = cell_of(grid_coord(v.y, si.g_min[1], si.inv_h0), dim);
       const int cz = cell_of(grid_coord(v.z, si.g_min[2], si.inv_h0), dim);
-      keys[si.off + e] = morton3(cx, cy, cz);
+      const uint32_t key = morton3(cx, cy, cz);
+      keys[si.off + e] = key;
+      count_digits(sh, key);
     }
   }
+  __syncthreads();
+  flush_digits(sh, totals, n_slots, slot);
 }
 
 __device__ __forceinline__ int levels_started(const uint32_t* __restrict__ k, uint32_t e, int nlev) {
@@ -143,10 +153,18 @@ __global__ void __launch_bounds__(kSortThreads) hash_insert_kernel(const SlotInf
     if (e >= n) continue;
     const int started = levels_started(k, e, si.nlev);
     const uint32_t key0 = k[e];
+    uint32_t lo = e + 1;  // cells nest: the level-L cell ends where the level-(L-1) cell ended, or later
     for (int L = 0; L < started; ++L) {
       const uint32_t ck = key0 >> (3 * L);
-      // end = first position whose level-L cell differs (keys ascending => cells ascending)
-      uint32_t lo = e + 1, hi = n;
+      // end = first position whose level-L cell differs (keys ascending => cells ascending).  Cells are short (1.2 points at the
+      // finest level, ~4x per level), so gallop from the last known member instead of bisecting [e, n): 2-4 dependent loads
+      // instead of 17 per (cell, level) — the bisection made this kernel 80 % of the grid stage (profiles/r02_summary.md).
+      uint32_t hi = n;
+      for (uint32_t step = 1; lo + step <= n; step <<= 1) {
+        const uint32_t p = lo + step - 1;
+        if ((k[p] >> (3 * L)) > ck) { hi = p; break; }
+        lo = p + 1;
+      }
       while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((k[mid] >> (3 * L)) > ck) hi = mid; else lo = mid + 1; }
       uint32_t s = hash_slot(ck, (uint32_t)L, si.hash_cap);
       for (;;) {  // all inserted (level, cell) pairs are distinct: claim the first empty entry
@@ -167,9 +185,11 @@ void run_grid(Workspace& ws, float leaf_hint) {
   bbox_kernel<kCountPts><<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.work.as<float4>(), ws.n_slots, bbox_done, GridParams{leaf_hint});
   uint32_t* keys[2] = {ws.keys0.as<uint32_t>(), ws.keys1.as<uint32_t>()};
   uint32_t* vals[2] = {ws.vals0.as<uint32_t>(), ws.vals1.as<uint32_t>()};
-  grid_keys_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.work.as<float4>(), keys[0]);
+  const SortState ss = ws.sort_state();
+  sort_clear_aux(st, ss, ws.n_slots);
+  grid_keys_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.n_slots, ws.work.as<float4>(), keys[0], ss.aux);
   ws.launches += 2;
-  radix_sort_segmented(st, slots, ws.n_slots, tm, ws.slot_tile_begin.as<uint32_t>(), keys, vals, ws.sort_state(), kCountPts, /*digits_done=*/false, &ws.launches);
+  radix_sort_segmented(st, slots, ws.n_slots, tm, ws.slot_tile_begin.as<uint32_t>(), keys, vals, ss, kCountPts, /*digits_done=*/true, &ws.launches);
   grid_gather_kernel<<<ws.n_tiles, kSortThreads, 0, st>>>(slots, tm, ws.work.as<float4>(), keys[0], vals[0], ws.gpts.as<float4>());
   hash_layout_kernel<<<1, 32, 0, st>>>(slots, ws.n_slots, (uint32_t)std::min<size_t>(ws.hash_cap, 0xFFFFFFF0u), ws.flags.as<int32_t>());
   hash_clear_kernel<<<ws.n_sms * 4, 256, 0, st>>>(ws.hash.as<HashEntry>(), ws.flags.as<int32_t>());
