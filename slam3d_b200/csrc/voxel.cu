@@ -9,6 +9,11 @@
 //   heads     run starts -> per-tile counts -> per-slot scan           A.1 step 7
 //   centroid  one thread per run sums its points in ascending input order in float, / float(count)   A.1 steps 8,9
 // All kernels are streaming and HBM/L2-bandwidth bound: 16 B/point in, 8 B/point keys, 16 B/voxel out.
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <thread>
+
 #include "internal.h"
 #include "bbox.cuh"
 #include "sort.cuh"
@@ -86,6 +91,74 @@ void Workspace::destroy() {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Pageable -> pinned staging copies, spread over a few helper threads shared by all workspaces of the process.  One thread's
+// memcpy moves ~10 GB/s; a chunk of 16 scan pairs is 134 MB, so a chunk's own thread needed 13 ms for what its GPU work does in 5.
+// Pieces of 1 MB go to a queue; the caller copies pieces too and returns when all of ITS pieces are done.
+class CopyPool {
+ public:
+  static CopyPool& get() { static CopyPool p; return p; }
+  struct Job { char* dst; const char* src; size_t bytes; std::atomic<int>* left; };
+  void copy(const std::vector<std::pair<void*, std::pair<const void*, size_t>>>& spans) {
+    constexpr size_t kPiece = 1u << 20;
+    std::atomic<int> left{0};
+    std::vector<Job> jobs;
+    for (const auto& sp : spans)
+      for (size_t o = 0; o < sp.second.second; o += kPiece)
+        jobs.push_back(Job{static_cast<char*>(sp.first) + o, static_cast<const char*>(sp.second.first) + o, std::min(kPiece, sp.second.second - o), &left});
+    if (jobs.empty()) return;
+    left.store((int)jobs.size());
+    if (n_threads_ > 0 && jobs.size() > 1) {
+      { std::lock_guard<std::mutex> g(mu_); for (const Job& j : jobs) q_.push_back(j); }
+      cv_.notify_all();
+    } else {
+      for (const Job& j : jobs) { memcpy(j.dst, j.src, j.bytes); }
+      return;
+    }
+    for (;;) {  // help until the queue is empty, then wait for the pieces other threads still hold
+      Job j;
+      { std::lock_guard<std::mutex> g(mu_); if (q_.empty()) break; j = q_.front(); q_.pop_front(); }
+      memcpy(j.dst, j.src, j.bytes);
+      j.left->fetch_sub(1, std::memory_order_acq_rel);
+    }
+    while (left.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+  }
+ private:
+  CopyPool() {
+    // helpers = half the cores this rank can count on (torchrun exports LOCAL_WORLD_SIZE), at most 8; S3D_COPY_THREADS overrides
+    int n = (int)std::thread::hardware_concurrency();
+    const char* lws = getenv("LOCAL_WORLD_SIZE");
+    n = n / (2 * std::max(1, lws ? atoi(lws) : 1));
+    n = std::min(8, std::max(0, n - 1));
+    if (const char* e = getenv("S3D_COPY_THREADS")) n = std::max(0, atoi(e));
+    n_threads_ = n;
+    for (int i = 0; i < n; ++i) threads_.emplace_back([this] { loop(); });
+  }
+  ~CopyPool() {
+    { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+  }
+  void loop() {
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+      cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+      if (stop_) return;
+      Job j = q_.front(); q_.pop_front();
+      lk.unlock();
+      memcpy(j.dst, j.src, j.bytes);
+      j.left->fetch_sub(1, std::memory_order_acq_rel);
+      lk.lock();
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::deque<Job> q_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  int n_threads_ = 0;
+  bool stop_ = false;
+};
+
+// ------------------------------------------------------------------------------------------------------------
 // Batch set-up: slot table, tile table, input staging.  clouds[2p] = slam3d source of pair p, clouds[2p+1] = target
 // (or any list of clouds for the stage-level entry points).
 void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const std::vector<uint64_t>& sizes, uint32_t n_pairs) {
@@ -153,8 +226,10 @@ void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const s
   static const bool bounce_enabled = [] { const char* e = getenv("S3D_PINNED_BOUNCE"); return !e || atoi(e) != 0; }();  // 0: A/B measurements
   if (need_bounce && bounce_enabled) {
     ws.h_bounce.reserve(16 * tot);
+    std::vector<std::pair<void*, std::pair<const void*, size_t>>> spans;
     for (uint32_t s = 0; s < ns; ++s)
-      if (pageable[s]) memcpy(ws.h_bounce.as<char>() + 16 * size_t(ws.h_off[s]), clouds[s], 16 * sizes[s]);
+      if (pageable[s]) spans.push_back({ws.h_bounce.as<char>() + 16 * size_t(ws.h_off[s]), {clouds[s], 16 * size_t(sizes[s])}});
+    CopyPool::get().copy(spans);
   } else {
     need_bounce = false;
   }
