@@ -105,6 +105,9 @@ constexpr uint64_t KMAX = 0xFFFFFFFFFFFFFFFFull;
 #define S3D_KNN_BATCH 4
 #endif
 
+// (Round 2 also tried admission for the whole batch first and the heap insertions afterwards, one per turn of a loop, so that the
+// lanes with something to insert do it together — same results; 9.70 ms against 9.26 for batches of 4, 8.95 for batches of 8: the
+// extra selects and spills cost what the better lane use saves.  Not kept.)
 // scans the points [begin, end) of one cell for the query qv: fill phase (append, heapify once when the k-th candidate
 // arrives), then replace-the-root insertions.  S3D_KNN_BATCH points are fetched before the first of them is examined, so
 // their load latencies overlap (B200, 32 pairs per step: 4.41 / 4.30 / 4.06 ms for batches of 1 / 2 / 4).
