@@ -525,12 +525,20 @@ def bench_c3(ctx, peak, peak_src, args, headline):
     if not headline:
         return res
     ms = res["leaf_0.1"]["ms"]
+    traffic, traffic_src = None, None
+    import glob
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_c3_traffic.json")))[-1:]:  # measured by ncu (scripts/profile_round.sh, c3_traffic_json.py)
+        t = json.load(open(f))["leaf_0.1"]
+        traffic = t["cold"]["dram_bytes"]
+        traffic_src = (f"{os.path.basename(f)}: DRAM read + write of the 8 launches of one call, caches flushed before every launch "
+                       f"(warm, input L2-resident: {t['warm']['dram_bytes'] / 1e6:.1f} MB)")
     return {"metric": "voxelgrid_mpoints_per_s_2m_cloud", "value": cloud.shape[0] / ms / 1e3, "unit": "Mpoints/s", "n_gpus": 1, "steps": n, "warmup": 3,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/u32", "data": "synthetic",
             "config": {"workload": "VoxelGrid downsample + covariance stress: 2M-point synthetic cloud, leaf sizes 0.05/0.1/0.2 m (BASELINE.json configs[2])",
                        "l2": "input 33.5 MB < L2: L2-resident stream", **res},
-            "roofline": {"bound": "hbm", "kernel": "voxel filter (bbox, keys, radix sort, centroids)", "achieved": res["leaf_0.1"]["algorithmic_gb_s"], "peak": peak,
-                         "unit": "GB/s", "frac": res["leaf_0.1"]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src}}
+            "roofline": {"bound": "hbm", "kernel": "voxel filter (bbox, keys, 4 radix passes, centroids: 8 launches)", "achieved": res["leaf_0.1"]["algorithmic_gb_s"],
+                         "peak": peak, "unit": "GB/s", "frac": res["leaf_0.1"]["frac_of_hbm_peak"], "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes": 16.0 * cloud.shape[0] + 16.0 * res["leaf_0.1"]["voxels"], "peak_source": peak_src}}
 
 
 def bench_c4(ctx, args, rank, world, n_dev, headline, barrier):

@@ -21,4 +21,11 @@ done
 # the persistent loop kernel of the single-call path (one pair) and the control kernel of the batch path
 ncu --set full --clock-control none --import-source on -k regex:gicp_loop_kernel --launch-skip 2 -c 1 -f -o gpurun_out/gicp_loop_kernel_${TAG} env -u S3D_LOOP_MODE python scripts/single_pair.py > gpurun_out/b_gicp_loop_kernel_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gicp_ctrl_kernel --launch-skip 6 -c 1 -f -o gpurun_out/gicp_ctrl_kernel_${TAG} $B > gpurun_out/b_gicp_ctrl_kernel_${TAG}.log 2>&1
+# config 3 (VoxelGrid on the 2M-point cloud, leaf 0.05 / 0.1 / 0.2 m, two calls each): time and DRAM bytes of every launch, with the
+# cache flush between launches (cold) and without (warm: the 33.5 MB input stays in L2, as in a running pipeline)
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
+ncu --metrics $M --clock-control none -c 60 --csv --log-file gpurun_out/c3_launches_${TAG}.csv python scripts/c3_voxel_only.py > /dev/null 2>&1
+ncu --metrics $M --clock-control none --cache-control none -c 60 --csv --log-file gpurun_out/c3_launches_warm_${TAG}.csv python scripts/c3_voxel_only.py > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:sort_pass_kernel --launch-skip 4 -c 1 -f -o gpurun_out/sort_pass_kernel_${TAG} python scripts/c3_voxel_only.py > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:voxel_centroid_kernel --launch-skip 1 -c 1 -f -o gpurun_out/voxel_centroid_kernel_${TAG} python scripts/c3_voxel_only.py > /dev/null 2>&1
 ls -la gpurun_out/*${TAG}*
