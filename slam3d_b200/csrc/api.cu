@@ -677,6 +677,7 @@ static void align_prepared_chunk(s3d_context* ctx, int slot, const s3d_prepared_
   S3D_CUDA(cudaSetDevice(ws.device));
   const uint32_t ns = 2 * n;
   ws.n_slots = ns; ws.n_pairs = n; ws.n_tiles = 0;
+  ws.grid_frac = 1.f;  // prepared clouds: the sizes below are the filtered sizes
   ws.h_off.assign(ns, 0); ws.h_n.assign(ns, 0);
   ws.pair_off.resize(n);
   ws.slots.reserve(sizeof(SlotInfo) * ns);

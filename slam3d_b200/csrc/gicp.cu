@@ -116,13 +116,13 @@ __global__ void __launch_bounds__(256) gicp_prepare_kernel(const SlotInfo* __res
     psched[p].claim = 1ull << 32;
   }
   if (!enough) return;
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= sa.n_pts) return;
-  const float4 v = sa.gpts[r];
-  const float3 m = transform_se3(ps.guess, v.x, v.y, v.z);
-  moved[ps.pt_off + r] = make_float4(m.x, m.y, m.z, v.w);
-  prev_nn[ps.pt_off + r] = kNoIndex;
-  sec_lb[ps.pt_off + r] = 0.f;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < sa.n_pts; r += gridDim.x * blockDim.x) {  // any grid covers the cloud (Workspace::grid_frac)
+    const float4 v = sa.gpts[r];
+    const float3 m = transform_se3(ps.guess, v.x, v.y, v.z);
+    moved[ps.pt_off + r] = make_float4(m.x, m.y, m.z, v.w);
+    prev_nn[ps.pt_off + r] = kNoIndex;
+    sec_lb[ps.pt_off + r] = 0.f;
+  }
 }
 
 // Temporal-coherence certificate (exactness preserving).  The last search for this point ran at position q_old and left
@@ -680,11 +680,14 @@ __global__ void __launch_bounds__(kIterTile, 2) gicp_loop_kernel(const __grid_co
 // 10.3 ms on six (profiles/r02_summary.md).  Results are bit-identical in both modes (same tile partials, same control step).
 __global__ void __launch_bounds__(kIterTile, 4) gicp_search_kernel(const __grid_constant__ GicpArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const uint32_t p = blockIdx.y, tile = blockIdx.x;
+  const uint32_t p = blockIdx.y;
   if (__ldcg(&a.pairs[p].phase) != kPhaseNeedNN) return;
   const SlotInfo& sa = a.slots[2 * p + 1];
-  if (tile * kIterTile >= sa.n_pts) return;
-  iter_tile<true>(a, stage_state(a, p, smem + kSmStateA), a.slots[2 * p], sa, p, tile, smem);
+  // the grid is sized from an estimate of the filtered size (Workspace::grid_frac): a CTA strides over the tiles beyond it
+  for (uint32_t tile = blockIdx.x; tile * kIterTile < sa.n_pts; tile += gridDim.x) {
+    if (tile != blockIdx.x) __syncthreads();  // the previous tile is done with the scratch the state is staged into
+    iter_tile<true>(a, stage_state(a, p, smem + kSmStateA), a.slots[2 * p], sa, p, tile, smem);
+  }
 }
 
 // (Tried: the control step fused into this kernel by the ticket scheme — one launch less per trial pass, but the inlined FP64
@@ -693,11 +696,15 @@ __global__ void __launch_bounds__(kIterTile, 4) gicp_search_kernel(const __grid_
 __global__ void __launch_bounds__(kIterTile) gicp_trial_kernel(const __grid_constant__ GicpArgs a) {
   constexpr size_t kScratch = size_t(kIterTile) * 64 + 16 * kEvalSums * 8;
   __shared__ __align__(16) unsigned char smem[kScratch + sizeof(PairState)];
-  const uint32_t p = blockIdx.y, tile = blockIdx.x;
+  const uint32_t p = blockIdx.y;
   if (__ldcg(&a.pairs[p].phase) != kPhaseEval) return;
   const SlotInfo& sa = a.slots[2 * p + 1];
-  if (tile * kIterTile >= sa.n_pts) return;
-  eval_tile<true>(a, stage_state(a, p, smem + kScratch), a.slots[2 * p], sa, p, tile, smem);
+  if (blockIdx.x * kIterTile >= sa.n_pts) return;
+  const PairState& ps = stage_state(a, p, smem + kScratch);
+  for (uint32_t tile = blockIdx.x; tile * kIterTile < sa.n_pts; tile += gridDim.x) {
+    if (tile != blockIdx.x) __syncthreads();  // the previous tile's partial sums have left the scratch
+    eval_tile<true>(a, ps, a.slots[2 * p], sa, p, tile, smem);
+  }
 }
 
 // one CTA per pair; the first control launch of a round serves pairs that just searched, the later ones pairs that were just evaluated
@@ -723,11 +730,13 @@ __global__ void gicp_cond_kernel(const __grid_constant__ GicpArgs a, cudaGraphCo
 
 __global__ void __launch_bounds__(kIterTile, 4) gicp_fitness_kernel(const __grid_constant__ GicpArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const uint32_t p = blockIdx.y, tile = blockIdx.x;
+  const uint32_t p = blockIdx.y;
   if (__ldcg(&a.pairs[p].phase) != kPhaseFitness) return;
   const SlotInfo& sa = a.slots[2 * p + 1];
-  if (tile * kIterTile >= sa.n_pts) return;
-  fitness_tile<true>(a, stage_state(a, p, smem + kSmStateA), a.slots[2 * p], sa, p, tile, smem);
+  for (uint32_t tile = blockIdx.x; tile * kIterTile < sa.n_pts; tile += gridDim.x) {
+    if (tile != blockIdx.x) __syncthreads();
+    fitness_tile<true>(a, stage_state(a, p, smem + kSmStateA), a.slots[2 * p], sa, p, tile, smem);
+  }
 }
 
 __global__ void __launch_bounds__(kIterTile) gicp_fitness_finish_kernel(const __grid_constant__ GicpArgs a) {
@@ -785,7 +794,7 @@ static int loop_grid(const Workspace& ws) {
 // Throughput mode: WHILE (a pair iterates) { search, control, trial, control, trial, control, condition } as a CUDA graph with a
 // conditional node.  The kernels read everything from the GicpArgs block at a fixed device address; only the grid dimensions
 // depend on the batch, so executable graphs are cached per workspace by (tiles per pair, pairs).
-static cudaGraphExec_t loop_graph_for(Workspace& ws, const GicpArgs& args, uint32_t tiles_per_pair, uint32_t np) {
+static cudaGraphExec_t loop_graph_for(Workspace& ws, const GicpArgs& args, uint32_t tiles_per_pair, uint32_t grid_tiles, uint32_t np) {
   // the graphs hold the argument block by value: when a buffer has moved (the batch grew), the cached graphs are stale
   uint64_t sig = 1469598103934665603ull;
   {
@@ -800,7 +809,7 @@ static cudaGraphExec_t loop_graph_for(Workspace& ws, const GicpArgs& args, uint3
     ws.loop_graphs.clear(); ws.loop_graph_defs.clear();
     ws.loop_graph_sig = sig;
   }
-  const uint64_t key = (uint64_t)tiles_per_pair << 32 | np;
+  const uint64_t key = (uint64_t)grid_tiles << 44 | (uint64_t)tiles_per_pair << 20 | np;
   auto it = ws.loop_graphs.find(key);
   if (it != ws.loop_graphs.end()) return it->second;
   cudaGraph_t graph;
@@ -829,7 +838,7 @@ static cudaGraphExec_t loop_graph_for(Workspace& ws, const GicpArgs& args, uint3
   void* a_ctrl0[] = {&ap, &zero};
   void* a_ctrl1[] = {&ap, &one};
   void* a_cond[] = {&ap, &handle};
-  const dim3 tiles(tiles_per_pair, np);
+  const dim3 tiles(grid_tiles, np);
   add(reinterpret_cast<void*>(gicp_search_kernel), tiles, kIterTile, (unsigned)kSmTile, a1);
   add(reinterpret_cast<void*>(gicp_ctrl_kernel), dim3(np), 256, 0, a_ctrl0);
   for (int e = 0; e < 2; ++e) {  // two trial/advance passes per round: most outer iterations finish within one round
@@ -905,7 +914,10 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
                  ws.moments.as<double>(), ws.eval_part.as<double>(), ws.fit_partial.as<double>(), flags, psched, ctl, tiles_per_pair, np,
                  linger, 1u << 20, watchdog};
   S3D_CUDA(cudaMemsetAsync(ctl, 0, 64, st));
-  dim3 grid(tiles_per_pair, np);
+  // launch grid: the tiles the filtered clouds are expected to have (the kernels stride over what a short grid leaves), in steps
+  // of 16 tiles so that the cached graphs stay few
+  const uint32_t grid_tiles = std::min<uint32_t>(tiles_per_pair, ((uint32_t)ceilf(tiles_per_pair * ws.grid_frac) + 15u) & ~15u);
+  dim3 grid(std::max<uint32_t>(1, grid_tiles), np);
   {
     StageTimer timer(ws, kStageSolve);
     gicp_prepare_kernel<<<grid, 256, 0, st>>>(slots, pairs, ws.moved.as<float4>(), ws.prev_nn.as<uint32_t>(), ws.sec_lb.as<float>(), psched, flags);
@@ -920,7 +932,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   } else {
     if (!ws.profiling && loop_mode != 3) {
       StageTimer timer(ws, kStageIter);
-      S3D_CUDA(cudaGraphLaunch(loop_graph_for(ws, dargs, tiles_per_pair, np), st));
+      S3D_CUDA(cudaGraphLaunch(loop_graph_for(ws, dargs, tiles_per_pair, grid_tiles, np), st));
     } else {
       // the same kernels from the host, one poll per round, so that each can be timed
       for (uint32_t round = 0; round < (1u << 20); ++round) {
@@ -960,6 +972,12 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   ws.sync();
   ws.d2h += sizeof(PairState) * np + sizeof(SlotInfo) * ws.n_slots + 32;
   ws.passes += h_ctl[0]; ws.ctrl_steps += h_ctl[1];
+  if (ws.n_tiles > 0) {  // raw-cloud batch: remember how much of the raw clouds survived the voxel filter (sizes the next batch's grids)
+    float frac = 0.f;
+    for (uint32_t s = 0; s < ws.n_slots; ++s)
+      if (hs[s].n_raw > 0) frac = std::max(frac, (float)hs[s].n_pts / (float)hs[s].n_raw);
+    ws.learned_frac = std::min(1.f, frac * 1.08f + 1.f / 64.f);
+  }
   if (getenv("S3D_LOOP_STATS") && !throughput)
     fprintf(stderr, "[s3d loop] pairs %u tiles %u control steps %u | per control step %.1f us | CTA-time in search tiles %.0f us, trial tiles %.0f us, fitness tiles %.0f us\n",
             np, h_ctl[0], h_ctl[1], h_ctl[1] ? 1e-3 * h_ctl[7] / h_ctl[1] : 0.0, 1e-3 * h_ctl[4], 1e-3 * h_ctl[5], 1e-3 * h_ctl[6]);

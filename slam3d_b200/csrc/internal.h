@@ -131,6 +131,12 @@ struct Workspace {
   DevBuf keys0, keys1, vals0, vals1;          // uint32[total]
   DevBuf hist;                                // uint64[n_tiles*256]: look-back status words of the radix sort (sort.cuh), zero when (re)allocated
   DevBuf sort_totals;                         // uint32[4 passes * n_slots * 256] digit totals + 4 tile tickets
+  // Launch grids are sized on the host from RAW cloud sizes, but the kernels behind the voxel filter work on the filtered clouds
+  // (36 % of the points for a 0.1 m leaf on a 64-beam scan): two thirds of the CTAs of every kNN / search / trial / fitness launch
+  // found nothing to do.  Those kernels now stride over their tiles, so ANY grid is correct, and the grid is sized with the
+  // filtered / raw ratio the previous batch on this workspace showed (1 until one has run; S3D_GRID_FRAC pins it for A/B runs).
+  float learned_frac = 1.f;                   // what the last raw-cloud batch showed (+ margin)
+  float grid_frac = 1.f;                      // what the current batch uses (1 for prepared clouds: their sizes are exact)
   uint32_t sort_epoch = 0;                    // bumped once per sort pass: tags the status words, so that they are never cleared
   size_t status_words = 0;
   DevBuf long_runs;                           // uint4[total/64]  voxels with more than 64 points: (slot, first sorted position, output rank)

@@ -118,11 +118,12 @@ __global__ void __launch_bounds__(kKnnThreads, S3D_KNN_MINBLOCKS) knn_cov_kernel
                                                               float* __restrict__ knn_dist2) {
   extern __shared__ uint64_t heap_smem[];  // k * kKnnThreads keys
   const SlotInfo& si = slots[blockIdx.y];
-  const uint32_t r = blockIdx.x * kKnnThreads + threadIdx.x;
-  if (r >= si.n_pts) return;
+  if (blockIdx.x * kKnnThreads >= si.n_pts) return;
   const GridView g = make_grid_view(si);
   if (g.cap == 0) return;  // grid build overflowed its arena: the host re-runs the batch
-  knn_cov_query(si, g, work, normals, k, r, SmemHeap{heap_smem + threadIdx.x}, knn_index, knn_dist2);
+  // the grid is sized from an estimate of the filtered size (Workspace::grid_frac): stride over the chunks it did not cover
+  for (uint32_t r = blockIdx.x * kKnnThreads + threadIdx.x; r < si.n_pts; r += gridDim.x * kKnnThreads)
+    knn_cov_query(si, g, work, normals, k, r, SmemHeap{heap_smem + threadIdx.x}, knn_index, knn_dist2);
 }
 
 // correspondence_randomness beyond what the shared-memory heap holds: the same walk on a heap in global memory (one column per
@@ -131,13 +132,13 @@ __global__ void __launch_bounds__(kKnnThreads) knn_cov_bigk_kernel(const SlotInf
                                                                    double4* __restrict__ normals, int k, uint64_t* __restrict__ arena,
                                                                    uint32_t* __restrict__ knn_index, float* __restrict__ knn_dist2) {
   const SlotInfo& si = slots[blockIdx.y];
-  const uint32_t r = blockIdx.x * kKnnThreads + threadIdx.x;
-  if (r >= si.n_pts) return;
+  if (blockIdx.x * kKnnThreads >= si.n_pts) return;
   const GridView g = make_grid_view(si);
   if (g.cap == 0) return;
   const size_t stride = (size_t)gridDim.x * gridDim.y * kKnnThreads;
   const size_t column = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kKnnThreads + threadIdx.x;
-  knn_cov_query(si, g, work, normals, k, r, GlobalHeap{arena + column, stride}, knn_index, knn_dist2);
+  for (uint32_t r = blockIdx.x * kKnnThreads + threadIdx.x; r < si.n_pts; r += gridDim.x * kKnnThreads)
+    knn_cov_query(si, g, work, normals, k, r, GlobalHeap{arena + column, stride}, knn_index, knn_dist2);
 }
 
 // stage-API helper: full regularised covariance per ORIGINAL index, column-major 3x3
@@ -157,7 +158,8 @@ void run_knn_covariances(Workspace& ws, int k, uint32_t* knn_index, float* knn_d
   uint32_t max_n = 0;
   for (uint32_t s = 0; s < ws.n_slots; ++s) max_n = std::max(max_n, ws.h_n[s]);
   StageTimer timer(ws, kStageKnn);
-  dim3 grid((max_n + kKnnThreads - 1) / kKnnThreads, ws.n_slots);
+  const uint32_t chunks = (max_n + kKnnThreads - 1) / kKnnThreads;
+  dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>(chunks, (uint32_t)ceilf(chunks * ws.grid_frac))), ws.n_slots);
   const size_t heap_bytes = sizeof(uint64_t) * k * kKnnThreads;
   if (k <= kMaxKShared) {
     if (heap_bytes > 48 * 1024) S3D_CUDA(cudaFuncSetAttribute(knn_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heap_bytes));

@@ -165,6 +165,10 @@ void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const s
   S3D_CUDA(cudaSetDevice(ws.device));
   const uint32_t ns = static_cast<uint32_t>(clouds.size());
   ws.n_slots = ns; ws.n_pairs = n_pairs;
+  {
+    static const float pinned = [] { const char* e = getenv("S3D_GRID_FRAC"); return e ? (float)atof(e) : 0.f; }();
+    ws.grid_frac = pinned > 0.f ? std::min(1.f, pinned) : ws.learned_frac;
+  }
   ws.h_off.resize(ns); ws.h_n.resize(ns);
   uint64_t total = 0; uint32_t n_tiles = 0;
   for (uint32_t s = 0; s < ns; ++s) {
