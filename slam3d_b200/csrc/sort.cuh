@@ -112,7 +112,7 @@ __device__ __forceinline__ uint32_t lb_walk(const uint64_t* __restrict__ status,
 #define S3D_SORT_MUL 1
 #endif
 #ifndef S3D_SORT_MINB
-#define S3D_SORT_MINB 4
+#define S3D_SORT_MINB 6
 #endif
 #ifndef S3D_SORT_EARLY_VALS
 #define S3D_SORT_EARLY_VALS 1
