@@ -693,7 +693,10 @@ __global__ void __launch_bounds__(kIterTile, 4) gicp_search_kernel(const __grid_
 // (Tried: the control step fused into this kernel by the ticket scheme — one launch less per trial pass, but the inlined FP64
 // chain raises the kernel from 56 to 80+ registers and the light trial tiles lose a resident CTA per SM: 3262-3283 against
 // 3294-3300 registrations/s, profiles/r02_summary.md.)
-__global__ void __launch_bounds__(kIterTile) gicp_trial_kernel(const __grid_constant__ GicpArgs a) {
+#ifndef S3D_TRIAL_MINB
+#define S3D_TRIAL_MINB 4
+#endif
+__global__ void __launch_bounds__(kIterTile, S3D_TRIAL_MINB) gicp_trial_kernel(const __grid_constant__ GicpArgs a) {
   constexpr size_t kScratch = size_t(kIterTile) * 64 + 16 * kEvalSums * 8;
   __shared__ __align__(16) unsigned char smem[kScratch + sizeof(PairState)];
   const uint32_t p = blockIdx.y;
