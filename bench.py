@@ -55,35 +55,46 @@ def loop_params():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md): ONE `nvidia-smi -lms 200` process, started
+    before and killed after, on rank 0 only.  (A fresh nvidia-smi every 200 ms on every rank — 8 processes that each enumerate all
+    GPUs of the box — slowed the timed region of the 8-GPU run itself: 24.9 ms per step against 22.1 ms for the e2e pass that ran
+    without a sampler, profiles/r02_summary.md.)"""
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True):
         self.index = index
+        self.enabled = enabled
         self.rows = []
-        self.stop = threading.Event()
-        self.th = None
-
-    def _run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.2)
+        self.proc = None
 
     def __enter__(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
-        self.th.start()
+        if self.enabled:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except Exception:
+                self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop.set()
-        self.th.join(timeout=6)
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=6)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        if not out.strip():  # nothing came through the pipe: one query now, right behind the timed region
+            try:
+                q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                    "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout
+            except Exception:
+                out = ""
+        self.rows = [[c.strip() for c in line.split(",")] for line in out.splitlines() if line.strip()]
 
     def summary(self):
         sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
@@ -304,7 +315,7 @@ def main():
 
     # ---- warm-up, then EXACTLY K timed steps with device-resident inputs --------------------------------------------------
     # the clock sampler runs from the warm-up on (same load), so that short timed regions still collect several samples
-    with ClockSampler(devices[0]) as clk:
+    with ClockSampler(devices[0], enabled=(rank == 0)) as clk:
         for _ in range(max(args.warmup, 3)):
             ctx.gicp_align_batch(dev_src, dev_tgt, None, p)
         ev_ms, wall_ms, cnt, last = timed(dev_src, dev_tgt, args.steps)
