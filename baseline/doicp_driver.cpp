@@ -112,7 +112,14 @@ int main(int argc, char** argv) {
   std::vector<PointCloud::Ptr> clouds;
   for (int i = 1; i <= 4; ++i) clouds.push_back(load_bin(std::string(argv[1]) + "/cloud" + std::to_string(i) + ".bin"));
   std::ostringstream js;
-  js << std::setprecision(17) << "{\n  \"pcl_version\": \"" << PCL_VERSION_PRETTY << "\",\n  \"clouds\": [";
+  // GICP's inner optimiser: BFGS (pcl/registration/bfgs.h) up to 1.13, Newton from 1.14 on (useBFGS() switches back); the tests
+  // put the oracle into the same mode before they compare (oracle.set_gicp_optimizer)
+#if PCL_VERSION_COMPARE(>=, 1, 14, 0)
+  const char* inner_optimizer = "newton";
+#else
+  const char* inner_optimizer = "bfgs";
+#endif
+  js << std::setprecision(17) << "{\n  \"pcl_version\": \"" << PCL_VERSION_PRETTY << "\",\n  \"inner_optimizer\": \"" << inner_optimizer << "\",\n  \"clouds\": [";
   for (size_t i = 0; i < clouds.size(); ++i) js << (i ? ", " : "") << clouds[i]->size();
   js << "],\n  \"voxel\": {";
   // (a) VoxelGrid: number of output points and a hash of the output cloud (x, y, z floats in output order) per leaf size

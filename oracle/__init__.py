@@ -18,7 +18,7 @@ _lib = None
 
 
 def build(force=False):
-    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("s3d_oracle.cpp", "ndt_oracle.inc"))
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("s3d_oracle.cpp", "ndt_oracle.inc", "bfgs_oracle.inc"))
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < newest:
         subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -46,7 +46,7 @@ def use_native():
     out = os.path.join(_NATIVE_DIR, "libs3d_oracle_native.so")
     try:
         os.makedirs(_NATIVE_DIR, exist_ok=True)
-        newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("s3d_oracle.cpp", "ndt_oracle.inc"))
+        newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("s3d_oracle.cpp", "ndt_oracle.inc", "bfgs_oracle.inc"))
         if not os.path.exists(out) or os.path.getmtime(out) < newest:
             subprocess.check_call(["/usr/bin/g++", "-O3", "-march=native", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-pthread",
                                    "-shared", "-o", out, src], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -124,6 +124,25 @@ def nearest_neighbors(reference, queries, transform=None):
     if st != 0:
         raise RuntimeError("nearest_neighbors failed")
     return idx, d2
+
+
+def set_gicp_optimizer(which):
+    """Inner optimiser of gicp_align: "newton" (PCL >= 1.14 default, what the CUDA path mirrors; default) or "bfgs" (PCL <= 1.13 and
+    `useBFGS()`: pcl/registration/bfgs.h, bfgs_oracle.inc).  Process-wide; returns the previous setting."""
+    names = {"newton": 0, "bfgs": 1}
+    old = lib().s3d_oracle_set_gicp_optimizer(names[which])
+    return "bfgs" if old == 1 else "newton"
+
+
+def test_bfgs(pts_moved, pts_fixed, mahal, T, max_inner=20):
+    """estimateRigidTransformationBFGS on explicit correspondences (test hook). T: 4x4 float start; returns (T_out, inner, status)."""
+    a = np.ascontiguousarray(pts_moved, np.float32); b = np.ascontiguousarray(pts_fixed, np.float32)
+    M = np.ascontiguousarray(mahal, np.float64)
+    Tm = np.ascontiguousarray(np.asarray(T, np.float32).T)
+    done = C.c_int(0)
+    st = lib().s3d_oracle_test_bfgs(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), M.ctypes.data_as(C.c_void_p), a.shape[0],
+                                    Tm.ctypes.data_as(C.c_void_p), max_inner, C.byref(done))
+    return Tm.T.copy(), done.value, st
 
 
 def _guess_ptr(guess):

@@ -580,6 +580,11 @@ static bool gicp_newton(const GicpProblem& P, M4f& T, int max_inner, int* inner_
   return true;
 }
 
+#include "bfgs_oracle.inc"  // PCL <= 1.13's inner optimiser (and useBFGS() later)
+
+// which inner optimiser gicp_register uses: 0 = Newton (PCL >= 1.14 default; what the CUDA path mirrors), 1 = BFGS
+static int g_gicp_optimizer = 0;
+
 struct GicpOutput { M4f final_T; bool converged; int outer_iterations; int inner_iterations; uint32_t n_corr; double fitness; };
 
 // Registration::align + GICP::computeTransformation + getFitnessScore, as driven by doICP (:52-82).
@@ -630,7 +635,9 @@ static bool gicp_register(const std::vector<P4>& pcl_source, const std::vector<P
     }
     out.n_corr = static_cast<uint32_t>(P.src_idx.size());
     prev = T;
-    if (!gicp_newton(P, T, cfg.maximum_optimizer_iterations, &out.inner_iterations)) break;  // exception path: converged stays false
+    const bool solved = g_gicp_optimizer == 1 ? gicp_bfgs(P, T, cfg.maximum_optimizer_iterations, &out.inner_iterations)
+                                              : gicp_newton(P, T, cfg.maximum_optimizer_iterations, &out.inner_iterations);
+    if (!solved) break;  // exception path: converged stays false
     double delta = 0;
     for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) {
       const double ratio = (r < 3 && c < 3) ? 1.0 / cfg.rotation_epsilon : 1.0 / cfg.transformation_epsilon;
@@ -932,6 +939,33 @@ int s3d_oracle_test_objective(const float* pts_moved, const float* pts_fixed, co
     for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) H[c * 6 + r] = HH[r][c];
   }
   return S3D_OK;
+}
+
+// 0 = Newton (default), 1 = BFGS; process-wide (test infrastructure).  Returns the previous setting.
+int s3d_oracle_set_gicp_optimizer(int which) {
+  const int old = g_gicp_optimizer;
+  g_gicp_optimizer = which == 1 ? 1 : 0;
+  return old;
+}
+
+// Test hook: estimateRigidTransformationBFGS on explicit correspondences. T: column-major float 4x4 in/out.
+int s3d_oracle_test_bfgs(const float* pts_moved, const float* pts_fixed, const double* mahal, int m, float T[16], int max_inner, int* inner_done) {
+  std::vector<P4> a(reinterpret_cast<const P4*>(pts_moved), reinterpret_cast<const P4*>(pts_moved) + m);
+  std::vector<P4> b(reinterpret_cast<const P4*>(pts_fixed), reinterpret_cast<const P4*>(pts_fixed) + m);
+  GicpProblem P;
+  P.moved = &a; P.fixed = &b;
+  P.mahalanobis.resize(m);
+  for (int i = 0; i < m; ++i) {
+    P.src_idx.push_back(i); P.tgt_idx.push_back(i);
+    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) P.mahalanobis[i].a[r][c] = mahal[i * 9 + c * 3 + r];
+  }
+  M4f Tm;
+  std::memcpy(Tm.m, T, sizeof Tm.m);
+  int done = 0;
+  const bool ok = gicp_bfgs(P, Tm, max_inner, &done);
+  std::memcpy(T, Tm.m, sizeof Tm.m);
+  if (inner_done) *inner_done = done;
+  return ok ? S3D_OK : S3D_NOT_CONVERGED;
 }
 
 // Test hook: estimateRigidTransformationNewton on explicit correspondences. T: column-major float 4x4 in/out.
