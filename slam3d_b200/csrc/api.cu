@@ -572,6 +572,7 @@ static void prepare_chunk(s3d_context* ctx, int device_slot, const s3d_cloud* cl
     ws.d2h += sizeof(SlotInfo) * n + 16;
     ws.collect_spans();
     check_arena(ws, hf);
+    ws.learn_grid_frac(hs, (uint32_t)n);
   });
   auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
   std::vector<std::unique_ptr<s3d_prepared_cloud>> hh(n);

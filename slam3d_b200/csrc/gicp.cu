@@ -919,7 +919,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   S3D_CUDA(cudaMemsetAsync(ctl, 0, 64, st));
   // launch grid: the tiles the filtered clouds are expected to have (the kernels stride over what a short grid leaves), in steps
   // of 16 tiles so that the cached graphs stay few
-  const uint32_t grid_tiles = std::min<uint32_t>(tiles_per_pair, ((uint32_t)ceilf(tiles_per_pair * ws.grid_frac) + 15u) & ~15u);
+  const uint32_t grid_tiles = std::min<uint32_t>(tiles_per_pair, (ws.grid_x(tiles_per_pair, np, 4) + 15u) & ~15u);
   dim3 grid(std::max<uint32_t>(1, grid_tiles), np);
   {
     StageTimer timer(ws, kStageSolve);
@@ -975,12 +975,7 @@ void run_gicp(Workspace& ws, const std::vector<s3d_registration_parameters>& par
   ws.sync();
   ws.d2h += sizeof(PairState) * np + sizeof(SlotInfo) * ws.n_slots + 32;
   ws.passes += h_ctl[0]; ws.ctrl_steps += h_ctl[1];
-  if (ws.n_tiles > 0) {  // raw-cloud batch: remember how much of the raw clouds survived the voxel filter (sizes the next batch's grids)
-    float frac = 0.f;
-    for (uint32_t s = 0; s < ws.n_slots; ++s)
-      if (hs[s].n_raw > 0) frac = std::max(frac, (float)hs[s].n_pts / (float)hs[s].n_raw);
-    ws.learned_frac = std::min(1.f, frac * 1.08f + 1.f / 64.f);
-  }
+  if (ws.n_tiles > 0) ws.learn_grid_frac(hs, ws.n_slots);  // raw-cloud batch: how much of the raw clouds survived the voxel filter sizes the next batch's grids
   if (getenv("S3D_LOOP_STATS") && !throughput)
     fprintf(stderr, "[s3d loop] pairs %u tiles %u control steps %u | per control step %.1f us | CTA-time in search tiles %.0f us, trial tiles %.0f us, fitness tiles %.0f us\n",
             np, h_ctl[0], h_ctl[1], h_ctl[1] ? 1e-3 * h_ctl[7] / h_ctl[1] : 0.0, 1e-3 * h_ctl[4], 1e-3 * h_ctl[5], 1e-3 * h_ctl[6]);

@@ -3,6 +3,8 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <map>
 #include <mutex>
@@ -135,8 +137,25 @@ struct Workspace {
   // (36 % of the points for a 0.1 m leaf on a 64-beam scan): two thirds of the CTAs of every kNN / search / trial / fitness launch
   // found nothing to do.  Those kernels now stride over their tiles, so ANY grid is correct, and the grid is sized with the
   // filtered / raw ratio the previous batch on this workspace showed (1 until one has run; S3D_GRID_FRAC pins it for A/B runs).
-  float learned_frac = 1.f;                   // what the last raw-cloud batch showed (+ margin)
+  // The ratio depends on the leaf size, so it is remembered per leaf (a loop-closure call alternates 0.5 m and 0.1 m passes).
+  std::map<float, float> learned_frac;        // leaf size -> what the last raw-cloud batch with that leaf showed (+ margin)
+  float batch_leaf = 0.f;                     // leaf size of the current batch (set by run_voxel)
   float grid_frac = 1.f;                      // what the current batch uses (1 for prepared clouds: their sizes are exact)
+  // after a batch: `hs` = the slot table read back from the device
+  void learn_grid_frac(const SlotInfo* hs, uint32_t ns) {
+    if (!(batch_leaf > 0.f)) return;
+    float frac = 0.f;
+    for (uint32_t s = 0; s < ns; ++s)
+      if (hs[s].n_raw > 0) frac = std::max(frac, (float)hs[s].n_pts / (float)hs[s].n_raw);
+    if (frac > 0.f) learned_frac[batch_leaf] = std::min(1.f, frac * 1.08f + 1.f / 64.f);
+  }
+  // grid.x for a launch of `units` work items per cloud / pair over `rows` clouds / pairs: the estimate, but never so small that the
+  // launch could not fill the GPU (`per_sm` CTAs per SM) when the bound allows it
+  uint32_t grid_x(uint32_t units, uint32_t rows, uint32_t per_sm) const {
+    const uint32_t est = (uint32_t)ceilf(units * grid_frac);
+    const uint32_t fill = (uint32_t)((size_t(n_sms) * per_sm + rows - 1) / (rows ? rows : 1));
+    return std::max<uint32_t>(1, std::min<uint32_t>(units, std::max(est, fill)));
+  }
   uint32_t sort_epoch = 0;                    // bumped once per sort pass: tags the status words, so that they are never cleared
   size_t status_words = 0;
   DevBuf long_runs;                           // uint4[total/64]  voxels with more than 64 points: (slot, first sorted position, output rank)

@@ -159,7 +159,7 @@ void run_knn_covariances(Workspace& ws, int k, uint32_t* knn_index, float* knn_d
   for (uint32_t s = 0; s < ws.n_slots; ++s) max_n = std::max(max_n, ws.h_n[s]);
   StageTimer timer(ws, kStageKnn);
   const uint32_t chunks = (max_n + kKnnThreads - 1) / kKnnThreads;
-  dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>(chunks, (uint32_t)ceilf(chunks * ws.grid_frac))), ws.n_slots);
+  dim3 grid(ws.grid_x(chunks, ws.n_slots, S3D_KNN_MINBLOCKS), ws.n_slots);
   const size_t heap_bytes = sizeof(uint64_t) * k * kKnnThreads;
   if (k <= kMaxKShared) {
     if (heap_bytes > 48 * 1024) S3D_CUDA(cudaFuncSetAttribute(knn_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heap_bytes));

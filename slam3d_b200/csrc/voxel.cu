@@ -165,10 +165,7 @@ void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const s
   S3D_CUDA(cudaSetDevice(ws.device));
   const uint32_t ns = static_cast<uint32_t>(clouds.size());
   ws.n_slots = ns; ws.n_pairs = n_pairs;
-  {
-    static const float pinned = [] { const char* e = getenv("S3D_GRID_FRAC"); return e ? (float)atof(e) : 0.f; }();
-    ws.grid_frac = pinned > 0.f ? std::min(1.f, pinned) : ws.learned_frac;
-  }
+  ws.grid_frac = 1.f; ws.batch_leaf = 0.f;  // until run_voxel knows the leaf size
   ws.h_off.resize(ns); ws.h_n.resize(ns);
   uint64_t total = 0; uint32_t n_tiles = 0;
   for (uint32_t s = 0; s < ns; ++s) {
@@ -178,6 +175,8 @@ void setup_batch(Workspace& ws, const std::vector<const float*>& clouds, const s
     n_tiles += static_cast<uint32_t>((sizes[s] + kSortTile - 1) / kSortTile);
   }
   if (total >= (1ull << 31)) throw CudaError{"batch too large: more than 2^31 points"};
+  for (uint32_t s = 0; s < ns; ++s)
+    if (sizes[s] >= (1ull << 30)) throw CudaError{"cloud too large: 2^30 points or more (the sort's look-back words count 30 bits)"};
   ws.total = static_cast<uint32_t>(total); ws.n_tiles = n_tiles;
   const size_t tot = std::max<size_t>(total, 4);
   ws.slots.reserve(sizeof(SlotInfo) * ns);
@@ -584,6 +583,12 @@ void run_voxel(Workspace& ws, float leaf, uint32_t* leaf_keys) {
     return;
   }
   cudaStream_t st = ws.stream;
+  {  // how much of a raw cloud the last batch with this leaf size kept: sizes the grids of the kernels behind the filter (internal.h)
+    static const float pinned = [] { const char* e = getenv("S3D_GRID_FRAC"); return e ? (float)atof(e) : 0.f; }();
+    ws.batch_leaf = leaf > 0.f ? leaf : 0.f;
+    const auto it = ws.learned_frac.find(ws.batch_leaf);
+    ws.grid_frac = pinned > 0.f ? std::min(1.f, pinned) : (leaf > 0.f && it != ws.learned_frac.end() ? it->second : 1.f);
+  }
   StageTimer timer(ws, kStageVoxel);
   SlotInfo* slots = ws.slots.as<SlotInfo>();
   TileMap tm{ws.tile_slot.as<uint32_t>(), ws.tile_first.as<uint32_t>(), ws.n_tiles};
