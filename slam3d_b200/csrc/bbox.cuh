@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(kSortThreads) bbox_kernel(SlotInfo* __restrict
     for (int j = 0; j < kSortTile / kSortThreads; ++j) {
       const uint32_t e = first + j * kSortThreads + threadIdx.x;
       if (e < n) {
-        const float4 v = p[e];
+        const float4 v = __ldg(p + e);  // pointer from the slot table: a plain load would be a generic LD
         if (finite3(v.x, v.y, v.z)) {
           ++cnt;
           mn[0] = fminf(mn[0], v.x); mn[1] = fminf(mn[1], v.y); mn[2] = fminf(mn[2], v.z);

@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kSortThreads) voxel_keys_kernel(const SlotInfo
   for (int j = 0; j < kSortTile / kSortThreads; ++j) {
     const uint32_t e = first + j * kSortThreads + threadIdx.x;
     if (e < si.n_raw) {
-      const float4 v = si.raw[e];
+      const float4 v = __ldg(si.raw + e);  // the pointer comes out of the slot table: without __ldg the load is a generic LD
       uint32_t key = kInvalidKey;
       if (finite3(v.x, v.y, v.z)) {
         const int i0 = (int)__fsub_rn(floorf(__fmul_rn(v.x, inv)), mb0);
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kSortThreads) voxel_centroid_kernel(SlotInfo* 
 #pragma unroll
     for (int j = 0; j < kSortTile / kSortThreads; ++j) {
       const uint32_t e = first + j * kSortThreads + threadIdx.x;
-      if (e < si.n_raw) work[si.off + e] = si.raw[e];
+      if (e < si.n_raw) work[si.off + e] = __ldg(si.raw + e);
     }
     return;
   }
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(kSortThreads) voxel_centroid_kernel(SlotInfo* 
   for (int j = 0; j < kSortTile / kSortThreads; ++j) {
     const uint32_t i = j * kSortThreads + threadIdx.x;
     if (i < live) {
-      const float4 p = raw[v[first + i]];
+      const float4 p = __ldg(raw + v[first + i]);
       sk[i] = k[first + i]; sx[i] = p.x; sy[i] = p.y; sz[i] = p.z;
     }
   }
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(kSortThreads) voxel_centroid_kernel(SlotInfo* 
     uint32_t g = first + l;
     if (l == live) {  // the run may continue in the next tile(s)
       while (g < n && k[g] == kk) {
-        const float4 p = raw[v[g]];
+        const float4 p = __ldg(raw + v[g]);
         ax = __fadd_rn(ax, p.x); ay = __fadd_rn(ay, p.y); az = __fadd_rn(az, p.z);
         ++g;
       }
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(256, 2) voxel_long_centroid_kernel(const SlotI
       const uint32_t ke = e < n ? k[e] : ~kk, ve = e < n ? v[e] : 0u;
       nk[d] = e2 < n ? k[e2] : ~kk; nv[d] = e2 < n ? v[e2] : 0u;
       in[d] = ke == kk;
-      buf[d] = in[d] ? raw[ve] : zero;
+      buf[d] = in[d] ? __ldg(raw + ve) : zero;
     }
     uint32_t len = 0;
     int stage = 0;
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(256, 2) voxel_long_centroid_kernel(const SlotI
         const float4 p = buf[d];
         const int take = __popc(__ballot_sync(FULL, in[d]));
         in[d] = nk[d] == kk;                                         // the batch kDepth ahead: its index is here already
-        buf[d] = in[d] ? raw[nv[d]] : zero;
+        buf[d] = in[d] ? __ldg(raw + nv[d]) : zero;
         const uint32_t e2 = b + (d + 2 * kDepth) * 32 + lane;      // and the index of the batch 2 x kDepth ahead
         nk[d] = e2 < n ? k[e2] : ~kk; nv[d] = e2 < n ? v[e2] : 0u;
         if (more) {
