@@ -91,10 +91,17 @@ typedef struct s3d_context s3d_context;
 /* Library / device bring-up.  `devices` = CUDA ordinals to shard batches over (NULL/0: current device).
  * Scheduling knobs, read from the environment when the context is created (measurement aids; results never depend on them,
  * tests/test_gpu_gicp.py::test_batch_scheduling_is_invisible):
- *   S3D_STREAMS_PER_DEVICE   host threads / streams that push chunks of a batch call through one device (default: 6 for GICP
+ *   S3D_STREAMS_PER_DEVICE   host threads / streams that push chunks of a batch call through one device (default: 4 for GICP
  *                            on raw scans, 3 for prepared clouds and NDT)
  *   S3D_MAX_PAIRS_PER_LAUNCH upper bound of a chunk (default 32 pairs)
- *   S3D_GATE_UPLOADS=0       lets the chunks of a device upload concurrently instead of one after the other */
+ *   S3D_GATE_UPLOADS=0       lets the chunks of a device upload concurrently instead of one after the other
+ *   S3D_BLOCKING_SYNC=0      chunk threads spin on their stream instead of sleeping on a blocking event
+ *   S3D_PINNED_BOUNCE=0      pageable clouds go straight to cudaMemcpyAsync instead of through the library's pinned buffer;
+ *   S3D_COPY_THREADS=n       helper threads for that staging copy (default: half of the rank's cores, at most 8)
+ *   S3D_LOOP_MODE=1|2|3      GICP loop as one persistent kernel / as a graph replay of per-pass kernels / launched from the host
+ *                            (default: persistent for single calls, graph replay for the chunks of a batch)
+ *   S3D_GRID_FRAC=f          pins the filtered / raw ratio the launch grids are sized with (default: learned per leaf size)
+ *   S3D_WATCHDOG_MCYCLES=n   cycles (millions) after which a loop kernel that finds no work reports an internal error */
 int s3d_create_context(const int* devices, int n_devices, s3d_context** out);
 int s3d_destroy_context(s3d_context* ctx);
 
