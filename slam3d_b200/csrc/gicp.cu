@@ -796,7 +796,7 @@ static int loop_grid(const Workspace& ws) {
 
 // Throughput mode: WHILE (a pair iterates) { search, control, trial, control, trial, control, condition } as a CUDA graph with a
 // conditional node.  The kernels read everything from the GicpArgs block at a fixed device address; only the grid dimensions
-// depend on the batch, so executable graphs are cached per workspace by (tiles per pair, pairs).
+// depend on the batch, so executable graphs are cached per workspace by (grid tiles, tiles per pair, pairs).
 static cudaGraphExec_t loop_graph_for(Workspace& ws, const GicpArgs& args, uint32_t tiles_per_pair, uint32_t grid_tiles, uint32_t np) {
   // the graphs hold the argument block by value: when a buffer has moved (the batch grew), the cached graphs are stale
   uint64_t sig = 1469598103934665603ull;
@@ -806,7 +806,8 @@ static cudaGraphExec_t loop_graph_for(Workspace& ws, const GicpArgs& args, uint3
     const unsigned char* b = reinterpret_cast<const unsigned char*>(&key_args);
     for (size_t i = 0; i < sizeof key_args; ++i) { sig ^= b[i]; sig *= 1099511628211ull; }
   }
-  if (sig != ws.loop_graph_sig) {
+  // ... and a service that sees many batch shapes must not collect executable graphs without bound
+  if (sig != ws.loop_graph_sig || ws.loop_graphs.size() >= 64) {
     for (auto& g : ws.loop_graphs) cudaGraphExecDestroy(g.second);
     for (cudaGraph_t g : ws.loop_graph_defs) cudaGraphDestroy(g);
     ws.loop_graphs.clear(); ws.loop_graph_defs.clear();
